@@ -1,0 +1,91 @@
+"""ctypes mirror of include/ccc_b200.h (plain-data interface structs only)."""
+import ctypes as C
+
+import numpy as np
+
+CCC_MEM_HOST = 0
+CCC_MEM_DEVICE = 1
+CCC_DDP_M_MAX = 32
+CCC_DDP_MAX_ALPHA = 16
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int8_p = C.POINTER(C.c_int8)
+c_uint32_p = C.POINTER(C.c_uint32)
+
+
+class DdpConfig(C.Structure):
+    """ccc_ddp_config_t"""
+
+    _fields_ = [
+        ("with_input_constraint", C.c_int32),
+        ("max_iter", C.c_int32),
+        ("reg_type", C.c_int32),
+        ("n_alpha", C.c_int32),
+        ("initial_lambda", C.c_double),
+        ("initial_dlambda", C.c_double),
+        ("lambda_factor", C.c_double),
+        ("lambda_min", C.c_double),
+        ("lambda_max", C.c_double),
+        ("k_rel_norm_thre", C.c_double),
+        ("lambda_thre", C.c_double),
+        ("cost_update_ratio_thre", C.c_double),
+        ("cost_update_thre", C.c_double),
+        ("alpha", C.c_double * CCC_DDP_MAX_ALPHA),
+        ("boxqp_max_iter", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("boxqp_grad_thre", C.c_double),
+        ("boxqp_rel_improve_thre", C.c_double),
+        ("boxqp_step_factor", C.c_double),
+        ("boxqp_min_step", C.c_double),
+        ("boxqp_armijo", C.c_double),
+    ]
+
+
+class DdpResult(C.Structure):
+    """ccc_ddp_result_t"""
+
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("u", C.c_void_p),
+        ("cost", C.c_void_p),
+        ("iters", C.c_void_p),
+        ("status", C.c_void_p),
+        ("trace_len", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("alpha_idx", C.c_void_p),
+        ("lambda_trace", C.c_void_p),
+        ("clamped", C.c_void_p),
+    ]
+
+
+class DdpCentroidalBatch(C.Structure):
+    """ccc_ddp_centroidal_batch_t"""
+
+    _fields_ = [
+        ("horizon_steps", C.c_int32),
+        ("batch", C.c_int32),
+        ("n_sched", C.c_int32),
+        ("m_max", C.c_int32),
+        ("dt", C.c_double),
+        ("mass", C.c_double),
+        ("sched_id", C.c_void_p),
+        ("m", C.c_void_p),
+        ("ridge", C.c_void_p),
+        ("vertex", C.c_void_p),
+        ("ref_pos", C.c_void_p),
+        ("w_run", C.c_double * 10),
+        ("w_term", C.c_double * 9),
+        ("u_lo", C.c_double),
+        ("u_hi", C.c_double),
+        ("x0", C.c_void_p),
+        ("u_init", C.c_void_p),
+    ]
+
+
+def ptr(a):
+    """Address of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"], "need a C-contiguous numpy array"
+    return a.ctypes.data

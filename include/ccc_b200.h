@@ -1,0 +1,146 @@
+/* ccc_b200.h — C ABI of the B200-native batched centroidal-MPC solve engine.
+ *
+ * This is the drop-in boundary.  The reference
+ * (isri-aist/CentroidalControlCollection) has no FFI: its boundary is the C++
+ * `CCC::<Method>::planOnce()` member functions of libCCC.so.  Every entry point below
+ * replaces the arithmetic that one of those member functions triggers, with a batch
+ * axis of independent problem instances added.  The C++ classes of the same names in
+ * `centroidalcontrolcollection_b200/include/CCC/` sample the user's callbacks on the host
+ * into the flat stage tables declared here and call these functions.
+ *
+ * Conventions
+ *  - all arrays are row-major, `double` unless stated, batch index outermost;
+ *  - the caller owns every buffer; the library allocates only inside *_create();
+ *  - `CCC_MEM_HOST`: pointers are host memory, the call copies H2D/D2H itself and is
+ *    synchronous; `CCC_MEM_DEVICE`: pointers are device memory on the current CUDA
+ *    device, the call only enqueues work on `stream` (a cudaStream_t passed as void*);
+ *  - return value: 0 = ok, <0 = CCC_ERR_*; never throws; per-problem solver outcome
+ *    is reported in `status[]`, mirroring nmpc_ddp's procOnce return codes;
+ *  - there is NO CPU fallback: with no CUDA device every solve returns CCC_ERR_CUDA.
+ */
+#ifndef CCC_B200_H
+#define CCC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCC_B200_ABI_VERSION 1
+
+enum {
+  CCC_OK = 0,
+  CCC_ERR_INVALID = -1, /* bad argument (size mismatch, null pointer, m > m_max ...) */
+  CCC_ERR_CUDA = -2,    /* CUDA runtime error / no device; see ccc_last_error() */
+  CCC_ERR_ALLOC = -3    /* workspace too small for this batch */
+};
+
+enum { CCC_MEM_HOST = 0, CCC_MEM_DEVICE = 1 };
+
+/* Largest per-stage input dimension the DDP kernels hold in one warp (one ridge per lane). */
+#define CCC_DDP_M_MAX 32
+#define CCC_DDP_MAX_ALPHA 16
+
+/* ---- nmpc_ddp::DDPSolver<>::Configuration + nmpc_ddp::BoxQP<>::Configuration ------------
+ * Replaces: ddp_solver_->config() as set at reference src/DdpCentroidal.cpp:197-201,
+ * src/DdpSingleRigidBody.cpp:267-271, include/CCC/DdpZmp.h:279-281 and
+ * tests/src/TestDdpCentroidal.cpp:116 (max_iter).  Defaults: ccc_ddp_config_default(). */
+typedef struct
+{
+  int32_t with_input_constraint; /* 1: BoxQP per stage (Centroidal, SRB); 0: plain LLT (Zmp) */
+  int32_t max_iter;              /* DDP iterations (procOnce calls) */
+  int32_t reg_type;              /* only 1 (Quu + lambda I) is implemented */
+  int32_t n_alpha;               /* entries of alpha[] used by the line search */
+  double initial_lambda, initial_dlambda, lambda_factor, lambda_min, lambda_max;
+  double k_rel_norm_thre, lambda_thre;
+  double cost_update_ratio_thre, cost_update_thre;
+  double alpha[CCC_DDP_MAX_ALPHA]; /* 10^linspace(0,-3,11), evaluated on the host */
+  int32_t boxqp_max_iter;
+  int32_t reserved0;
+  double boxqp_grad_thre, boxqp_rel_improve_thre, boxqp_step_factor, boxqp_min_step, boxqp_armijo;
+} ccc_ddp_config_t;
+
+/* Fill `cfg` with nmpc_ddp's defaults. */
+void ccc_ddp_config_default(ccc_ddp_config_t * cfg);
+
+/* ---- per-problem outputs of a DDP solve ---------------------------------------------------
+ * Replaces: ddp_solver_->controlData().{x_list,u_list,cost_list} and
+ * ddp_solver_->traceDataList() (reference src/DdpCentroidal.cpp:236,
+ * tests/src/TestDdpCentroidal.cpp:102,129).  Any pointer may be NULL = not wanted. */
+typedef struct
+{
+  double * x;      /* [B][N+1][nx]   optimal state trajectory */
+  double * u;      /* [B][N][m_max]  optimal inputs, entries j >= m_k are 0 */
+  double * cost;   /* [B]            sum of the accepted trajectory's cost_list */
+  int32_t * iters; /* [B]            traceDataList().back().iter */
+  int32_t * status; /* [B]           last procOnce return: 1 converged, 0 max_iter hit, -1 lambda > lambda_max */
+  /* parity trace (optional) */
+  int32_t trace_len;   /* slots per problem in alpha_idx[] / lambda_trace[] */
+  int32_t reserved0;
+  int8_t * alpha_idx;  /* [B][trace_len] accepted alpha index of iteration i+1; -1 = line search
+                          failed; -2 = terminated on small gradient before the line search;
+                          -3 = backward pass gave up (lambda_max); -4 = slot not reached */
+  double * lambda_trace; /* [B][trace_len] lambda after iteration i+1 */
+  uint32_t * clamped;  /* [B][N] bit j set = input j clamped by BoxQP in the last completed backward pass */
+} ccc_ddp_result_t;
+
+/* ---- CCC::DdpCentroidal ---------------------------------------------------------------------
+ * Flat form of what DdpCentroidal::planOnce (reference src/DdpCentroidal.cpp:213-237) reads
+ * through its two std::function callbacks, sampled at t_k = current_time + k*dt:
+ *  MotionParam.contact_list -> m / ridge / vertex tables (order of
+ *    src/DdpCentroidal.cpp:49-60: contact, vertex, ridge);
+ *  RefData.pos              -> ref_pos (k = 0..N; the N-th entry feeds terminalCost).
+ * `n_sched` distinct schedules are shared by the batch; problem b uses sched_id[b]. */
+typedef struct
+{
+  int32_t horizon_steps; /* N */
+  int32_t batch;         /* B */
+  int32_t n_sched;       /* S */
+  int32_t m_max;         /* row stride of ridge/vertex/u tables, <= CCC_DDP_M_MAX */
+  double dt;             /* horizon_dt [s] */
+  double mass;           /* [kg] */
+  const int32_t * sched_id; /* [B] */
+  const int32_t * m;        /* [S][N]   input dimension of each stage (0 = flight) */
+  const double * ridge;     /* [S][N][m_max][3] friction-pyramid ridge of input j */
+  const double * vertex;    /* [S][N][m_max][3] contact vertex input j acts on */
+  const double * ref_pos;   /* [S][N+1][3] */
+  double w_run[10];  /* WeightParam: running_pos(3), running_linear_momentum(3), running_angular_momentum(3), running_force */
+  double w_term[9];  /* terminal_pos(3), terminal_linear_momentum(3), terminal_angular_momentum(3) */
+  double u_lo, u_hi; /* force_scale_limits_ (reference include/CCC/DdpCentroidal.h:364) */
+  const double * x0;     /* [B][9]  InitialParam::toState: pos, mass*vel, angular_momentum */
+  const double * u_init; /* [B][N][m_max] warm start, or NULL = zeros (src/DdpCentroidal.cpp:221-229) */
+} ccc_ddp_centroidal_batch_t;
+
+typedef struct ccc_ddp_centroidal_ws ccc_ddp_centroidal_ws_t;
+
+/* Allocate the device workspace (gain lists, candidate trajectories, staging buffers) for up
+ * to `max_batch` problems of `horizon_steps` stages and `max_sched` schedules on the current
+ * CUDA device.  Returns NULL on failure (see ccc_last_error()). */
+ccc_ddp_centroidal_ws_t * ccc_ddp_centroidal_create(int32_t horizon_steps, int32_t max_batch, int32_t max_sched);
+void ccc_ddp_centroidal_destroy(ccc_ddp_centroidal_ws_t * ws);
+
+/* Solve `batch->batch` independent DdpCentroidal problems: rollout, then up to
+ * cfg->max_iter iterations of {derivatives, backward pass with BoxQP, line search, lambda
+ * schedule} per problem, one warp per problem.
+ * Replaces: nmpc_ddp::DDPSolver<9,Dynamic>::solve as called at reference
+ * src/DdpCentroidal.cpp:229,233 together with the DdpProblem callbacks at :32-177. */
+int32_t ccc_ddp_centroidal_solve(ccc_ddp_centroidal_ws_t * ws,
+                                 const ccc_ddp_centroidal_batch_t * batch,
+                                 const ccc_ddp_config_t * cfg,
+                                 ccc_ddp_result_t * result,
+                                 int32_t mem,
+                                 void * stream);
+
+/* Number of kernels the last solve on this workspace launched (bench.py's gpu_launches). */
+int32_t ccc_ddp_centroidal_last_launches(const ccc_ddp_centroidal_ws_t * ws);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+int32_t ccc_abi_version(void);
+int32_t ccc_device_count(void);
+const char * ccc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCC_B200_H */

@@ -1,0 +1,224 @@
+// oracle/boxqp.hpp — CPU restatement of nmpc_ddp::BoxQP (projected-Newton box QP).
+//
+// TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED: nmpc_ddp (isri-aist/NMPC, un-versioned
+// dependency, reference CMakeLists.txt:25) is not in /root/reference, so this restates its
+// published algorithm — Tassa, Mansard, Todorov, "Control-limited differential dynamic
+// programming", ICRA 2014, boxQP.m — which nmpc_ddp ports.  It is reached from the reference
+// through ddp_solver_->config().with_input_constraint = true (src/DdpCentroidal.cpp:197,
+// src/DdpSingleRigidBody.cpp:267).
+//
+//   min 0.5 x'Hx + g'x   s.t.  lo <= x <= hi
+//
+// result codes (boxQP.m): -1 Hessian not PD, 0 no descent direction, 1 max iterations,
+// 2 max line-search iterations, 4 small improvement, 5 small gradient, 6 all clamped.
+#pragma once
+#include "num.hpp"
+
+namespace oracle
+{
+struct BoxQpConfig
+{
+  int max_iter = 500;
+  double grad_thre = 1e-8;
+  double rel_improve_thre = 1e-8;
+  double step_factor = 0.6;
+  double min_step = 1e-22;
+  double armijo = 0.1;
+};
+
+/** Cholesky factor of the free block H[free,free] (compact storage, row-major nf x nf). */
+struct FreeLlt
+{
+  int nf = 0;
+  std::vector<int> idx;     // free indices, ascending
+  std::vector<double> L;    // nf*nf, lower
+  std::vector<double> invd; // 1 / L[k][k]
+
+  /** Unblocked left-looking LL^T; returns false if a pivot is not > 0. */
+  bool compute(const double * H, int ld, const std::vector<int> & free_idx)
+  {
+    idx = free_idx;
+    nf = static_cast<int>(idx.size());
+    L.assign(static_cast<size_t>(nf) * nf, 0.0);
+    invd.assign(nf, 0.0);
+    for(int k = 0; k < nf; k++)
+    {
+      double acc = H[idx[k] * ld + idx[k]];
+      for(int j = 0; j < k; j++) acc = std::fma(-L[k * nf + j], L[k * nf + j], acc);
+      if(!(acc > 0.0)) return false;
+      double d = std::sqrt(acc);
+      double inv = 1.0 / d;
+      L[k * nf + k] = d;
+      invd[k] = inv;
+      for(int i = k + 1; i < nf; i++)
+      {
+        double a = H[idx[i] * ld + idx[k]]; // lower triangle of H, like Eigen::LLT<Lower>
+        for(int j = 0; j < k; j++) a = std::fma(-L[i * nf + j], L[k * nf + j], a);
+        L[i * nf + k] = a * inv;
+      }
+    }
+    return true;
+  }
+
+  /** Solve (L L') y = b in place on a compact vector of length nf (stride sb). */
+  void solve(double * b, int sb) const
+  {
+    for(int i = 0; i < nf; i++)
+    {
+      double acc = b[i * sb];
+      for(int j = 0; j < i; j++) acc = std::fma(-L[i * nf + j], b[j * sb], acc);
+      b[i * sb] = acc * invd[i];
+    }
+    for(int i = nf - 1; i >= 0; i--)
+    {
+      double acc = b[i * sb];
+      for(int j = nf - 1; j > i; j--) acc = std::fma(-L[j * nf + i], b[j * sb], acc);
+      b[i * sb] = acc * invd[i];
+    }
+  }
+};
+
+struct BoxQp
+{
+  BoxQpConfig cfg;
+  int retval = 0;
+  int iters = 0;
+  int nfactor = 0;
+  std::vector<double> x;
+  std::vector<uint8_t> clamped;
+  FreeLlt llt; // factor matching `clamped` (valid unless all clamped)
+
+  static double objective(const double * H, int m, const double * g, const double * x, double * Hx)
+  {
+    double xHx[32], xg[32];
+    for(int i = 0; i < m; i++)
+    {
+      Hx[i] = dot_seq(H + i * m, 1, x, 1, m);
+      xHx[i] = x[i] * Hx[i];
+      xg[i] = x[i] * g[i];
+    }
+    return std::fma(0.5, tree_sum32(xHx, m), tree_sum32(xg, m));
+  }
+
+  /** H: m x m row-major.  Returns retval. */
+  int solve(const double * H, const double * g, const double * lo, const double * hi, const double * x0, int m)
+  {
+    x.assign(m, 0.0);
+    clamped.assign(m, 0);
+    std::vector<uint8_t> old_clamped(m, 0);
+    std::vector<double> Hx(m), grad(m), gc(m), search(m), xc(m), Hxc(m), tmp(m);
+    for(int i = 0; i < m; i++) x[i] = clampd(x0[i], lo[i], hi[i]);
+    double obj = objective(H, m, g, x.data(), Hx.data());
+    double old_obj = obj;
+    retval = 0;
+    nfactor = 0;
+    int iter = 1;
+    for(;; iter++)
+    {
+      iters = iter;
+      if(iter > 1 && (old_obj - obj) < cfg.rel_improve_thre * std::fabs(old_obj))
+      {
+        retval = 4;
+        break;
+      }
+      old_obj = obj;
+
+      // gradient (Hx is H*x of the current x)
+      for(int i = 0; i < m; i++) grad[i] = g[i] + Hx[i];
+
+      // clamped dimensions
+      old_clamped = clamped;
+      bool all_clamped = true, changed = false;
+      std::vector<int> free_idx;
+      for(int i = 0; i < m; i++)
+      {
+        clamped[i] = ((x[i] == lo[i] && grad[i] > 0) || (x[i] == hi[i] && grad[i] < 0)) ? 1 : 0;
+        if(!clamped[i])
+        {
+          all_clamped = false;
+          free_idx.push_back(i);
+        }
+        if(clamped[i] != old_clamped[i]) changed = true;
+      }
+      if(all_clamped)
+      {
+        retval = 6;
+        break;
+      }
+
+      // factorize if the clamped set changed
+      if(iter == 1 || changed)
+      {
+        if(!llt.compute(H, m, free_idx))
+        {
+          retval = -1;
+          break;
+        }
+        nfactor++;
+      }
+
+      // gradient norm over the free dimensions
+      for(int i = 0; i < m; i++) tmp[i] = clamped[i] ? 0.0 : grad[i] * grad[i];
+      double gnorm = std::sqrt(tree_sum32(tmp.data(), m));
+      if(gnorm < cfg.grad_thre)
+      {
+        retval = 5;
+        break;
+      }
+
+      // search direction
+      for(int i = 0; i < m; i++) xc[i] = clamped[i] ? x[i] : 0.0;
+      for(int i = 0; i < m; i++) gc[i] = g[i] + dot_seq(H + i * m, 1, xc.data(), 1, m);
+      {
+        int nf = llt.nf;
+        std::vector<double> rhs(nf);
+        for(int a = 0; a < nf; a++) rhs[a] = gc[llt.idx[a]];
+        llt.solve(rhs.data(), 1);
+        for(int i = 0; i < m; i++) search[i] = 0.0;
+        for(int a = 0; a < nf; a++) search[llt.idx[a]] = (-rhs[a]) - x[llt.idx[a]];
+      }
+
+      // descent check
+      for(int i = 0; i < m; i++) tmp[i] = search[i] * grad[i];
+      double sdotg = tree_sum32(tmp.data(), m);
+      if(sdotg >= 0) // should not happen
+      {
+        retval = 0;
+        break;
+      }
+
+      // Armijo line search
+      double step = 1.0;
+      for(int i = 0; i < m; i++) xc[i] = clampd(std::fma(step, search[i], x[i]), lo[i], hi[i]);
+      double objc = objective(H, m, g, xc.data(), Hxc.data());
+      bool ls_fail = false;
+      while((objc - old_obj) / (step * sdotg) < cfg.armijo)
+      {
+        step = step * cfg.step_factor;
+        for(int i = 0; i < m; i++) xc[i] = clampd(std::fma(step, search[i], x[i]), lo[i], hi[i]);
+        objc = objective(H, m, g, xc.data(), Hxc.data());
+        if(step < cfg.min_step)
+        {
+          ls_fail = true;
+          break;
+        }
+      }
+      // accept candidate
+      x = xc;
+      Hx = Hxc;
+      obj = objc;
+      if(ls_fail)
+      {
+        retval = 2;
+        break;
+      }
+      if(iter >= cfg.max_iter)
+      {
+        retval = 1;
+        break;
+      }
+    }
+    return retval;
+  }
+};
+} // namespace oracle

@@ -1,0 +1,214 @@
+// oracle/capi.cpp — C entry points of the CPU oracle (ctypes-loadable).
+//
+// TEST INFRASTRUCTURE ONLY: called from tests/, from bench.py's cpu_baseline and
+// --impl reference legs, and from __graft_entry__.smoke() as the checker.  The product
+// library (libccc_b200.so) never links or loads this file.
+//
+// The batch/config/result structs are the plain-data interface structs of
+// include/ccc_b200.h, so the same buffers can be handed to the oracle and to the engine.
+#include "../include/ccc_b200.h"
+#include "centroidal.hpp"
+
+#include <atomic>
+#include <thread>
+
+using namespace oracle;
+
+namespace
+{
+DdpConfig toConfig(const ccc_ddp_config_t * c)
+{
+  DdpConfig cfg;
+  cfg.with_input_constraint = c->with_input_constraint != 0;
+  cfg.max_iter = c->max_iter;
+  cfg.reg_type = c->reg_type;
+  cfg.initial_lambda = c->initial_lambda;
+  cfg.initial_dlambda = c->initial_dlambda;
+  cfg.lambda_factor = c->lambda_factor;
+  cfg.lambda_min = c->lambda_min;
+  cfg.lambda_max = c->lambda_max;
+  cfg.k_rel_norm_thre = c->k_rel_norm_thre;
+  cfg.lambda_thre = c->lambda_thre;
+  cfg.cost_update_ratio_thre = c->cost_update_ratio_thre;
+  cfg.cost_update_thre = c->cost_update_thre;
+  cfg.alpha_list.assign(c->alpha, c->alpha + c->n_alpha);
+  cfg.boxqp.max_iter = c->boxqp_max_iter;
+  cfg.boxqp.grad_thre = c->boxqp_grad_thre;
+  cfg.boxqp.rel_improve_thre = c->boxqp_rel_improve_thre;
+  cfg.boxqp.step_factor = c->boxqp_step_factor;
+  cfg.boxqp.min_step = c->boxqp_min_step;
+  cfg.boxqp.armijo = c->boxqp_armijo;
+  return cfg;
+}
+
+template<class F>
+void parallelFor(int n, int n_threads, F && f)
+{
+  if(n_threads <= 1)
+  {
+    for(int i = 0; i < n; i++) f(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for(int t = 0; t < n_threads; t++)
+    pool.emplace_back([&]() {
+      for(;;)
+      {
+        int i = next.fetch_add(1);
+        if(i >= n) break;
+        f(i);
+      }
+    });
+  for(auto & th : pool) th.join();
+}
+
+/** Write solver outputs of problem b into the result arrays. */
+void storeResult(const DdpSolver & s, int b, int N, int nx, int m_max, ccc_ddp_result_t * r)
+{
+  if(r->x)
+    for(int k = 0; k <= N; k++)
+      for(int i = 0; i < nx; i++) r->x[(static_cast<size_t>(b) * (N + 1) + k) * nx + i] = s.x[k][i];
+  if(r->u)
+    for(int k = 0; k < N; k++)
+      for(int j = 0; j < m_max; j++)
+        r->u[(static_cast<size_t>(b) * N + k) * m_max + j] = j < static_cast<int>(s.u[k].size()) ? s.u[k][j] : 0.0;
+  if(r->cost) r->cost[b] = DdpSolver::sum_seq(s.cost);
+  if(r->iters) r->iters[b] = s.trace.back().iter;
+  if(r->status) r->status[b] = s.retval;
+  for(int i = 0; i < r->trace_len; i++)
+  {
+    size_t o = static_cast<size_t>(b) * r->trace_len + i;
+    bool have = static_cast<size_t>(i + 1) < s.trace.size();
+    if(r->alpha_idx) r->alpha_idx[o] = have ? static_cast<int8_t>(s.trace[i + 1].alpha_idx) : static_cast<int8_t>(-4);
+    if(r->lambda_trace) r->lambda_trace[o] = have ? s.trace[i + 1].lambda : 0.0;
+  }
+  if(r->clamped)
+    for(int k = 0; k < N; k++) r->clamped[static_cast<size_t>(b) * N + k] = s.clamped_mask[k];
+}
+
+void bindCentroidal(CentroidalProblem & p, const ccc_ddp_centroidal_batch_t * bt, int sched)
+{
+  const int N = bt->horizon_steps, mm = bt->m_max;
+  p.N = N;
+  p.dt = bt->dt;
+  p.mass = bt->mass;
+  p.m_max = mm;
+  p.m_tab = bt->m + static_cast<size_t>(sched) * N;
+  p.ridge = bt->ridge + static_cast<size_t>(sched) * N * mm * 3;
+  p.vertex = bt->vertex + static_cast<size_t>(sched) * N * mm * 3;
+  p.ref_pos = bt->ref_pos + static_cast<size_t>(sched) * (N + 1) * 3;
+  for(int i = 0; i < 10; i++) p.w_run[i] = bt->w_run[i];
+  for(int i = 0; i < 9; i++) p.w_term[i] = bt->w_term[i];
+  p.u_lo = bt->u_lo;
+  p.u_hi = bt->u_hi;
+}
+} // namespace
+
+extern "C" {
+
+/** nmpc_ddp defaults as recalled in SURVEY.md App. A (restated independently of the engine). */
+void ccc_oracle_ddp_config_default(ccc_ddp_config_t * c)
+{
+  DdpConfig d;
+  c->with_input_constraint = 0;
+  c->max_iter = d.max_iter;
+  c->reg_type = d.reg_type;
+  c->n_alpha = static_cast<int32_t>(d.alpha_list.size());
+  c->initial_lambda = d.initial_lambda;
+  c->initial_dlambda = d.initial_dlambda;
+  c->lambda_factor = d.lambda_factor;
+  c->lambda_min = d.lambda_min;
+  c->lambda_max = d.lambda_max;
+  c->k_rel_norm_thre = d.k_rel_norm_thre;
+  c->lambda_thre = d.lambda_thre;
+  c->cost_update_ratio_thre = d.cost_update_ratio_thre;
+  c->cost_update_thre = d.cost_update_thre;
+  for(int i = 0; i < CCC_DDP_MAX_ALPHA; i++) c->alpha[i] = i < c->n_alpha ? d.alpha_list[i] : 0.0;
+  c->boxqp_max_iter = d.boxqp.max_iter;
+  c->reserved0 = 0;
+  c->boxqp_grad_thre = d.boxqp.grad_thre;
+  c->boxqp_rel_improve_thre = d.boxqp.rel_improve_thre;
+  c->boxqp_step_factor = d.boxqp.step_factor;
+  c->boxqp_min_step = d.boxqp.min_step;
+  c->boxqp_armijo = d.boxqp.armijo;
+}
+
+/** Same contract as ccc_ddp_centroidal_solve with host pointers; n_threads host threads. */
+int32_t ccc_oracle_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t * bt,
+                                        const ccc_ddp_config_t * c,
+                                        ccc_ddp_result_t * r,
+                                        int32_t n_threads)
+{
+  if(!bt || !c || !r || bt->m_max > 32 || bt->m_max < 0) return CCC_ERR_INVALID;
+  const int N = bt->horizon_steps, mm = bt->m_max;
+  DdpConfig cfg = toConfig(c);
+  parallelFor(bt->batch, n_threads, [&](int b) {
+    CentroidalProblem p;
+    bindCentroidal(p, bt, bt->sched_id[b]);
+    DdpSolver s(p);
+    s.cfg = cfg;
+    std::vector<std::vector<double>> u0(N);
+    for(int k = 0; k < N; k++)
+    {
+      int m = p.inputDim(k);
+      u0[k].assign(m, 0.0);
+      if(bt->u_init)
+        for(int j = 0; j < m; j++) u0[k][j] = bt->u_init[(static_cast<size_t>(b) * N + k) * mm + j];
+    }
+    s.solve(bt->x0 + static_cast<size_t>(b) * 9, u0);
+    storeResult(s, b, N, 9, mm, r);
+  });
+  return CCC_OK;
+}
+
+/** Evaluate the DdpCentroidal problem functions of stage k of schedule 0 at (x, u): for the
+ *  derivative known-answer tests (reference tests/src/TestDdpCentroidal.cpp:176-284).
+ *  Fx 9x9, Fu 9xm (row-major), Lx 9, Lu m; any output may be NULL. */
+int32_t ccc_oracle_centroidal_eval(const ccc_ddp_centroidal_batch_t * bt,
+                                   int32_t k,
+                                   const double * x,
+                                   const double * u,
+                                   double * xn,
+                                   double * running_cost,
+                                   double * terminal_cost,
+                                   double * Fx,
+                                   double * Fu,
+                                   double * Lx,
+                                   double * Lu,
+                                   double * Vx)
+{
+  CentroidalProblem p;
+  bindCentroidal(p, bt, 0);
+  const int m = p.inputDim(k);
+  if(xn) p.stateEq(k, x, u, xn);
+  if(running_cost) *running_cost = p.runningCost(k, x, u);
+  if(terminal_cost) *terminal_cost = p.terminalCost(x);
+  if(Fx || Fu)
+  {
+    std::vector<double> fx(81), fu(9 * m);
+    p.stateEqDeriv(k, x, u, fx.data(), fu.data());
+    if(Fx) std::copy(fx.begin(), fx.end(), Fx);
+    if(Fu) std::copy(fu.begin(), fu.end(), Fu);
+  }
+  if(Lx || Lu)
+  {
+    std::vector<double> lx(9), lu(m), lxx(81), luu(m * m), lxu(9 * m);
+    p.runningCostDeriv(k, x, u, lx.data(), lu.data(), lxx.data(), luu.data(), lxu.data());
+    if(Lx) std::copy(lx.begin(), lx.end(), Lx);
+    if(Lu) std::copy(lu.begin(), lu.end(), Lu);
+  }
+  if(Vx)
+  {
+    std::vector<double> vxx(81);
+    p.terminalCostDeriv(x, Vx, vxx.data());
+  }
+  return CCC_OK;
+}
+
+int32_t ccc_oracle_hardware_threads(void)
+{
+  return static_cast<int32_t>(std::thread::hardware_concurrency());
+}
+
+} // extern "C"

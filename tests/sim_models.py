@@ -1,0 +1,39 @@
+"""Test plants, restated from reference tests/src/SimModels.h (test fixtures, numpy)."""
+import numpy as np
+
+G = 9.80665
+
+
+class CentroidalSim:
+    """reference tests/src/SimModels.h:233-332: 18-state linear plant, ZOH-discretised.
+
+    state = [c(3), euler(3), v(3), omega(3), P(3), L(3)], input = (force, moment about CoM).
+    A has only the block d(pos)/dt = vel, so A^2 = 0 and the ZOH matrices are exact polynomials
+    (SURVEY.md App. D): Ad = I + A dt, Bd = (I dt + A dt^2/2) B, Ed = (I dt + A dt^2/2) E.
+    """
+
+    def __init__(self, mass, inertia, sim_dt):
+        A = np.zeros((18, 18))
+        A[0:6, 6:12] = np.eye(6)
+        B = np.zeros((18, 6))
+        B[6:9, 0:3] = np.eye(3) / mass
+        B[9:12, 3:6] = np.diag(1.0 / np.asarray(inertia))
+        B[12:18, 0:6] = np.eye(6)
+        E = np.zeros(18)
+        E[8] = -G
+        E[14] = -mass * G
+        M = np.eye(18) * sim_dt + A * (sim_dt**2 / 2)
+        self.Ad, self.Bd, self.Ed = np.eye(18) + A * sim_dt, M @ B, M @ E
+        self.x = np.zeros(18)
+        self.mass = mass
+
+    pos = property(lambda s: s.x[0:3])
+    vel = property(lambda s: s.x[6:9])
+    angular_momentum = property(lambda s: s.x[15:18])
+
+    def update(self, force, moment):
+        self.x = self.Ad @ self.x + self.Bd @ np.concatenate([force, moment]) + self.Ed
+
+    def add_disturb(self, lin_impulse_per_mass, ang_impulse_per_mass):
+        self.x[6:9] += lin_impulse_per_mass
+        self.x[9:12] += ang_impulse_per_mass
