@@ -1,0 +1,739 @@
+// ddp_centroidal_core.cuh — one warp solves one DdpCentroidal problem (9 states, <= 32 ridge
+// force scales per stage, box limits), start to finish.
+//
+// Replaces (reference file:line):
+//   nmpc_ddp::DDPSolver<9,Dynamic>::solve         call sites src/DdpCentroidal.cpp:229,233
+//   DdpCentroidal::DdpProblem::stateEq            src/DdpCentroidal.cpp:32-64
+//   ...::runningCost / terminalCost               src/DdpCentroidal.cpp:66-83
+//   ...::calcStateEqDeriv                         src/DdpCentroidal.cpp:85-121
+//   ...::calcRunningCostDeriv / TerminalCostDeriv src/DdpCentroidal.cpp:123-177
+//   input limits                                  src/DdpCentroidal.cpp:202-210
+// Algorithm and evaluation order: oracle/ddp.hpp, oracle/centroidal.hpp (bit-exact).
+//
+// Work split inside the warp: lane j owns input (ridge) j — its vertex/ridge pair, its
+// column of Fu, row j of Quu (32 FP64 registers), row j of Qux / K / Quu*K.  State-sized
+// objects (Vx, Vxx, Fx, Vxx*Fx, Qxx; 9x9) live in the warp's shared-memory slice and their
+// 81 entries are dealt round-robin to the lanes.  Derivatives Fx/Fu are rebuilt from (x,u)
+// and the stage tables in registers, never stored.  The gain lists k, K spill to HBM in a
+// lane-contiguous layout ([stage][10][32]) so that every access is a 256-byte coalesced row.
+#pragma once
+#include "boxqp_warp.cuh"
+
+namespace ccc
+{
+// plain-data mirror of ccc_ddp_config_t's solver part (kept separate so that this header
+// compiles without the public C header)
+struct DdpCfg
+{
+  int with_input_constraint, max_iter, n_alpha;
+  double initial_lambda, initial_dlambda, lambda_factor, lambda_min, lambda_max;
+  double k_rel_norm_thre, lambda_thre, cost_update_ratio_thre, cost_update_thre;
+  double alpha[16];
+  BoxQpCfg boxqp;
+};
+
+struct CentroidalParams
+{
+  int N, B, S;
+  double dt, mass;
+  const int * sched_id;  // [B]
+  const int * m;         // [S][N]
+  const double * tab;    // [S][N][6][32] packed stage tables: ridge xyz, vertex xyz (lane-contiguous)
+  const double * ref_pos; // [S][N+1][3]
+  double w_run[10], w_term[9];
+  double u_lo, u_hi;
+  const double * x0;     // [B][9]
+  const double * u_init; // [B][N][32] or null
+  DdpCfg cfg;
+  // workspace (device)
+  double * xbuf; // [2][B][N+1][9]  nominal / candidate state trajectories (ping-pong)
+  double * ubuf; // [2][B][N][32]
+  double * gains; // [B][N][10][32]  k (row 0) and the 9 columns of K
+  // outputs (device, nullable)
+  double * out_x;
+  double * out_u;
+  double * out_cost;
+  int * out_iters;
+  int * out_status;
+  int trace_len;
+  signed char * out_alpha_idx;
+  double * out_lambda;
+  unsigned * out_clamped;
+};
+
+// per-warp shared-memory slice, offsets in doubles
+namespace sm
+{
+constexpr int A = 0;                // 32 x kLda tile: upper+diag = Quu_F, strict lower = L
+constexpr int VB0 = A + 32 * kLda;  // three 32-vectors
+constexpr int VB1 = VB0 + 32;
+constexpr int VB2 = VB1 + 32;
+constexpr int VXX = VB2 + 32;       // 9x9 (+1 pad)
+constexpr int VX = VXX + 82;        // 9 (+1)
+constexpr int FX = VX + 10;         // 9x9 dense Fx
+constexpr int T = FX + 82;          // Vxx * Fx
+constexpr int QXX = T + 82;
+constexpr int S2 = QXX + 82;        // scratch 9x9
+constexpr int QX = S2 + 82;
+constexpr int TOTAL = QX + 10;      // 1614 doubles = 12912 bytes
+// aliases inside A, valid while no factor is alive
+constexpr int WT = A;               // [32][6]  rows 3..8 of Vxx*Fu, transposed
+constexpr int KB = A;               // [32][10] K rows
+constexpr int ZB = A + 320;         // [32][10] (Quu K) rows
+constexpr int QB = A + 640;         // [32][10] Qux rows
+} // namespace sm
+
+struct CentroidalWarp
+{
+  const CentroidalParams & P;
+  double * s; // this warp's shared-memory slice
+  int b, sched, lane;
+  int cur; // index of the nominal trajectory buffer (0/1)
+  double lambda, dlambda, dV0, dV1, J;
+  double krel; // running max of |k|/(|u|+1) of the last backward pass (per lane)
+
+  CCC_DEV CentroidalWarp(const CentroidalParams & p, double * smem, int prob)
+  : P(p), s(smem), b(prob), sched(p.sched_id[prob]), lane(lane_id()), cur(0), lambda(0), dlambda(0), dV0(0), dV1(0),
+    J(0), krel(0)
+  {
+  }
+
+  CCC_DEV double * xtraj(int which) const { return P.xbuf + ((size_t)which * P.B + b) * (size_t)(P.N + 1) * 9; }
+  CCC_DEV double * utraj(int which) const { return P.ubuf + ((size_t)which * P.B + b) * (size_t)P.N * 32; }
+  CCC_DEV double * gain(int k) const { return P.gains + ((size_t)b * P.N + k) * 320; }
+  CCC_DEV int stage_m(int k) const { return ldg(P.m + (size_t)sched * P.N + k); }
+  CCC_DEV const double * stage_tab(int k) const { return P.tab + ((size_t)sched * P.N + k) * 192; }
+  CCC_DEV const double * ref(int k) const { return P.ref_pos + ((size_t)sched * (P.N + 1) + k) * 3; }
+
+  /** lanes 0..8 store the (warp-uniform) state vector; no dynamic register indexing. */
+  CCC_DEV void store9(double * dst, const double (&x)[9]) const
+  {
+    CCC_UNROLL
+    for(int i = 0; i < 9; i++)
+      if(lane == i) dst[i] = x[i];
+  }
+
+  // ---- problem functions (src/DdpCentroidal.cpp:32-83) -----------------------------------
+  CCC_DEV static double quad9(const double * w, const double * x, const double * r)
+  {
+    double c = 0.0;
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++)
+    {
+      double d = x[a] - r[a];
+      c = dfma(w[a], d * d, c);
+    }
+    CCC_UNROLL
+    for(int a = 3; a < 9; a++) c = dfma(w[a], x[a] * x[a], c);
+    return c;
+  }
+
+  /** x <- stateEq(x, u); returns runningCost(x, u) of the stage (all lanes hold x; lane j holds u_j). */
+  CCC_DEV double step_and_cost(int k, int m, double (&x)[9], double u)
+  {
+    const bool active = lane < m;
+    const double * tb = stage_tab(k);
+    double rho[3], d[3], cr[3];
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++)
+    {
+      rho[a] = active ? ldg(tb + a * 32 + lane) : 0.0;
+      d[a] = (active ? ldg(tb + (3 + a) * 32 + lane) : 0.0) - x[a];
+    }
+    cross3(d, rho, cr);
+    double f[3], n[3];
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++)
+    {
+      f[a] = warp_sum(active ? u * rho[a] : 0.0);
+      n[a] = warp_sum(active ? u * cr[a] : 0.0);
+    }
+    const double usq = warp_sum(active ? u * u : 0.0);
+    double rr[3];
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++) rr[a] = ldg(ref(k) + a);
+    const double cost = dfma(0.5 * P.w_run[9], usq, 0.5 * quad9(P.w_run, x, rr));
+    double xdot[9];
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++)
+    {
+      xdot[a] = x[3 + a] / P.mass;
+      xdot[3 + a] = f[a];
+      xdot[6 + a] = n[a];
+    }
+    xdot[5] = f[2] + (-1 * P.mass * 9.80665);
+    CCC_UNROLL
+    for(int i = 0; i < 9; i++) x[i] = dfma(P.dt, xdot[i], x[i]);
+    return cost;
+  }
+
+  CCC_DEV double terminal_cost(const double (&x)[9])
+  {
+    double rr[3];
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++) rr[a] = ldg(ref(P.N) + a);
+    return 0.5 * quad9(P.w_term, x, rr);
+  }
+
+  /** Initial rollout (alpha < 0) or line-search forward pass into trajectory buffer `dst`.
+   *  Returns the summed cost of the produced trajectory. */
+  CCC_DEV double rollout(int dst, double alpha, bool initial)
+  {
+    const int N = P.N;
+    double * xd = xtraj(dst);
+    double * ud = utraj(dst);
+    const double * xn = xtraj(cur);
+    const double * un = utraj(cur);
+    double x[9];
+    CCC_UNROLL
+    for(int i = 0; i < 9; i++) x[i] = initial ? ldg(P.x0 + (size_t)b * 9 + i) : xn[i];
+    double Jc = 0.0;
+    for(int k = 0; k < N; k++)
+    {
+      const int m = stage_m(k);
+      const bool active = lane < m;
+      double u;
+      if(initial)
+      {
+        u = (active && P.u_init) ? ldg(P.u_init + ((size_t)b * N + k) * 32 + lane) : 0.0;
+      }
+      else
+      {
+        double dx[9];
+        CCC_UNROLL
+        for(int c = 0; c < 9; c++) dx[c] = x[c] - xn[(size_t)k * 9 + c];
+        const double * g = gain(k);
+        double fb = 0.0;
+        double kj = 0.0, uj = 0.0;
+        if(active)
+        {
+          kj = g[lane];
+          uj = un[(size_t)k * 32 + lane];
+          CCC_UNROLL
+          for(int c = 0; c < 9; c++) fb = dfma(g[(1 + c) * 32 + lane], dx[c], fb);
+        }
+        u = dfma(alpha, kj, uj) + fb;
+        if(P.cfg.with_input_constraint) u = clampd(u, P.u_lo, P.u_hi);
+        if(!active) u = 0.0;
+      }
+      ud[(size_t)k * 32 + lane] = u;
+      store9(xd + (size_t)k * 9, x);
+      const double c = step_and_cost(k, m, x, u);
+      Jc = Jc + c;
+    }
+    store9(xd + (size_t)N * 9, x);
+    Jc = Jc + terminal_cost(x);
+    return Jc;
+  }
+
+  // ---- backward pass ----------------------------------------------------------------------
+  /** One stage of the backward recursion.  Returns false if BoxQP failed (retval < 1). */
+  CCC_DEV bool backward_stage(int k, double & k_next, int & m_next)
+  {
+    const int N = P.N;
+    const int m = stage_m(k);
+    const bool active = lane < m;
+    const double * xn = xtraj(cur) + (size_t)k * 9;
+    double x[9];
+    CCC_UNROLL
+    for(int i = 0; i < 9; i++) x[i] = xn[i];
+    const double u = active ? utraj(cur)[(size_t)k * 32 + lane] : 0.0;
+    const double * tb = stage_tab(k);
+    double rho[3], d[3], cr[3];
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++)
+    {
+      rho[a] = active ? ldg(tb + a * 32 + lane) : 0.0;
+      d[a] = (active ? ldg(tb + (3 + a) * 32 + lane) : 0.0) - x[a];
+    }
+    cross3(d, rho, cr);
+    double f[3];
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++) f[a] = warp_sum(active ? u * rho[a] : 0.0);
+
+    // Fx: only the cross-product block changes from stage to stage (rows 6..8, cols 0..2)
+    warp_sync();
+    if(lane == 0)
+    {
+      double * Fx = s + sm::FX;
+      Fx[6 * 9 + 1] = -f[2] * P.dt;
+      Fx[6 * 9 + 2] = f[1] * P.dt;
+      Fx[7 * 9 + 0] = f[2] * P.dt;
+      Fx[7 * 9 + 2] = -f[0] * P.dt;
+      Fx[8 * 9 + 0] = -f[1] * P.dt;
+      Fx[8 * 9 + 1] = f[0] * P.dt;
+    }
+    warp_sync();
+    const double * Fx = s + sm::FX;
+    const double * Vxx = s + sm::VXX;
+    const double * Vx = s + sm::VX;
+    double * T = s + sm::T;
+    double * Qxx = s + sm::QXX;
+    double * Qx = s + sm::QX;
+    // T = Vxx Fx
+    for(int e = lane; e < 81; e += 32)
+    {
+      const int i = e / 9, j = e - 9 * i;
+      double acc = 0.0;
+      CCC_UNROLL
+      for(int c = 0; c < 9; c++) acc = dfma(Vxx[i * 9 + c], Fx[c * 9 + j], acc);
+      T[e] = acc;
+    }
+    if(lane < 9)
+    {
+      double rr = lane < 3 ? ldg(ref(k) + lane) : 0.0;
+      double xl = xn[lane];
+      double lx = lane < 3 ? P.w_run[lane] * (xl - rr) : P.w_run[lane] * xl;
+      double acc = 0.0;
+      CCC_UNROLL
+      for(int c = 0; c < 9; c++) acc = dfma(Fx[c * 9 + lane], Vx[c], acc);
+      Qx[lane] = lx + acc;
+    }
+    warp_sync();
+    // Qxx = Lxx + Fx' T
+    for(int e = lane; e < 81; e += 32)
+    {
+      const int i = e / 9, j = e - 9 * i;
+      double acc = 0.0;
+      CCC_UNROLL
+      for(int c = 0; c < 9; c++) acc = dfma(Fx[c * 9 + i], T[c * 9 + j], acc);
+      Qxx[e] = (i == j ? P.w_run[i] : 0.0) + acc;
+    }
+
+    if(m == 0)
+    {
+      // no input: Vx = Qx, Vxx = sym(Qxx)
+      warp_sync();
+      double * Vxxw = s + sm::VXX;
+      double * Vxw = s + sm::VX;
+      for(int e = lane; e < 81; e += 32)
+      {
+        const int i = e / 9, j = e - 9 * i;
+        Vxxw[e] = 0.5 * (Qxx[e] + Qxx[j * 9 + i]);
+      }
+      if(lane < 9) Vxw[lane] = Qx[lane];
+      if(P.out_clamped && lane == 0) P.out_clamped[(size_t)b * N + k] = 0u;
+      warp_sync();
+      k_next = 0.0;
+      m_next = 0;
+      return true;
+    }
+
+    // Fu column of this lane (rows 3..8; rows 0..2 are zero)
+    double Fu[6];
+    CCC_UNROLL
+    for(int a = 0; a < 3; a++)
+    {
+      Fu[a] = rho[a] * P.dt;
+      Fu[3 + a] = cr[a] * P.dt;
+    }
+    // Qu
+    double Qu;
+    {
+      double acc = 0.0;
+      CCC_UNROLL
+      for(int c = 0; c < 6; c++) acc = dfma(Fu[c], Vx[3 + c], acc);
+      Qu = P.w_run[9] * u + acc;
+    }
+    // W = Vxx Fu, rows 3..8, published transposed: WT[lane][0..5]
+    double * WT = s + sm::WT;
+    {
+      double w[6];
+      CCC_UNROLL
+      for(int r = 0; r < 6; r++)
+      {
+        double acc = 0.0;
+        CCC_UNROLL
+        for(int c = 0; c < 6; c++) acc = dfma(Vxx[(3 + r) * 9 + 3 + c], Fu[c], acc);
+        w[r] = active ? acc : 0.0;
+      }
+      CCC_UNROLL
+      for(int r = 0; r < 6; r++) WT[lane * 6 + r] = w[r];
+    }
+    // Qux row of this lane: Fu' (Vxx Fx)
+    double Qux[9];
+    CCC_UNROLL
+    for(int c = 0; c < 9; c++)
+    {
+      double acc = 0.0;
+      CCC_UNROLL
+      for(int r = 0; r < 6; r++) acc = dfma(Fu[r], T[(3 + r) * 9 + c], acc);
+      Qux[c] = 0.0 + acc;
+    }
+    warp_sync();
+    // Quu row (lower triangle is the definition; mirrored through A's upper triangle)
+    double H[32];
+    CCC_UNROLL
+    for(int j = 0; j < 32; j++) H[j] = 0.0;
+    CCC_UNROLL
+    for(int j = 0; j < 32; j++)
+    {
+      if(j >= m) break;
+      double acc = 0.0;
+      CCC_UNROLL
+      for(int r = 0; r < 3; r++)
+      {
+        d2 w = ld2(WT + j * 6 + 2 * r);
+        acc = dfma(Fu[2 * r], w.x, acc);
+        acc = dfma(Fu[2 * r + 1], w.y, acc);
+      }
+      H[j] = (j == lane ? P.w_run[9] : 0.0) + acc;
+    }
+    double quu_diag = 0.0;
+    CCC_UNROLL
+    for(int j = 0; j < 32; j++)
+      if(j == lane) quu_diag = H[j];
+    warp_sync(); // everyone is done reading WT (aliases A)
+    double * A = s + sm::A;
+    CCC_UNROLL
+    for(int j = 0; j < 32; j++)
+    {
+      if(j >= m) break;
+      if(active && j <= lane) A[j * kLda + lane] = (j == lane) ? quu_diag + lambda : H[j];
+    }
+    warp_sync();
+    load_sym_row(H, A, m);
+
+    // gains
+    double kk = 0.0;
+    double K[9];
+    unsigned clamped = 0;
+    double invd = 1.0;
+    if(P.cfg.with_input_constraint)
+    {
+      const double lo = P.u_lo - u, hi = P.u_hi - u;
+      // warm start: gain of the next stage if the dimensions agree (iLQG.m: k(:,min(i+1,N-1)))
+      double x0;
+      if(k == N - 1)
+        x0 = active ? gain(k)[lane] : 0.0;
+      else
+        x0 = (m_next == m) ? k_next : 0.0;
+      BoxQpOut r = boxqp_warp(H, A, s + sm::VB0, s + sm::VB1, s + sm::VB2, Qu, lo, hi, x0, m, P.cfg.boxqp);
+      if(r.retval < 1) return false;
+      kk = active ? x0 : 0.0;
+      clamped = r.clamped;
+      invd = r.invd;
+      const unsigned active_mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+      CCC_UNROLL
+      for(int c = 0; c < 9; c++) K[c] = Qux[c];
+      if(clamped != active_mask)
+      {
+        llt_solveN<9>(K, A, clamped, m, invd);
+        CCC_UNROLL
+        for(int c = 0; c < 9; c++) K[c] = -K[c];
+        const bool free_i = active && !((clamped >> lane) & 1u);
+        CCC_UNROLL
+        for(int c = 0; c < 9; c++) K[c] = free_i ? K[c] : 0.0;
+      }
+      else
+      {
+        CCC_UNROLL
+        for(int c = 0; c < 9; c++) K[c] = 0.0;
+      }
+    }
+    else
+    {
+      bool ok = llt_factor(H, A, s + sm::VB0, s + sm::VB1, 0u, m, invd);
+      load_sym_row(H, A, m);
+      if(!ok) return false;
+      double r10[10];
+      r10[0] = Qu;
+      CCC_UNROLL
+      for(int c = 0; c < 9; c++) r10[1 + c] = Qux[c];
+      llt_solveN<10>(r10, A, 0u, m, invd);
+      kk = active ? -r10[0] : 0.0;
+      CCC_UNROLL
+      for(int c = 0; c < 9; c++) K[c] = active ? -r10[1 + c] : 0.0;
+    }
+    if(P.out_clamped && lane == 0) P.out_clamped[(size_t)b * N + k] = clamped;
+
+    // store gains (coalesced rows) and track max |k| / (|u| + 1)
+    {
+      double * g = gain(k);
+      g[lane] = kk;
+      CCC_UNROLL
+      for(int c = 0; c < 9; c++) g[(1 + c) * 32 + lane] = K[c];
+      if(active)
+      {
+        double r = dabs(kk) / (dabs(u) + 1.0);
+        krel = krel < r ? r : krel;
+      }
+    }
+
+    // ---- cost-to-go update with the unregularised Quu ------------------------------------
+    CCC_UNROLL
+    for(int j = 0; j < 32; j++)
+      if(j == lane) H[j] = quu_diag;
+    double * VB0 = s + sm::VB0;
+    double * VB1 = s + sm::VB1;
+    double * VB2 = s + sm::VB2;
+    warp_sync(); // the factor in A is dead from here on: KB/ZB/QB alias it
+    double * KB = s + sm::KB;
+    double * ZB = s + sm::ZB;
+    double * QB = s + sm::QB;
+    VB0[lane] = kk;
+    CCC_UNROLL
+    for(int c = 0; c < 9; c++) KB[lane * 10 + c] = K[c];
+    KB[lane * 10 + 9] = 0.0;
+    warp_sync();
+    const double Quuk = matvec32(H, VB0, m);
+    double Z[9];
+    CCC_UNROLL
+    for(int c = 0; c < 9; c++) Z[c] = 0.0;
+    CCC_UNROLL
+    for(int j = 0; j < 32; j++)
+    {
+      if(j >= m) break;
+      const double h = H[j];
+      d2 k01 = ld2(KB + j * 10 + 0), k23 = ld2(KB + j * 10 + 2), k45 = ld2(KB + j * 10 + 4), k67 = ld2(KB + j * 10 + 6);
+      const double k8 = KB[j * 10 + 8];
+      Z[0] = dfma(h, k01.x, Z[0]);
+      Z[1] = dfma(h, k01.y, Z[1]);
+      Z[2] = dfma(h, k23.x, Z[2]);
+      Z[3] = dfma(h, k23.y, Z[3]);
+      Z[4] = dfma(h, k45.x, Z[4]);
+      Z[5] = dfma(h, k45.y, Z[5]);
+      Z[6] = dfma(h, k67.x, Z[6]);
+      Z[7] = dfma(h, k67.y, Z[7]);
+      Z[8] = dfma(h, k8, Z[8]);
+    }
+    dV0 = dV0 + warp_sum(active ? kk * Qu : 0.0);
+    dV1 = dfma(0.5, warp_sum(active ? kk * Quuk : 0.0), dV1);
+    CCC_UNROLL
+    for(int c = 0; c < 9; c++)
+    {
+      ZB[lane * 10 + c] = active ? Z[c] : 0.0;
+      QB[lane * 10 + c] = active ? Qux[c] : 0.0;
+    }
+    VB1[lane] = active ? Quuk : 0.0;
+    VB2[lane] = active ? Qu : 0.0;
+    warp_sync();
+    double * Vxw = s + sm::VX;
+    double * Vxxw = s + sm::VXX;
+    double * S2 = s + sm::S2;
+    if(lane < 9)
+    {
+      double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for(int j = 0; j < m; j++)
+      {
+        const double kj = KB[j * 10 + lane];
+        a1 = dfma(kj, VB1[j], a1);
+        a2 = dfma(kj, VB2[j], a2);
+        a3 = dfma(QB[j * 10 + lane], VB0[j], a3);
+      }
+      Vxw[lane] = ((Qx[lane] + a1) + a2) + a3;
+    }
+    double s1v[3], s2v[3];
+    CCC_UNROLL
+    for(int q = 0; q < 3; q++)
+    {
+      const int e = lane + 32 * q;
+      s1v[q] = 0.0;
+      s2v[q] = 0.0;
+      if(e < 81)
+      {
+        const int a = e / 9, c = e - 9 * a;
+        double s1 = 0.0, s2 = 0.0;
+        for(int j = 0; j < m; j++)
+        {
+          const double kj = KB[j * 10 + a];
+          s1 = dfma(kj, ZB[j * 10 + c], s1);
+          s2 = dfma(kj, QB[j * 10 + c], s2);
+        }
+        s1v[q] = s1;
+        s2v[q] = s2;
+        S2[e] = s2;
+      }
+    }
+    warp_sync();
+    // Vn = ((Qxx + K'QuuK) + K'Qux) + Qux'K   (Qux'K = (K'Qux)' bit for bit), staged in T
+    CCC_UNROLL
+    for(int q = 0; q < 3; q++)
+    {
+      const int e = lane + 32 * q;
+      if(e < 81)
+      {
+        const int a = e / 9, c = e - 9 * a;
+        T[e] = ((Qxx[e] + s1v[q]) + s2v[q]) + S2[c * 9 + a];
+      }
+    }
+    warp_sync();
+    CCC_UNROLL
+    for(int q = 0; q < 3; q++)
+    {
+      const int e = lane + 32 * q;
+      if(e < 81)
+      {
+        const int a = e / 9, c = e - 9 * a;
+        Vxxw[e] = 0.5 * (T[e] + T[c * 9 + a]);
+      }
+    }
+    warp_sync();
+    k_next = kk;
+    m_next = m;
+    return true;
+  }
+
+  CCC_DEV bool backward_pass()
+  {
+    const int N = P.N;
+    // terminal cost derivatives (src/DdpCentroidal.cpp:156-177)
+    const double * xN = xtraj(cur) + (size_t)N * 9;
+    warp_sync();
+    for(int e = lane; e < 81; e += 32)
+    {
+      const int i = e / 9, j = e - 9 * i;
+      s[sm::VXX + e] = (i == j) ? P.w_term[i] : 0.0;
+    }
+    if(lane < 9)
+    {
+      double rr = lane < 3 ? ldg(ref(N) + lane) : 0.0;
+      double xv = xN[lane];
+      s[sm::VX + lane] = lane < 3 ? P.w_term[lane] * (xv - rr) : P.w_term[lane] * xv;
+    }
+    warp_sync();
+    dV0 = 0.0;
+    dV1 = 0.0;
+    krel = 0.0;
+    double k_next = 0.0;
+    int m_next = -1;
+    for(int k = N - 1; k >= 0; k--)
+    {
+      if(!backward_stage(k, k_next, m_next)) return false;
+    }
+    return true;
+  }
+
+  CCC_DEV void increase_lambda()
+  {
+    const double f = P.cfg.lambda_factor;
+    double t = dlambda * f;
+    dlambda = t < f ? f : t; // std::max(dlambda * f, f)
+    double l = lambda * dlambda;
+    lambda = l < P.cfg.lambda_min ? P.cfg.lambda_min : l;
+  }
+  CCC_DEV void decrease_lambda()
+  {
+    const double f = P.cfg.lambda_factor;
+    double t = dlambda / f, u = 1.0 / f;
+    dlambda = u < t ? u : t; // std::min(dlambda / f, 1 / f)
+    lambda = (lambda * dlambda) * (lambda > P.cfg.lambda_min ? 1.0 : 0.0);
+  }
+
+  CCC_DEV void trace(int iter, int alpha_idx)
+  {
+    if(lane == 0 && iter - 1 < P.trace_len)
+    {
+      size_t o = (size_t)b * P.trace_len + (iter - 1);
+      if(P.out_alpha_idx) P.out_alpha_idx[o] = (signed char)alpha_idx;
+      if(P.out_lambda) P.out_lambda[o] = lambda;
+    }
+  }
+
+  /** nmpc_ddp procOnce: 0 continue, 1 converged, -1 failed. */
+  CCC_DEV int proc_once(int iter)
+  {
+    while(!backward_pass())
+    {
+      increase_lambda();
+      if(lambda > P.cfg.lambda_max)
+      {
+        trace(iter, -3);
+        return -1;
+      }
+    }
+    const double k_rel_norm = warp_max(krel);
+    if(k_rel_norm < P.cfg.k_rel_norm_thre && lambda < P.cfg.lambda_thre)
+    {
+      decrease_lambda();
+      trace(iter, -2);
+      return 1;
+    }
+    bool success = false;
+    double actual = 0.0;
+    int a_acc = -1;
+    for(int a = 0; a < P.cfg.n_alpha; a++)
+    {
+      const double alpha = P.cfg.alpha[a];
+      const double Jc = rollout(1 - cur, alpha, false);
+      actual = J - Jc;
+      const double expected = -(alpha * dfma(alpha, dV1, dV0));
+      double ratio;
+      if(expected > 0)
+        ratio = actual / expected;
+      else
+        ratio = (double)((0 < actual) - (actual < 0));
+      if(ratio > P.cfg.cost_update_ratio_thre)
+      {
+        success = true;
+        a_acc = a;
+        J = Jc;
+        break;
+      }
+    }
+    int rv = 0;
+    if(success)
+    {
+      decrease_lambda();
+      cur = 1 - cur;
+      if(actual < P.cfg.cost_update_thre) rv = 1;
+    }
+    else
+    {
+      increase_lambda();
+      if(lambda > P.cfg.lambda_max) rv = -1;
+    }
+    trace(iter, success ? a_acc : -1);
+    return rv;
+  }
+
+  CCC_DEV void solve()
+  {
+    const int N = P.N;
+    lambda = P.cfg.initial_lambda;
+    dlambda = P.cfg.initial_dlambda;
+    // constant part of Fx: identity + (1/mass) dt on the (pos, momentum) block
+    warp_sync();
+    for(int e = lane; e < 82; e += 32)
+    {
+      const int i = e / 9, j = e - 9 * i;
+      double v = (i == j && e < 81) ? 1.0 : 0.0;
+      if(i < 3 && j == i + 3) v = (1 / P.mass) * P.dt;
+      s[sm::FX + e] = v;
+    }
+    // the BoxQP warm start of the last stage reads its own previous gain: zero it
+    gain(N - 1)[lane] = 0.0;
+    warp_sync();
+    cur = 0;
+    J = rollout(0, 0.0, true);
+    for(int i = lane; i < P.trace_len; i += 32)
+    {
+      size_t o = (size_t)b * P.trace_len + i;
+      if(P.out_alpha_idx) P.out_alpha_idx[o] = (signed char)-4;
+      if(P.out_lambda) P.out_lambda[o] = 0.0;
+    }
+    warp_sync();
+    int rv = 0, iter = 0;
+    for(iter = 1; iter <= P.cfg.max_iter; iter++)
+    {
+      rv = proc_once(iter);
+      if(rv != 0) break;
+    }
+    if(iter > P.cfg.max_iter) iter = P.cfg.max_iter;
+    // outputs
+    warp_sync();
+    const double * xs = xtraj(cur);
+    const double * us = utraj(cur);
+    if(P.out_x)
+      for(int i = lane; i < (N + 1) * 9; i += 32) P.out_x[(size_t)b * (N + 1) * 9 + i] = xs[i];
+    if(P.out_u)
+      for(int k = 0; k < N; k++) P.out_u[((size_t)b * N + k) * 32 + lane] = us[(size_t)k * 32 + lane];
+    if(lane == 0)
+    {
+      if(P.out_cost) P.out_cost[b] = J;
+      if(P.out_iters) P.out_iters[b] = iter;
+      if(P.out_status) P.out_status[b] = rv;
+    }
+  }
+};
+} // namespace ccc

@@ -1,0 +1,103 @@
+"""ctypes binding of libccc_b200.so — the host-side mirror of the reference's solver objects.
+
+There is no CPU fallback: loading fails loudly if the CUDA library is missing, and every solve
+returns CCC_ERR_CUDA without a device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from .problem import DdpCentroidalProblemSet, DdpResultArrays
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libccc_b200.so")
+_LIB = None
+
+EXPORTS = [
+    "ccc_abi_version", "ccc_device_count", "ccc_last_error", "ccc_ddp_config_default",
+    "ccc_ddp_centroidal_create", "ccc_ddp_centroidal_destroy", "ccc_ddp_centroidal_solve",
+    "ccc_ddp_centroidal_last_launches",
+]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                f"{LIB_PATH} is missing: build it with `python -m centroidalcontrolcollection_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.ccc_abi_version.restype = C.c_int32
+        L.ccc_device_count.restype = C.c_int32
+        L.ccc_last_error.restype = C.c_char_p
+        L.ccc_ddp_config_default.argtypes = [C.c_void_p]
+        L.ccc_ddp_config_default.restype = None
+        L.ccc_ddp_centroidal_create.restype = C.c_void_p
+        L.ccc_ddp_centroidal_create.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.ccc_ddp_centroidal_destroy.argtypes = [C.c_void_p]
+        L.ccc_ddp_centroidal_destroy.restype = None
+        L.ccc_ddp_centroidal_solve.restype = C.c_int32
+        L.ccc_ddp_centroidal_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ccc_ddp_centroidal_last_launches.restype = C.c_int32
+        L.ccc_ddp_centroidal_last_launches.argtypes = [C.c_void_p]
+        L.ccc_ddp_centroidal_set_variant.restype = C.c_int32
+        L.ccc_ddp_centroidal_set_variant.argtypes = [C.c_int32]
+        _LIB = L
+    return _LIB
+
+
+def last_error():
+    return lib().ccc_last_error().decode()
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EngineError(f"{what} failed with code {rc}: {last_error()}")
+
+
+class DdpCentroidalEngine:
+    """Batched counterpart of CCC::DdpCentroidal's solver object (reference
+    include/CCC/DdpCentroidal.h:342-365): owns the device workspace, solves batches."""
+
+    def __init__(self, horizon_steps, max_batch, max_sched=16):
+        self._h = lib().ccc_ddp_centroidal_create(int(horizon_steps), int(max_batch), int(max_sched))
+        if not self._h:
+            raise EngineError(f"ccc_ddp_centroidal_create failed: {last_error()}")
+        self.N, self.max_batch, self.max_sched = horizon_steps, max_batch, max_sched
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ccc_ddp_centroidal_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def solve(self, problem_set: DdpCentroidalProblemSet, cfg, trace_len=0, result=None):
+        """Host buffers in, host buffers out (H2D + solve + D2H, synchronous)."""
+        res = result if result is not None else problem_set.new_result(trace_len)
+        bs, rs = problem_set.as_struct(), res.as_struct()
+        rc = lib().ccc_ddp_centroidal_solve(self._h, C.addressof(bs), C.addressof(cfg), C.addressof(rs),
+                                            _abi.CCC_MEM_HOST, None)
+        _check(rc, "ccc_ddp_centroidal_solve")
+        return res
+
+    def solve_device(self, batch_struct, cfg, result_struct, stream=0):
+        """Device pointers in/out; only enqueues work on `stream` (an int cudaStream_t)."""
+        rc = lib().ccc_ddp_centroidal_solve(self._h, C.addressof(batch_struct), C.addressof(cfg),
+                                            C.addressof(result_struct), _abi.CCC_MEM_DEVICE, C.c_void_p(stream))
+        _check(rc, "ccc_ddp_centroidal_solve")
+
+    @property
+    def last_launches(self):
+        return int(lib().ccc_ddp_centroidal_last_launches(self._h))
+
+    @staticmethod
+    def set_variant(v):
+        return int(lib().ccc_ddp_centroidal_set_variant(int(v)))

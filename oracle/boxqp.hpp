@@ -84,6 +84,7 @@ struct BoxQp
   int retval = 0;
   int iters = 0;
   int nfactor = 0;
+  int ls_steps = 0; // Armijo backtracking steps (statistics only)
   std::vector<double> x;
   std::vector<uint8_t> clamped;
   FreeLlt llt; // factor matching `clamped` (valid unless all clamped)
@@ -195,6 +196,7 @@ struct BoxQp
       while((objc - old_obj) / (step * sdotg) < cfg.armijo)
       {
         step = step * cfg.step_factor;
+        ls_steps++;
         for(int i = 0; i < m; i++) xc[i] = clampd(std::fma(step, search[i], x[i]), lo[i], hi[i]);
         objc = objective(H, m, g, xc.data(), Hxc.data());
         if(step < cfg.min_step)

@@ -16,6 +16,8 @@ using namespace oracle;
 
 namespace
 {
+std::atomic<long long> g_stats[6];
+
 DdpConfig toConfig(const ccc_ddp_config_t * c)
 {
   DdpConfig cfg;
@@ -158,6 +160,7 @@ int32_t ccc_oracle_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t * bt,
     }
     s.solve(bt->x0 + static_cast<size_t>(b) * 9, u0);
     storeResult(s, b, N, 9, mm, r);
+    for(int i = 0; i < 6; i++) g_stats[i] += s.stats[i];
   });
   return CCC_OK;
 }
@@ -204,6 +207,12 @@ int32_t ccc_oracle_centroidal_eval(const ccc_ddp_centroidal_batch_t * bt,
     p.terminalCostDeriv(x, Vx, vxx.data());
   }
   return CCC_OK;
+}
+
+/** Read and reset the aggregated solver statistics (see DdpSolver::stats). */
+void ccc_oracle_stats(int64_t * out)
+{
+  for(int i = 0; i < 6; i++) out[i] = g_stats[i].exchange(0);
 }
 
 int32_t ccc_oracle_hardware_threads(void)

@@ -97,6 +97,8 @@ struct DdpSolver
   std::vector<DdpTrace> trace;
   double lambda = 0, dlambda = 0, dV[2] = {0, 0};
   int retval = 0;
+  // statistics only: backward passes, forward passes, BoxQP calls / iterations / factorisations / Armijo steps
+  long long stats[6] = {0, 0, 0, 0, 0, 0};
 
   explicit DdpSolver(const DdpProblem & prob) : p(prob), nx(prob.nx), N(prob.N) {}
 
@@ -257,6 +259,7 @@ struct DdpSolver
     std::vector<double> Vn(nx * nx);
     p.terminalCostDeriv(x[N].data(), Vx.data(), Vxx.data());
     dV[0] = dV[1] = 0.0;
+    stats[0]++;
 
     for(int k = N - 1; k >= 0; k--)
     {
@@ -276,8 +279,14 @@ struct DdpSolver
           Qxx[i * nx + j] = Lxx[i * nx + j] + dot_seq(Fx.data() + i, nx, T.data() + j, nx, nx);
       for(int i = 0; i < nx; i++) // W = Vxx Fu
         for(int j = 0; j < m; j++) W[i * m + j] = dot_seq(Vxx.data() + i * nx, 1, Fu.data() + j, m, nx);
+      // Quu is evaluated on its lower triangle and mirrored, so that it is symmetric bit for bit
+      // (Eigen::LLT reads the lower triangle only; the engine stores one triangle)
       for(int i = 0; i < m; i++)
-        for(int j = 0; j < m; j++) Quu[i * m + j] = Luu[i * m + j] + dot_seq(Fu.data() + i, m, W.data() + j, m, nx);
+        for(int j = 0; j <= i; j++)
+        {
+          Quu[i * m + j] = Luu[i * m + j] + dot_seq(Fu.data() + i, m, W.data() + j, m, nx);
+          Quu[j * m + i] = Quu[i * m + j];
+        }
       for(int j = 0; j < m; j++) // Qux = Lxu' + Fu' (Vxx Fx)
         for(int i = 0; i < nx; i++) Qux[j * nx + i] = Lxu[i * m + j] + dot_seq(Fu.data() + j, m, T.data() + i, nx, nx);
 
@@ -305,6 +314,10 @@ struct DdpSolver
           BoxQp qp;
           qp.cfg = cfg.boxqp;
           int r = qp.solve(QuuF.data(), Qu.data(), lo.data(), hi.data(), k0.data(), m);
+          stats[2]++;
+          stats[3] += qp.iters;
+          stats[4] += qp.nfactor;
+          stats[5] += qp.ls_steps;
           if(r < 1) return false;
           kk = qp.x;
           KK.assign(static_cast<size_t>(m) * nx, 0.0);
@@ -386,6 +399,7 @@ struct DdpSolver
   void forwardPass(double alpha)
   {
     xc[0] = x[0];
+    stats[1]++;
     std::vector<double> dx(nx), lo, hi;
     for(int k = 0; k < N; k++)
     {

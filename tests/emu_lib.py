@@ -1,0 +1,25 @@
+"""Loader of the warp emulator (tests/emu): runs the CUDA solver-core *source* on the CPU."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "emu")])
+        _LIB = C.CDLL(os.path.join(_HERE, "emu", "libccc_emu.so"))
+        _LIB.ccc_emu_ddp_centroidal_solve.restype = C.c_int32
+        _LIB.ccc_emu_ddp_centroidal_solve.argtypes = [C.c_void_p] * 3
+    return _LIB
+
+
+def ddp_centroidal_solve(problem_set, cfg, trace_len=0):
+    res = problem_set.new_result(trace_len)
+    bs, rs = problem_set.as_struct(), res.as_struct()
+    rc = lib().ccc_emu_ddp_centroidal_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))
+    assert rc == 0
+    return res

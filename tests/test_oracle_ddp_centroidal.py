@@ -114,3 +114,16 @@ def test_cold_start_converges_config3_sample(oracle):
         assert (res.u[:, :, j][m <= j] == 0).all()
     # the rollout of the returned u reproduces the returned x (stateEq consistency)
     assert np.isfinite(res.x).all() and np.isfinite(res.cost).all()
+
+
+def test_oracle_matches_golden_fixture(oracle):
+    """tests/golden/ddp_centroidal_config3_b16.npz (tests/golden/make_golden.py): drift pin."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ddp_centroidal_config3_b16.npz"))
+    w = workloads.ddp_centroidal_config3(batch=16)
+    ps = problem.DdpCentroidalProblemSet.from_workload(w)
+    assert np.array_equal(ps.x0, g["x0"])
+    res = oracle.ddp_centroidal_solve(ps, problem.ddp_centroidal_config(), trace_len=g["alpha_idx"].shape[1], n_threads=4)
+    for k in ("iters", "status", "alpha_idx", "clamped", "x", "u", "cost", "lambda_trace"):
+        assert np.array_equal(getattr(res, k), g[k]), k
