@@ -7,6 +7,17 @@
 // src/DdpSingleRigidBody.cpp:267); algorithm = Tassa et al. ICRA 2014 boxQP.m.
 // Evaluation order = oracle/boxqp.hpp (DESIGN.md §4 "canonical arithmetic"): sequential fma
 // chains over the input index, pairwise-tree warp sums, IEEE / and sqrt — bit-exact vs oracle.
+//
+// Code size is a first-class constraint here (profiles/r01_ncu_v1_icache.md): the first
+// version unrolled the factorisation over register-indexed columns and inlined the
+// matrix-vector product at six sites; the kernel spent 72 % of its issue slots waiting for
+// instruction fetch.  This version keeps every hot loop either rolled or single-site:
+//  * the free block is compacted (rank r <- r-th free input), so the factorisation is the
+//    oracle's dense nf x nf LL^T with no skipped columns;
+//  * the column loop is rolled: after column k every lane shifts its register row by one
+//    (folded into the update fma), so the live column is always register 0;
+//  * BoxQP has one objective-evaluation site, driven by a small phase variable;
+//  * division and square root are out-of-line calls.
 #pragma once
 #include "warp_ctx.cuh"
 
@@ -28,23 +39,34 @@ CCC_DEV d2 ld2(const double * p)
 #endif
 }
 
+/** IEEE division / square root as shared out-of-line routines (each inline copy is ~40 SASS). */
+CCC_DEV_NOINLINE double ddiv(double a, double b)
+{
+  return a / b;
+}
+CCC_DEV_NOINLINE double dsqrt_ool(double a)
+{
+  return dsqrt(a);
+}
+
 struct BoxQpCfg
 {
   int max_iter;
   double grad_thre, rel_improve_thre, step_factor, min_step, armijo;
 };
 
-/** y_lane = sum_j H[j] * vb[j], ascending j, one fma chain from +0.0 (vb: 32 doubles in smem). */
+/** y_lane = sum_j H[j] * vb[j], ascending j, one fma chain from +0.0.  vb: 32 doubles in smem,
+ *  entries j >= m are +0.0 and H[j >= m] is finite, so only the 16-boundary is tested. */
 CCC_DEV double matvec32(const double (&H)[32], const double * vb, int m)
 {
   double acc = 0.0;
   CCC_UNROLL
   for(int jj = 0; jj < 16; jj++)
   {
-    if(2 * jj >= m) break;
+    if(jj == 8 && m <= 16) break;
     d2 v = ld2(vb + 2 * jj);
     acc = dfma(H[2 * jj], v.x, acc);
-    if(2 * jj + 1 < m) acc = dfma(H[2 * jj + 1], v.y, acc);
+    acc = dfma(H[2 * jj + 1], v.y, acc);
   }
   return acc;
 }
@@ -57,149 +79,205 @@ CCC_DEV void publish(double * vb, double v, bool active)
   warp_sync();
 }
 
-/** Reload row `lane` of the symmetric matrix stored in the upper triangle (+diag) of A. */
+/** Reload row `lane` of the symmetric matrix stored in the upper triangle (+diag) of A;
+ *  entries j >= m are set to +0.0. */
 CCC_DEV void load_sym_row(double (&H)[32], const double * A, int m)
 {
   const int lane = lane_id();
   CCC_UNROLL
   for(int j = 0; j < 32; j++)
   {
-    if(j >= m) break;
     int r = j < lane ? j : lane, c = j < lane ? lane : j;
-    H[j] = A[r * kLda + c];
+    H[j] = (j < m && lane < m) ? A[r * kLda + c] : 0.0;
   }
 }
 
-/** In-register right-looking LL^T of the free block (clamped rows/columns behave as identity).
- *  In:  H = row `lane` of the matrix.  Out: H destroyed; strict lower triangle of A holds L for
- *  the free rows/columns; invd = 1 / L[lane][lane].  cb0/cb1: two 32-double smem vectors.
- *  Returns false (warp-uniform) if a pivot is not > 0. */
-CCC_DEV bool llt_factor(double (&H)[32], double * A, double * cb0, double * cb1, unsigned clamped, int m, double & invd)
+/** Compact numbering of the free inputs (the oracle's free_idx list). */
+struct FreeSet
+{
+  unsigned free_mask; // bit j = input j is free
+  int nf;             // number of free inputs
+  int idx;            // original index of compact row `lane` (valid for lane < nf)
+  int rank;           // compact position of original input `lane` (valid if free)
+};
+
+CCC_DEV int nth_set_bit(unsigned mask, int n)
+{
+#ifdef CCC_WARP_EMU
+  for(int i = 0; i < 32; i++)
+    if((mask >> i) & 1u)
+    {
+      if(n == 0) return i;
+      n--;
+    }
+  return 32;
+#else
+  return (int)__fns(mask, 0, n + 1);
+#endif
+}
+CCC_DEV int popc32(unsigned v)
+{
+#ifdef CCC_WARP_EMU
+  return __builtin_popcount(v);
+#else
+  return __popc(v);
+#endif
+}
+
+/** idxbuf: 32 ints of smem receiving the free list (for the compact row gather). */
+CCC_DEV FreeSet make_free_set(unsigned clamped, int m, int * idxbuf)
 {
   const int lane = lane_id();
-  const bool free_i = lane < m && !((clamped >> lane) & 1u);
-  bool ok = true;
-  int par = 0; // alternates per processed column: a buffer is rewritten only two syncs later
-  warp_sync(); // earlier readers of cb0/cb1 and of A's lower triangle are done
+  const unsigned active_mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+  FreeSet fs;
+  fs.free_mask = ~clamped & active_mask;
+  fs.nf = popc32(fs.free_mask);
+  fs.idx = lane < fs.nf ? nth_set_bit(fs.free_mask, lane) : 0;
+  fs.rank = popc32(fs.free_mask & ((1u << lane) - 1u));
+  warp_sync();
+  idxbuf[lane] = fs.idx;
+  warp_sync();
+  return fs;
+}
+
+/** Gather compact row `lane` of H[free,free] from the symmetric tile. */
+CCC_DEV void load_compact_row(double (&Hc)[32], const double * A, const int * idxbuf, const FreeSet & fs)
+{
+  const int lane = lane_id();
   CCC_UNROLL
-  for(int k = 0; k < 32; k++)
+  for(int c = 0; c < 32; c++)
   {
-    if(k >= m) break;
-    if((clamped >> k) & 1u) continue;
-    double piv = warp_shfl(H[k], k);
+    if((c & 7) == 0 && c >= fs.nf && c > 0) break;
+    const int ic = idxbuf[c];
+    const int r = ic < fs.idx ? ic : fs.idx, cc = ic < fs.idx ? fs.idx : ic;
+    Hc[c] = (c < fs.nf && lane < fs.nf) ? A[r * kLda + cc] : 0.0;
+  }
+}
+
+/** Dense LL^T of the compact nf x nf block, rows in registers, column loop rolled.
+ *  In: Hc = compact row `lane`.  Out: Hc destroyed; A's strict lower triangle holds the compact
+ *  factor (row r > col c at A[r][c]); invd_c = 1 / L[lane][lane] (compact numbering).
+ *  cb: 128 doubles of smem (two 64-double column buffers whose upper halves stay zero).
+ *  Returns false (warp-uniform) if a pivot is not > 0. */
+CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int nf, double & invd_c)
+{
+  const int lane = lane_id();
+  bool ok = true;
+  int par = 0;
+  warp_sync(); // earlier readers of cb and of A's lower triangle are done
+  cb[32 + lane] = 0.0;
+  cb[96 + lane] = 0.0;
+  CCC_NOUNROLL
+  for(int k = 0; k < nf; k++)
+  {
+    const double piv = warp_shfl(Hc[0], k);
     if(!(piv > 0.0))
     {
       ok = false;
       break;
     }
-    double d = dsqrt(piv);
-    double inv = 1.0 / d;
-    if(lane == k) invd = inv;
-    const bool below = free_i && lane > k;
-    double l = below ? H[k] * inv : 0.0;
-    double * cb = par ? cb1 : cb0;
+    const double d = dsqrt_ool(piv);
+    const double inv = ddiv(1.0, d);
+    if(lane == k) invd_c = inv;
+    const bool below = lane > k && lane < nf;
+    const double l = below ? Hc[0] * inv : 0.0;
+    double * cbuf = cb + par * 64;
     par ^= 1;
-    cb[lane] = l;
+    cbuf[lane] = l;
     if(below) A[lane * kLda + k] = l;
     warp_sync();
+    // trailing update folded with a shift by one register: entry (lane, k+j) moves to slot j-1
+    const int rem = nf - k;
+    const double * col = cbuf + k;
     CCC_UNROLL
-    for(int j = k + 1; j < 32; j++)
+    for(int j = 1; j < 32; j++)
     {
-      if(j >= m) break;
-      H[j] = dfma(-l, cb[j], H[j]);
+      if((j & 7) == 1 && j >= rem) break;
+      Hc[j - 1] = dfma(-l, col[j], Hc[j]);
     }
   }
   warp_sync();
   return ok;
 }
 
-/** Solve (L L') s = rhs on the free block; one value per lane (clamped/inactive lanes: 0). */
-CCC_DEV double llt_solve1(double rhs, const double * A, unsigned clamped, int m, double invd)
+/** Solve (L L') s = rhs on the compact block: rhs/solution in compact numbering (lane r). */
+CCC_DEV double llt_solve_compact(double rhs_c, const double * A, int nf, double invd_c)
 {
   const int lane = lane_id();
-  const bool free_i = lane < m && !((clamped >> lane) & 1u);
-  double acc = free_i ? rhs : 0.0;
-  for(int j = 0; j < m; j++)
+  const bool in = lane < nf;
+  double acc = in ? rhs_c : 0.0;
+  CCC_NOUNROLL
+  for(int j = 0; j < nf; j++)
   {
-    if((clamped >> j) & 1u) continue;
-    double yj = warp_shfl(acc * invd, j);
-    if(free_i && lane > j) acc = dfma(-A[lane * kLda + j], yj, acc);
+    const double yj = warp_shfl(acc * invd_c, j);
+    if(in && lane > j) acc = dfma(-A[lane * kLda + j], yj, acc);
   }
-  acc = free_i ? acc * invd : 0.0;
-  for(int j = m - 1; j >= 0; j--)
+  acc = in ? acc * invd_c : 0.0;
+  CCC_NOUNROLL
+  for(int j = nf - 1; j >= 0; j--)
   {
-    if((clamped >> j) & 1u) continue;
-    double xj = warp_shfl(acc * invd, j);
-    if(free_i && lane < j) acc = dfma(-A[j * kLda + lane], xj, acc);
+    const double xj = warp_shfl(acc * invd_c, j);
+    if(in && lane < j) acc = dfma(-A[j * kLda + lane], xj, acc);
   }
-  return free_i ? acc * invd : 0.0;
+  return in ? acc * invd_c : 0.0;
 }
 
-/** Same for NR right-hand sides held per lane (row `lane` of an m x NR matrix). */
+/** Same for NR right-hand sides per lane (compact numbering). */
 template<int NR>
-CCC_DEV void llt_solveN(double (&r)[NR], const double * A, unsigned clamped, int m, double invd)
+CCC_DEV void llt_solve_compactN(double (&r)[NR], const double * A, int nf, double invd_c)
 {
   const int lane = lane_id();
-  const bool free_i = lane < m && !((clamped >> lane) & 1u);
+  const bool in = lane < nf;
   CCC_UNROLL
-  for(int c = 0; c < NR; c++) r[c] = free_i ? r[c] : 0.0;
-  for(int j = 0; j < m; j++)
+  for(int c = 0; c < NR; c++) r[c] = in ? r[c] : 0.0;
+  CCC_NOUNROLL
+  for(int j = 0; j < nf; j++)
   {
-    if((clamped >> j) & 1u) continue;
-    const bool upd = free_i && lane > j;
-    double lij = upd ? A[lane * kLda + j] : 0.0;
+    const bool upd = in && lane > j;
+    const double lij = upd ? A[lane * kLda + j] : 0.0;
     CCC_UNROLL
     for(int c = 0; c < NR; c++)
     {
-      double yj = warp_shfl(r[c] * invd, j);
+      const double yj = warp_shfl(r[c] * invd_c, j);
       if(upd) r[c] = dfma(-lij, yj, r[c]);
     }
   }
   CCC_UNROLL
-  for(int c = 0; c < NR; c++) r[c] = free_i ? r[c] * invd : 0.0;
-  for(int j = m - 1; j >= 0; j--)
+  for(int c = 0; c < NR; c++) r[c] = in ? r[c] * invd_c : 0.0;
+  CCC_NOUNROLL
+  for(int j = nf - 1; j >= 0; j--)
   {
-    if((clamped >> j) & 1u) continue;
-    const bool upd = free_i && lane < j;
-    double lji = upd ? A[j * kLda + lane] : 0.0;
+    const bool upd = in && lane < j;
+    const double lji = upd ? A[j * kLda + lane] : 0.0;
     CCC_UNROLL
     for(int c = 0; c < NR; c++)
     {
-      double xj = warp_shfl(r[c] * invd, j);
+      const double xj = warp_shfl(r[c] * invd_c, j);
       if(upd) r[c] = dfma(-lji, xj, r[c]);
     }
   }
   CCC_UNROLL
-  for(int c = 0; c < NR; c++) r[c] = free_i ? r[c] * invd : 0.0;
+  for(int c = 0; c < NR; c++) r[c] = in ? r[c] * invd_c : 0.0;
 }
 
 struct BoxQpOut
 {
   int retval;       // boxQP.m result code
-  unsigned clamped; // bit j = input j clamped (matches the factor left in A unless all clamped)
-  double invd;      // 1 / L[lane][lane] of that factor
+  unsigned clamped; // bit j = input j clamped
+  FreeSet fs;       // compact numbering matching the factor left in A (unless all clamped)
+  double invd_c;    // 1 / L[r][r] of that factor, compact numbering
   int iters, nfactor, ls_steps;
 };
 
-/** 0.5 x'Hx + g'x with x published through vb; also returns Hx (row `lane`). */
-CCC_DEV double boxqp_objective(const double (&H)[32], double g, double x, double * vb, int m, bool active, double & Hx)
-{
-  publish(vb, x, active);
-  Hx = matvec32(H, vb, m);
-  double t1 = active ? x * Hx : 0.0;
-  double t2 = active ? x * g : 0.0;
-  return dfma(0.5, warp_sum(t1), warp_sum(t2));
-}
-
 /** One-warp BoxQP.  H: row `lane` of the symmetric Hessian, also stored in the upper triangle
  *  (+diagonal) of the smem tile A; on return H is intact again and A's strict lower triangle
- *  holds the factor of the final free block.  x (in: start point, out: solution), g, lo, hi:
- *  one value per lane.  vb0..vb2: three 32-double smem vectors. */
+ *  holds the compact factor of the final free block.  x (in: start point, out: solution), g,
+ *  lo, hi: one value per lane.  vb: 160 doubles of smem (128 column buffers + 32 publish
+ *  vector); idxbuf: 32 ints. */
 CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
                             double * A,
-                            double * vb0,
-                            double * vb1,
-                            double * vb2,
+                            double * vb,
+                            int * idxbuf,
                             double g,
                             double lo,
                             double hi,
@@ -210,21 +288,65 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
   const int lane = lane_id();
   const bool active = lane < m;
   const unsigned active_mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+  double * pub = vb + 128;
   BoxQpOut out;
   out.retval = 0;
   out.clamped = 0;
-  out.invd = 1.0;
+  out.invd_c = 1.0;
   out.nfactor = 0;
   out.ls_steps = 0;
+  out.iters = 0;
+  out.fs.free_mask = 0;
+  out.fs.nf = 0;
+  out.fs.idx = 0;
+  out.fs.rank = 0;
   x = clampd(x, lo, hi);
-  double Hx;
-  double obj = boxqp_objective(H, g, x, vb2, m, active, Hx);
-  double old_obj = obj;
+  double xc = x, Hx = 0.0, obj = 0.0, old_obj = 0.0;
+  double step = 1.0, sdotg = -1.0, search = 0.0;
   unsigned old_clamped = 0;
-  int iter = 1;
-  for(;; iter++)
+  int phase = 0; // 0: initial objective, 1: first Armijo trial, 2: later Armijo trials
+  int iter = 0;
+  CCC_NOUNROLL
+  for(;;)
   {
+    // ---- the single objective-evaluation site:  0.5 xc'H xc + g'xc  ----
+    publish(pub, xc, active);
+    const double Hxc = matvec32(H, pub, m);
+    const double objc = dfma(0.5, warp_sum(active ? xc * Hxc : 0.0), warp_sum(active ? xc * g : 0.0));
+    if(phase != 0)
+    {
+      const bool ls_fail = (phase == 2 && step < cfg.min_step);
+      if(!ls_fail && ddiv(objc - old_obj, step * sdotg) < cfg.armijo)
+      {
+        step = step * cfg.step_factor;
+        out.ls_steps++;
+        xc = clampd(dfma(step, search, x), lo, hi);
+        phase = 2;
+        continue;
+      }
+      x = xc;
+      Hx = Hxc;
+      obj = objc;
+      if(ls_fail)
+      {
+        out.retval = 2;
+        break;
+      }
+      if(iter >= cfg.max_iter)
+      {
+        out.retval = 1;
+        break;
+      }
+    }
+    else
+    {
+      Hx = Hxc;
+      obj = objc;
+      old_obj = objc;
+    }
+    iter++;
     out.iters = iter;
+    // ---- top of a projected-Newton iteration ----
     if(iter > 1 && (old_obj - obj) < cfg.rel_improve_thre * dabs(old_obj))
     {
       out.retval = 4;
@@ -240,15 +362,17 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
       out.retval = 6;
       break;
     }
-    // gradient with the free part of x removed: g + H (x .* clamped).  Needs H in registers, so it
-    // is evaluated before the factorisation overwrites them (it does not depend on the factor).
-    publish(vb2, x, cl);
-    const double gc = g + matvec32(H, vb2, m);
+    // g + H (x .* clamped): needs H in registers, so it is evaluated before the factorisation
+    // borrows them (it does not depend on the factor)
+    publish(pub, x, cl);
+    const double gc = g + matvec32(H, pub, m);
     if(iter == 1 || clamped != old_clamped)
     {
-      bool ok = llt_factor(H, A, vb0, vb1, clamped, m, out.invd);
-      load_sym_row(H, A, m);
       out.clamped = clamped;
+      out.fs = make_free_set(clamped, m, idxbuf);
+      load_compact_row(H, A, idxbuf, out.fs);
+      const bool ok = llt_factor_compact(H, A, vb, out.fs.nf, out.invd_c);
+      load_sym_row(H, A, m);
       if(!ok)
       {
         out.retval = -1;
@@ -257,52 +381,26 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
       out.nfactor++;
     }
     old_clamped = clamped;
-    out.clamped = clamped;
     const bool free_i = active && !cl;
-    const double gnorm = dsqrt(warp_sum(free_i ? grad * grad : 0.0));
+    const double gnorm = dsqrt_ool(warp_sum(free_i ? grad * grad : 0.0));
     if(gnorm < cfg.grad_thre)
     {
       out.retval = 5;
       break;
     }
-    const double sol = llt_solve1(gc, A, clamped, m, out.invd);
-    const double search = free_i ? (-sol) - x : 0.0;
-    const double sdotg = warp_sum(active ? search * grad : 0.0);
+    const double rhs_c = warp_shfl(gc, out.fs.idx);
+    const double sol_c = llt_solve_compact(rhs_c, A, out.fs.nf, out.invd_c);
+    const double sol = warp_shfl(sol_c, out.fs.rank);
+    search = free_i ? (-sol) - x : 0.0;
+    sdotg = warp_sum(active ? search * grad : 0.0);
     if(sdotg >= 0)
     {
       out.retval = 0;
       break;
     }
-    double step = 1.0;
-    double xc = clampd(dfma(step, search, x), lo, hi);
-    double Hxc;
-    double objc = boxqp_objective(H, g, xc, vb2, m, active, Hxc);
-    bool ls_fail = false;
-    while((objc - old_obj) / (step * sdotg) < cfg.armijo)
-    {
-      step = step * cfg.step_factor;
-      out.ls_steps++;
-      xc = clampd(dfma(step, search, x), lo, hi);
-      objc = boxqp_objective(H, g, xc, vb2, m, active, Hxc);
-      if(step < cfg.min_step)
-      {
-        ls_fail = true;
-        break;
-      }
-    }
-    x = xc;
-    Hx = Hxc;
-    obj = objc;
-    if(ls_fail)
-    {
-      out.retval = 2;
-      break;
-    }
-    if(iter >= cfg.max_iter)
-    {
-      out.retval = 1;
-      break;
-    }
+    step = 1.0;
+    xc = clampd(dfma(step, search, x), lo, hi);
+    phase = 1;
   }
   return out;
 }

@@ -64,18 +64,20 @@ struct CentroidalParams
 // per-warp shared-memory slice, offsets in doubles
 namespace sm
 {
-constexpr int A = 0;                // 32 x kLda tile: upper+diag = Quu_F, strict lower = L
-constexpr int VB0 = A + 32 * kLda;  // three 32-vectors
-constexpr int VB1 = VB0 + 32;
-constexpr int VB2 = VB1 + 32;
-constexpr int VXX = VB2 + 32;       // 9x9 (+1 pad)
+constexpr int A = 0;                // 32 x kLda tile: upper+diag = Quu_F, strict lower = compact L
+constexpr int VB = A + 32 * kLda;   // 160 doubles: BoxQP column buffers (128) + publish vector (32)
+constexpr int VB0 = VB;             // outside BoxQP the same space serves as three 32-vectors
+constexpr int VB1 = VB + 32;
+constexpr int VB2 = VB + 64;
+constexpr int IDX = VB + 160;       // 32 ints: free list of the compact factor
+constexpr int VXX = IDX + 16;       // 9x9 (+1 pad)
 constexpr int VX = VXX + 82;        // 9 (+1)
 constexpr int FX = VX + 10;         // 9x9 dense Fx
 constexpr int T = FX + 82;          // Vxx * Fx
 constexpr int QXX = T + 82;
 constexpr int S2 = QXX + 82;        // scratch 9x9
 constexpr int QX = S2 + 82;
-constexpr int TOTAL = QX + 10;      // 1614 doubles = 12912 bytes
+constexpr int TOTAL = QX + 10;      // 1694 doubles = 13552 bytes
 // aliases inside A, valid while no factor is alive
 constexpr int WT = A;               // [32][6]  rows 3..8 of Vxx*Fu, transposed
 constexpr int KB = A;               // [32][10] K rows
@@ -157,7 +159,7 @@ struct CentroidalWarp
     CCC_UNROLL
     for(int a = 0; a < 3; a++)
     {
-      xdot[a] = x[3 + a] / P.mass;
+      xdot[a] = ddiv(x[3 + a], P.mass);
       xdot[3 + a] = f[a];
       xdot[6 + a] = n[a];
     }
@@ -188,6 +190,7 @@ struct CentroidalWarp
     CCC_UNROLL
     for(int i = 0; i < 9; i++) x[i] = initial ? ldg(P.x0 + (size_t)b * 9 + i) : xn[i];
     double Jc = 0.0;
+    CCC_NOUNROLL
     for(int k = 0; k < N; k++)
     {
       const int m = stage_m(k);
@@ -368,7 +371,7 @@ struct CentroidalWarp
     CCC_UNROLL
     for(int j = 0; j < 32; j++)
     {
-      if(j >= m) break;
+      if(j == 16 && m <= 16) break;
       double acc = 0.0;
       CCC_UNROLL
       for(int r = 0; r < 3; r++)
@@ -381,14 +384,13 @@ struct CentroidalWarp
     }
     double quu_diag = 0.0;
     CCC_UNROLL
-    for(int j = 0; j < 32; j++)
-      if(j == lane) quu_diag = H[j];
+    for(int j = 0; j < 32; j++) quu_diag = (j == lane) ? H[j] : quu_diag;
     warp_sync(); // everyone is done reading WT (aliases A)
     double * A = s + sm::A;
     CCC_UNROLL
     for(int j = 0; j < 32; j++)
     {
-      if(j >= m) break;
+      if(j == 16 && m <= 16) break;
       if(active && j <= lane) A[j * kLda + lane] = (j == lane) ? quu_diag + lambda : H[j];
     }
     warp_sync();
@@ -398,7 +400,7 @@ struct CentroidalWarp
     double kk = 0.0;
     double K[9];
     unsigned clamped = 0;
-    double invd = 1.0;
+    int * idxbuf = reinterpret_cast<int *>(s + sm::IDX);
     if(P.cfg.with_input_constraint)
     {
       const double lo = P.u_lo - u, hi = P.u_hi - u;
@@ -408,22 +410,24 @@ struct CentroidalWarp
         x0 = active ? gain(k)[lane] : 0.0;
       else
         x0 = (m_next == m) ? k_next : 0.0;
-      BoxQpOut r = boxqp_warp(H, A, s + sm::VB0, s + sm::VB1, s + sm::VB2, Qu, lo, hi, x0, m, P.cfg.boxqp);
+      BoxQpOut r = boxqp_warp(H, A, s + sm::VB, idxbuf, Qu, lo, hi, x0, m, P.cfg.boxqp);
       if(r.retval < 1) return false;
       kk = active ? x0 : 0.0;
       clamped = r.clamped;
-      invd = r.invd;
       const unsigned active_mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
-      CCC_UNROLL
-      for(int c = 0; c < 9; c++) K[c] = Qux[c];
       if(clamped != active_mask)
       {
-        llt_solveN<9>(K, A, clamped, m, invd);
+        // K[free,:] = -(Quu_F[free,free])^-1 Qux[free,:] with BoxQP's factor (compact numbering)
         CCC_UNROLL
-        for(int c = 0; c < 9; c++) K[c] = -K[c];
+        for(int c = 0; c < 9; c++) K[c] = warp_shfl(Qux[c], r.fs.idx);
+        llt_solve_compactN<9>(K, A, r.fs.nf, r.invd_c);
         const bool free_i = active && !((clamped >> lane) & 1u);
         CCC_UNROLL
-        for(int c = 0; c < 9; c++) K[c] = free_i ? K[c] : 0.0;
+        for(int c = 0; c < 9; c++)
+        {
+          const double v = warp_shfl(K[c], r.fs.rank);
+          K[c] = free_i ? -v : 0.0;
+        }
       }
       else
       {
@@ -433,14 +437,17 @@ struct CentroidalWarp
     }
     else
     {
-      bool ok = llt_factor(H, A, s + sm::VB0, s + sm::VB1, 0u, m, invd);
+      FreeSet fs = make_free_set(0u, m, idxbuf);
+      double invd_c = 1.0;
+      load_compact_row(H, A, idxbuf, fs);
+      const bool ok = llt_factor_compact(H, A, s + sm::VB, fs.nf, invd_c);
       load_sym_row(H, A, m);
       if(!ok) return false;
       double r10[10];
       r10[0] = Qu;
       CCC_UNROLL
       for(int c = 0; c < 9; c++) r10[1 + c] = Qux[c];
-      llt_solveN<10>(r10, A, 0u, m, invd);
+      llt_solve_compactN<10>(r10, A, fs.nf, invd_c);
       kk = active ? -r10[0] : 0.0;
       CCC_UNROLL
       for(int c = 0; c < 9; c++) K[c] = active ? -r10[1 + c] : 0.0;
@@ -455,15 +462,14 @@ struct CentroidalWarp
       for(int c = 0; c < 9; c++) g[(1 + c) * 32 + lane] = K[c];
       if(active)
       {
-        double r = dabs(kk) / (dabs(u) + 1.0);
+        double r = ddiv(dabs(kk), dabs(u) + 1.0);
         krel = krel < r ? r : krel;
       }
     }
 
     // ---- cost-to-go update with the unregularised Quu ------------------------------------
     CCC_UNROLL
-    for(int j = 0; j < 32; j++)
-      if(j == lane) H[j] = quu_diag;
+    for(int j = 0; j < 32; j++) H[j] = (j == lane) ? quu_diag : H[j]; // selects, not a branch tree
     double * VB0 = s + sm::VB0;
     double * VB1 = s + sm::VB1;
     double * VB2 = s + sm::VB2;
@@ -480,10 +486,10 @@ struct CentroidalWarp
     double Z[9];
     CCC_UNROLL
     for(int c = 0; c < 9; c++) Z[c] = 0.0;
-    CCC_UNROLL
+    CCC_UNROLL_N(4)
     for(int j = 0; j < 32; j++)
     {
-      if(j >= m) break;
+      if(j == 16 && m <= 16) break;
       const double h = H[j];
       d2 k01 = ld2(KB + j * 10 + 0), k23 = ld2(KB + j * 10 + 2), k45 = ld2(KB + j * 10 + 4), k67 = ld2(KB + j * 10 + 6);
       const double k8 = KB[j * 10 + 8];
@@ -514,6 +520,7 @@ struct CentroidalWarp
     if(lane < 9)
     {
       double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      CCC_NOUNROLL
       for(int j = 0; j < m; j++)
       {
         const double kj = KB[j * 10 + lane];
@@ -534,6 +541,7 @@ struct CentroidalWarp
       {
         const int a = e / 9, c = e - 9 * a;
         double s1 = 0.0, s2 = 0.0;
+        CCC_NOUNROLL
         for(int j = 0; j < m; j++)
         {
           const double kj = KB[j * 10 + a];
@@ -597,6 +605,7 @@ struct CentroidalWarp
     krel = 0.0;
     double k_next = 0.0;
     int m_next = -1;
+    CCC_NOUNROLL
     for(int k = N - 1; k >= 0; k--)
     {
       if(!backward_stage(k, k_next, m_next)) return false;
@@ -615,7 +624,7 @@ struct CentroidalWarp
   CCC_DEV void decrease_lambda()
   {
     const double f = P.cfg.lambda_factor;
-    double t = dlambda / f, u = 1.0 / f;
+    double t = ddiv(dlambda, f), u = ddiv(1.0, f);
     dlambda = u < t ? u : t; // std::min(dlambda / f, 1 / f)
     lambda = (lambda * dlambda) * (lambda > P.cfg.lambda_min ? 1.0 : 0.0);
   }
@@ -630,63 +639,9 @@ struct CentroidalWarp
     }
   }
 
-  /** nmpc_ddp procOnce: 0 continue, 1 converged, -1 failed. */
-  CCC_DEV int proc_once(int iter)
-  {
-    while(!backward_pass())
-    {
-      increase_lambda();
-      if(lambda > P.cfg.lambda_max)
-      {
-        trace(iter, -3);
-        return -1;
-      }
-    }
-    const double k_rel_norm = warp_max(krel);
-    if(k_rel_norm < P.cfg.k_rel_norm_thre && lambda < P.cfg.lambda_thre)
-    {
-      decrease_lambda();
-      trace(iter, -2);
-      return 1;
-    }
-    bool success = false;
-    double actual = 0.0;
-    int a_acc = -1;
-    for(int a = 0; a < P.cfg.n_alpha; a++)
-    {
-      const double alpha = P.cfg.alpha[a];
-      const double Jc = rollout(1 - cur, alpha, false);
-      actual = J - Jc;
-      const double expected = -(alpha * dfma(alpha, dV1, dV0));
-      double ratio;
-      if(expected > 0)
-        ratio = actual / expected;
-      else
-        ratio = (double)((0 < actual) - (actual < 0));
-      if(ratio > P.cfg.cost_update_ratio_thre)
-      {
-        success = true;
-        a_acc = a;
-        J = Jc;
-        break;
-      }
-    }
-    int rv = 0;
-    if(success)
-    {
-      decrease_lambda();
-      cur = 1 - cur;
-      if(actual < P.cfg.cost_update_thre) rv = 1;
-    }
-    else
-    {
-      increase_lambda();
-      if(lambda > P.cfg.lambda_max) rv = -1;
-    }
-    trace(iter, success ? a_acc : -1);
-    return rv;
-  }
-
+  /** nmpc_ddp DDPSolver::solve + procOnce as one state machine, so that the forward pass
+   *  (initial rollout and every line-search trial) and the backward pass each have a single
+   *  call site in the instruction stream.  a = -1: initial rollout; a >= 0: line-search index. */
   CCC_DEV void solve()
   {
     const int N = P.N;
@@ -698,14 +653,11 @@ struct CentroidalWarp
     {
       const int i = e / 9, j = e - 9 * i;
       double v = (i == j && e < 81) ? 1.0 : 0.0;
-      if(i < 3 && j == i + 3) v = (1 / P.mass) * P.dt;
+      if(i < 3 && j == i + 3) v = ddiv(1, P.mass) * P.dt;
       s[sm::FX + e] = v;
     }
     // the BoxQP warm start of the last stage reads its own previous gain: zero it
     gain(N - 1)[lane] = 0.0;
-    warp_sync();
-    cur = 0;
-    J = rollout(0, 0.0, true);
     for(int i = lane; i < P.trace_len; i += 32)
     {
       size_t o = (size_t)b * P.trace_len + i;
@@ -713,13 +665,77 @@ struct CentroidalWarp
       if(P.out_lambda) P.out_lambda[o] = 0.0;
     }
     warp_sync();
-    int rv = 0, iter = 0;
-    for(iter = 1; iter <= P.cfg.max_iter; iter++)
+    cur = 0;
+    int rv = 0, iter = 0, a = -1;
+    CCC_NOUNROLL
+    for(;;)
     {
-      rv = proc_once(iter);
-      if(rv != 0) break;
+      const double alpha = a >= 0 ? P.cfg.alpha[a] : 0.0;
+      const double Jc = rollout(a >= 0 ? 1 - cur : 0, alpha, a < 0);
+      if(a < 0)
+      {
+        J = Jc;
+      }
+      else
+      {
+        const double actual = J - Jc;
+        const double expected = -(alpha * dfma(alpha, dV1, dV0));
+        double ratio;
+        if(expected > 0)
+          ratio = ddiv(actual, expected);
+        else
+          ratio = (double)((0 < actual) - (actual < 0));
+        if(ratio > P.cfg.cost_update_ratio_thre)
+        {
+          // accept the step
+          decrease_lambda();
+          cur = 1 - cur;
+          J = Jc;
+          if(actual < P.cfg.cost_update_thre) rv = 1;
+          trace(iter, a);
+        }
+        else if(a + 1 < P.cfg.n_alpha)
+        {
+          a++;
+          continue;
+        }
+        else
+        {
+          // line search failed for every alpha
+          increase_lambda();
+          if(lambda > P.cfg.lambda_max) rv = -1;
+          trace(iter, -1);
+        }
+      }
+      // ---- next iteration: backward pass (with regularisation retries) ----
+      if(rv != 0 || iter >= P.cfg.max_iter) break;
+      iter++;
+      bool gave_up = false;
+      while(!backward_pass())
+      {
+        increase_lambda();
+        if(lambda > P.cfg.lambda_max)
+        {
+          gave_up = true;
+          break;
+        }
+      }
+      if(gave_up)
+      {
+        trace(iter, -3);
+        rv = -1;
+        break;
+      }
+      const double k_rel_norm = warp_max(krel);
+      if(k_rel_norm < P.cfg.k_rel_norm_thre && lambda < P.cfg.lambda_thre)
+      {
+        decrease_lambda();
+        trace(iter, -2);
+        rv = 1;
+        break;
+      }
+      a = 0;
     }
-    if(iter > P.cfg.max_iter) iter = P.cfg.max_iter;
     // outputs
     warp_sync();
     const double * xs = xtraj(cur);

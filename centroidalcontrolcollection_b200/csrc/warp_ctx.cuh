@@ -23,6 +23,7 @@ unsigned ballot(bool p);
 #  define CCC_DEV_NOINLINE
 #  define CCC_UNROLL
 #  define CCC_UNROLL_N(n)
+#  define CCC_NOUNROLL
 namespace ccc
 {
 inline int lane_id() { return ccc_emu::lane(); }
@@ -44,6 +45,7 @@ inline T ldg(const T * p) { return *p; }
 #  define CCC_DEV_NOINLINE __device__ __noinline__
 #  define CCC_UNROLL _Pragma("unroll")
 #  define CCC_UNROLL_N(n) _Pragma("unroll")
+#  define CCC_NOUNROLL _Pragma("unroll 1")
 namespace ccc
 {
 constexpr unsigned kFullMask = 0xffffffffu;
