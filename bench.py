@@ -170,11 +170,15 @@ def run_ours(args, rank, world, local_rank):
     engine.lib()
     if args.variant is not None:
         engine.DdpCentroidalEngine.set_variant(args.variant)
+    if args.chunk is not None:
+        engine.DdpCentroidalEngine.set_chunk(args.chunk)
 
     B = args.batch
     w = workloads.ddp_centroidal_config3(batch=B, seed=20260102 + rank)
     ps = problem.DdpCentroidalProblemSet.from_workload(w)
     cfg = problem.ddp_centroidal_config()
+    if args.max_iter is not None:
+        cfg.max_iter = args.max_iter
     N, S, mm = ps.N, ps.sched.S, ps.m_max
     eng = engine.DdpCentroidalEngine(N, B, S)
 
@@ -319,7 +323,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="problems per GPU per step")
     ap.add_argument("--variant", type=int, default=None, help="launch-shape variant of the solve kernel (tuning)")
+    ap.add_argument("--chunk", type=int, default=None, help="DDP iterations per visit before a solve is re-queued (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-iter", type=int, default=None, help="experiments only: cap DDP iterations (default 500 = nmpc_ddp's)")
     ap.add_argument("--ref-problems-per-thread", type=int, default=24,
                     help="--impl reference: problems per host thread per step (~0.1-0.2 s each)")
     ap.add_argument("--cpu-baseline-problems-per-thread", type=int, default=96,

@@ -44,10 +44,6 @@ CCC_DEV_NOINLINE double ddiv(double a, double b)
 {
   return a / b;
 }
-CCC_DEV_NOINLINE double dsqrt_ool(double a)
-{
-  return dsqrt(a);
-}
 
 struct BoxQpCfg
 {
@@ -55,20 +51,23 @@ struct BoxQpCfg
   double grad_thre, rel_improve_thre, step_factor, min_step, armijo;
 };
 
-/** y_lane = sum_j H[j] * vb[j], ascending j, one fma chain from +0.0.  vb: 32 doubles in smem,
- *  entries j >= m are +0.0 and H[j >= m] is finite, so only the 16-boundary is tested. */
+/** y_lane = sum_j H[j] * vb[j] as four interleaved fma chains (slot j % 4, ascending j, from
+ *  +0.0) combined as (s0 + s1) + (s2 + s3): the oracle's dot4 (oracle/num.hpp).  vb: 32 doubles
+ *  in smem; entries j >= m are +0.0 and H[j >= m] is finite, so only the 16-boundary is tested. */
 CCC_DEV double matvec32(const double (&H)[32], const double * vb, int m)
 {
-  double acc = 0.0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   CCC_UNROLL
-  for(int jj = 0; jj < 16; jj++)
+  for(int q = 0; q < 8; q++)
   {
-    if(jj == 8 && m <= 16) break;
-    d2 v = ld2(vb + 2 * jj);
-    acc = dfma(H[2 * jj], v.x, acc);
-    acc = dfma(H[2 * jj + 1], v.y, acc);
+    if(q == 4 && m <= 16) break;
+    d2 v01 = ld2(vb + 4 * q), v23 = ld2(vb + 4 * q + 2);
+    a0 = dfma(H[4 * q], v01.x, a0);
+    a1 = dfma(H[4 * q + 1], v01.y, a1);
+    a2 = dfma(H[4 * q + 2], v23.x, a2);
+    a3 = dfma(H[4 * q + 3], v23.y, a3);
   }
-  return acc;
+  return (a0 + a1) + (a2 + a3);
 }
 
 /** Publish one value per lane into a 32-double smem vector (inactive lanes publish +0.0). */
@@ -79,16 +78,18 @@ CCC_DEV void publish(double * vb, double v, bool active)
   warp_sync();
 }
 
-/** Reload row `lane` of the symmetric matrix stored in the upper triangle (+diag) of A;
- *  entries j >= m are set to +0.0. */
+/** Reload row `lane` of the symmetric matrix stored in the upper triangle (+diag) of A.  No
+ *  guards: entries outside the m x m block are whatever finite values the tile holds (it is
+ *  zero-filled once per solve and only ever receives finite data); they meet +0.0 in matvec32. */
 CCC_DEV void load_sym_row(double (&H)[32], const double * A, int m)
 {
   const int lane = lane_id();
   CCC_UNROLL
   for(int j = 0; j < 32; j++)
   {
-    int r = j < lane ? j : lane, c = j < lane ? lane : j;
-    H[j] = (j < m && lane < m) ? A[r * kLda + c] : 0.0;
+    if(j == 16 && m <= 16) break;
+    const int r = j < lane ? j : lane, c = j < lane ? lane : j;
+    H[j] = A[r * kLda + c];
   }
 }
 
@@ -101,20 +102,6 @@ struct FreeSet
   int rank;           // compact position of original input `lane` (valid if free)
 };
 
-CCC_DEV int nth_set_bit(unsigned mask, int n)
-{
-#ifdef CCC_WARP_EMU
-  for(int i = 0; i < 32; i++)
-    if((mask >> i) & 1u)
-    {
-      if(n == 0) return i;
-      n--;
-    }
-  return 32;
-#else
-  return (int)__fns(mask, 0, n + 1);
-#endif
-}
 CCC_DEV int popc32(unsigned v)
 {
 #ifdef CCC_WARP_EMU
@@ -124,7 +111,7 @@ CCC_DEV int popc32(unsigned v)
 #endif
 }
 
-/** idxbuf: 32 ints of smem receiving the free list (for the compact row gather). */
+/** idxbuf: 32 ints of smem receiving the free list (slots >= nf are 0). */
 CCC_DEV FreeSet make_free_set(unsigned clamped, int m, int * idxbuf)
 {
   const int lane = lane_id();
@@ -132,41 +119,44 @@ CCC_DEV FreeSet make_free_set(unsigned clamped, int m, int * idxbuf)
   FreeSet fs;
   fs.free_mask = ~clamped & active_mask;
   fs.nf = popc32(fs.free_mask);
-  fs.idx = lane < fs.nf ? nth_set_bit(fs.free_mask, lane) : 0;
   fs.rank = popc32(fs.free_mask & ((1u << lane) - 1u));
   warp_sync();
-  idxbuf[lane] = fs.idx;
+  if(lane >= fs.nf) idxbuf[lane] = 0;
+  if((fs.free_mask >> lane) & 1u) idxbuf[fs.rank] = lane; // inverse of rank: no find-nth-set-bit
   warp_sync();
+  fs.idx = idxbuf[lane];
   return fs;
 }
 
-/** Gather compact row `lane` of H[free,free] from the symmetric tile. */
+/** Gather compact row `lane` of H[free,free] from the symmetric tile (unguarded: lanes and
+ *  columns >= nf pick up finite tile entries that the factorisation never lets through). */
 CCC_DEV void load_compact_row(double (&Hc)[32], const double * A, const int * idxbuf, const FreeSet & fs)
 {
-  const int lane = lane_id();
   CCC_UNROLL
   for(int c = 0; c < 32; c++)
   {
     if((c & 7) == 0 && c >= fs.nf && c > 0) break;
     const int ic = idxbuf[c];
     const int r = ic < fs.idx ? ic : fs.idx, cc = ic < fs.idx ? fs.idx : ic;
-    Hc[c] = (c < fs.nf && lane < fs.nf) ? A[r * kLda + cc] : 0.0;
+    Hc[c] = A[r * kLda + cc];
   }
 }
+
+constexpr int kCbStride = 68; // one column buffer: 32 values (+1 shift) + zero tail up to index 63
 
 /** Dense LL^T of the compact nf x nf block, rows in registers, column loop rolled.
  *  In: Hc = compact row `lane`.  Out: Hc destroyed; A's strict lower triangle holds the compact
  *  factor (row r > col c at A[r][c]); invd_c = 1 / L[lane][lane] (compact numbering).
- *  cb: 128 doubles of smem (two 64-double column buffers whose upper halves stay zero).
+ *  cb: 2 * kCbStride doubles of smem.  Column k is published at offset (k & 1) of buffer (k & 1),
+ *  so that the trailing-update reads start at an even (16-byte aligned) index and pair up.
  *  Returns false (warp-uniform) if a pivot is not > 0. */
 CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int nf, double & invd_c)
 {
   const int lane = lane_id();
   bool ok = true;
-  int par = 0;
   warp_sync(); // earlier readers of cb and of A's lower triangle are done
-  cb[32 + lane] = 0.0;
-  cb[96 + lane] = 0.0;
+  cb[32 + lane] = 0.0;                 // buffer 0: indices 32..63
+  cb[kCbStride + 33 + lane] = 0.0;     // buffer 1: indices 33..64 (index 32 is lane 31's slot)
   CCC_NOUNROLL
   for(int k = 0; k < nf; k++)
   {
@@ -176,24 +166,26 @@ CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int n
       ok = false;
       break;
     }
-    const double d = dsqrt_ool(piv);
-    const double inv = ddiv(1.0, d);
+    const double inv = drcp(dsqrt(piv));
     if(lane == k) invd_c = inv;
     const bool below = lane > k && lane < nf;
     const double l = below ? Hc[0] * inv : 0.0;
-    double * cbuf = cb + par * 64;
-    par ^= 1;
-    cbuf[lane] = l;
+    const int odd = k & 1;
+    double * cbuf = cb + odd * kCbStride;
+    cbuf[lane + odd] = l;
     if(below) A[lane * kLda + k] = l;
     warp_sync();
     // trailing update folded with a shift by one register: entry (lane, k+j) moves to slot j-1
     const int rem = nf - k;
-    const double * col = cbuf + k;
+    const double * col = cbuf + k + odd; // even index: col[2q], col[2q+1] load as one LDS.128
+    Hc[0] = dfma(-l, col[1], Hc[1]);
     CCC_UNROLL
-    for(int j = 1; j < 32; j++)
+    for(int j = 2; j < 32; j += 2)
     {
-      if((j & 7) == 1 && j >= rem) break;
-      Hc[j - 1] = dfma(-l, col[j], Hc[j]);
+      if((j & 7) == 2 && j >= rem) break;
+      const d2 c2 = ld2(col + j);
+      Hc[j - 1] = dfma(-l, c2.x, Hc[j]);
+      if(j + 1 < 32) Hc[j] = dfma(-l, c2.y, Hc[j + 1]);
     }
   }
   warp_sync();
@@ -272,7 +264,7 @@ struct BoxQpOut
 /** One-warp BoxQP.  H: row `lane` of the symmetric Hessian, also stored in the upper triangle
  *  (+diagonal) of the smem tile A; on return H is intact again and A's strict lower triangle
  *  holds the compact factor of the final free block.  x (in: start point, out: solution), g,
- *  lo, hi: one value per lane.  vb: 160 doubles of smem (128 column buffers + 32 publish
+ *  lo, hi: one value per lane.  vb: 2 * kCbStride + 32 doubles of smem (column buffers + publish
  *  vector); idxbuf: 32 ints. */
 CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
                             double * A,
@@ -288,7 +280,7 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
   const int lane = lane_id();
   const bool active = lane < m;
   const unsigned active_mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
-  double * pub = vb + 128;
+  double * pub = vb + 2 * kCbStride;
   BoxQpOut out;
   out.retval = 0;
   out.clamped = 0;
@@ -312,7 +304,9 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     // ---- the single objective-evaluation site:  0.5 xc'H xc + g'xc  ----
     publish(pub, xc, active);
     const double Hxc = matvec32(H, pub, m);
-    const double objc = dfma(0.5, warp_sum(active ? xc * Hxc : 0.0), warp_sum(active ? xc * g : 0.0));
+    double sums[2] = {active ? xc * Hxc : 0.0, active ? xc * g : 0.0};
+    warp_sum_n<2>(sums);
+    const double objc = dfma(0.5, sums[0], sums[1]);
     if(phase != 0)
     {
       const bool ls_fail = (phase == 2 && step < cfg.min_step);
@@ -382,7 +376,7 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     }
     old_clamped = clamped;
     const bool free_i = active && !cl;
-    const double gnorm = dsqrt_ool(warp_sum(free_i ? grad * grad : 0.0));
+    const double gnorm = dsqrt(warp_sum(free_i ? grad * grad : 0.0));
     if(gnorm < cfg.grad_thre)
     {
       out.retval = 5;

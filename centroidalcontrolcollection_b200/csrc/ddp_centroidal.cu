@@ -10,40 +10,98 @@
 
 namespace
 {
-/** Launch shape variants (occupancy vs register budget; picked at run time, see solve()):
- *  the solver core wants ~240 registers when unconstrained; 128 costs a few spills. */
-template<int WARPS, int CTAS>
+constexpr int kResumeFlag = 1 << 30;
+
+/** Work queue shared by all warps of the persistent kernel (device memory).
+ *  slot[i] >= 0: problem id (| kResumeFlag if it is a suspended solve); -1: not published yet.
+ *  Problems 0..B-1 are published up front; a warp that suspends a solve appends it at `tail`, so
+ *  suspended solves come round again after everything that was queued before them. */
+struct SolveQueue
+{
+  int * slot;
+  int * head; // next ticket to hand out
+  int * tail; // next free slot
+  int * done; // finished problems
+  int capacity;
+};
+
+/** Launch shape variants (occupancy vs register budget; picked at run time, see solve()). */
+template<int WARPS, int CTAS, bool CONSTRAINED>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
-    ddp_centroidal_solve_kernel(const __grid_constant__ ccc::CentroidalParams P, int * __restrict__ counter)
+    ddp_centroidal_solve_kernel(const __grid_constant__ ccc::CentroidalParams P, const SolveQueue q)
 {
   extern __shared__ __align__(16) double smem[];
   double * s = smem + (threadIdx.x >> 5) * ccc::sm::TOTAL;
   const int lane = threadIdx.x & 31;
   for(;;)
   {
-    int b = 0;
-    if(lane == 0) b = atomicAdd(counter, 1);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if(b >= P.B) break;
-    ccc::CentroidalWarp w(P, s, b);
-    w.solve();
+    int e = -1;
+    if(lane == 0)
+    {
+      const int ticket = atomicAdd(q.head, 1);
+      if(ticket < q.capacity)
+      {
+        volatile int * vs = q.slot + ticket;
+        volatile int * vd = q.done;
+        for(;;)
+        {
+          e = *vs;
+          if(e >= 0) break;
+          if(*vd >= P.B) break; // everything is finished: nothing will be published any more
+          __nanosleep(256);
+        }
+      }
+    }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if(e < 0) break;
+    // acquire: the previous visit of this problem may have run on another SM
+    __threadfence();
+    const int b = e & (kResumeFlag - 1);
+    ccc::CentroidalWarp<CONSTRAINED> w(P, s, b);
+    const bool finished = w.solve((e & kResumeFlag) != 0);
     __syncwarp();
+    if(lane == 0)
+    {
+      if(finished)
+      {
+        atomicAdd(q.done, 1);
+      }
+      else
+      {
+        __threadfence(); // release: trajectories, gains and resume state before the slot
+        const int t = atomicAdd(q.tail, 1);
+        if(t < q.capacity) *(volatile int *)(q.slot + t) = b | kResumeFlag;
+      }
+    }
+  }
+}
+
+__global__ void init_queue_kernel(SolveQueue q, int B)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < q.capacity) q.slot[i] = i < B ? i : -1;
+  if(i == 0)
+  {
+    *q.head = 0;
+    *q.tail = B;
+    *q.done = 0;
   }
 }
 
 struct Variant
 {
   int warps, ctas;
-  void (*kernel)(const ccc::CentroidalParams, int *);
+  void (*kernel[2])(const ccc::CentroidalParams, const SolveQueue); // [unconstrained, constrained]
 };
+#define CCC_VARIANT(W, C) {W, C, {ddp_centroidal_solve_kernel<W, C, false>, ddp_centroidal_solve_kernel<W, C, true>}}
 const Variant kVariants[] = {
-    {8, 2, ddp_centroidal_solve_kernel<8, 2>}, // 16 warps/SM, 128 registers
-    {4, 3, ddp_centroidal_solve_kernel<4, 3>}, // 12 warps/SM, 168 registers
-    {8, 1, ddp_centroidal_solve_kernel<8, 1>}, //  8 warps/SM, 255 registers
-    {4, 5, ddp_centroidal_solve_kernel<4, 5>}, // 20 warps/SM,  96 registers (smem-limited to 17)
+    CCC_VARIANT(8, 2), // 16 warps/SM, 128 registers
+    CCC_VARIANT(4, 3), // 12 warps/SM, 168 registers
+    CCC_VARIANT(8, 1), //  8 warps/SM, 255 registers
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 int g_variant = 0;
+int g_chunk = 32; // DDP iterations per visit before a solve is suspended and re-queued
 
 /** ridge/vertex [S][N][m_max][3]  ->  tab [S][N][6][32] (component-major, lane-contiguous, zero padded). */
 __global__ void pack_tables_kernel(const double * __restrict__ ridge,
@@ -83,7 +141,10 @@ struct ccc_ddp_centroidal_ws
   int launches = 0;
   // solver workspace
   double *tab = nullptr, *xbuf = nullptr, *ubuf = nullptr, *gains = nullptr, *u32 = nullptr, *uo32 = nullptr;
-  int * counter = nullptr;
+  int * qslot = nullptr; // work queue: slots + head/tail/done
+  int * qctl = nullptr;
+  int qcap = 0;
+  ccc::DdpResume * resume = nullptr;
   // device staging for CCC_MEM_HOST calls (inputs and outputs)
   int *d_sched_id = nullptr, *d_m = nullptr;
   double *d_ridge = nullptr, *d_vertex = nullptr, *d_ref = nullptr, *d_x0 = nullptr, *d_uinit = nullptr;
@@ -157,7 +218,10 @@ ccc_ddp_centroidal_ws_t * ccc_ddp_centroidal_create(int32_t horizon_steps, int32
   ok = ok && devAlloc(ws->gains, B * N * 320);
   ok = ok && devAlloc(ws->u32, B * N * 32);
   ok = ok && devAlloc(ws->uo32, B * N * 32);
-  ok = ok && devAlloc(ws->counter, 1);
+  ws->qcap = (int)(B * 18);
+  ok = ok && devAlloc(ws->qslot, (size_t)ws->qcap);
+  ok = ok && devAlloc(ws->qctl, 4);
+  ok = ok && devAlloc(ws->resume, B);
   ok = ok && devAlloc(ws->d_sched_id, B);
   ok = ok && devAlloc(ws->d_m, S * N);
   ok = ok && devAlloc(ws->d_ridge, S * N * 32 * 3);
@@ -173,10 +237,11 @@ ccc_ddp_centroidal_ws_t * ccc_ddp_centroidal_create(int32_t horizon_steps, int32
   ok = ok && devAlloc(ws->d_clamped, B * N);
   ok = ok && ccc_host::check(cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   for(int v = 0; v < kNumVariants; v++)
-    ok = ok
-         && ccc_host::check(cudaFuncSetAttribute(kVariants[v].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(kVariants[v].warps * ccc::sm::TOTAL * sizeof(double))),
-                            "cudaFuncSetAttribute(smem)");
+    for(int c = 0; c < 2; c++)
+      ok = ok
+           && ccc_host::check(cudaFuncSetAttribute(kVariants[v].kernel[c], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(kVariants[v].warps * ccc::sm::TOTAL * sizeof(double))),
+                              "cudaFuncSetAttribute(smem)");
   if(!ok)
   {
     ccc_ddp_centroidal_destroy(ws);
@@ -188,7 +253,7 @@ ccc_ddp_centroidal_ws_t * ccc_ddp_centroidal_create(int32_t horizon_steps, int32
 void ccc_ddp_centroidal_destroy(ccc_ddp_centroidal_ws_t * ws)
 {
   if(!ws) return;
-  void * ptrs[] = {ws->tab,     ws->xbuf,   ws->ubuf,    ws->gains,  ws->u32,    ws->uo32, ws->counter, ws->d_sched_id,
+  void * ptrs[] = {ws->tab,     ws->xbuf,   ws->ubuf,    ws->gains,  ws->u32,    ws->uo32, ws->qslot, ws->qctl, ws->resume, ws->d_sched_id,
                    ws->d_m,     ws->d_ridge, ws->d_vertex, ws->d_ref, ws->d_x0,   ws->d_uinit, ws->d_x,
                    ws->d_u,     ws->d_cost, ws->d_lambda, ws->d_iters, ws->d_status, ws->d_alpha, ws->d_clamped};
   for(void * p : ptrs)
@@ -318,13 +383,38 @@ int32_t ccc_ddp_centroidal_solve(ccc_ddp_centroidal_ws_t * ws,
   P.out_lambda = o_lambda;
   P.out_clamped = o_clamped;
 
-  if(!check(cudaMemsetAsync(ws->counter, 0, sizeof(int), st), "memset counter")) return CCC_ERR_CUDA;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ws->device);
+  // work queue: every problem once, plus room for re-queued (suspended) solves
   const Variant & var = kVariants[g_variant];
+  void (*kernel)(const ccc::CentroidalParams, const SolveQueue) = var.kernel[cfg->with_input_constraint ? 1 : 0];
+  const size_t smem_bytes = (size_t)var.warps * ccc::sm::TOTAL * sizeof(double);
+  SolveQueue q;
+  q.slot = ws->qslot;
+  q.head = ws->qctl;
+  q.tail = ws->qctl + 1;
+  q.done = ws->qctl + 2;
+  P.chunk_iters = g_chunk;
+  P.resume = ws->resume;
+  if(g_chunk > 0)
+  {
+    // a solve is re-queued at most ceil(max_iter / chunk) - 1 times; fall back to run-to-completion
+    // if that does not fit the queue allocated with the workspace
+    const long long visits = ((long long)cfg->max_iter + g_chunk - 1) / g_chunk + 1;
+    if(visits * B > ws->qcap) P.chunk_iters = 0;
+  }
+  q.capacity = P.chunk_iters > 0 ? ws->qcap : B;
+  init_queue_kernel<<<(q.capacity + 255) / 256, 256, 0, st>>>(q, B);
+  ws->launches++;
+  // persistent grid: exactly the CTAs that are co-resident (warps spin on the queue, so every
+  // launched CTA must be running)
+  int n_sm = 148, per_sm = 0;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ws->device);
+  if(!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, var.warps * 32, smem_bytes), "occupancy"))
+    return CCC_ERR_CUDA;
+  if(per_sm < 1) return ccc_host::fail(CCC_ERR_CUDA, "solve kernel does not fit on an SM");
+  if(per_sm > var.ctas) per_sm = var.ctas;
   int grid = (B + var.warps - 1) / var.warps;
-  if(grid > n_sm * var.ctas) grid = n_sm * var.ctas; // persistent: one resident wave, warps pull problems
-  var.kernel<<<grid, var.warps * 32, (size_t)var.warps * ccc::sm::TOTAL * sizeof(double), st>>>(P, ws->counter);
+  if(grid > n_sm * per_sm) grid = n_sm * per_sm;
+  kernel<<<grid, var.warps * 32, smem_bytes, st>>>(P, q);
   ws->launches++;
   if(!check(cudaGetLastError(), "launch ddp_centroidal_solve_kernel")) return CCC_ERR_CUDA;
 
@@ -361,6 +451,12 @@ int32_t ccc_ddp_centroidal_set_variant(int32_t v)
 {
   if(v >= 0 && v < kNumVariants) g_variant = v;
   return kNumVariants;
+}
+
+/* Tuning hook: DDP iterations per visit before a solve is suspended and re-queued (0 = never). */
+void ccc_ddp_centroidal_set_chunk(int32_t chunk)
+{
+  g_chunk = chunk < 0 ? 0 : chunk;
 }
 
 int32_t ccc_ddp_centroidal_last_launches(const ccc_ddp_centroidal_ws_t * ws)

@@ -16,6 +16,10 @@
 // 81 entries are dealt round-robin to the lanes.  Derivatives Fx/Fu are rebuilt from (x,u)
 // and the stage tables in registers, never stored.  The gain lists k, K spill to HBM in a
 // lane-contiguous layout ([stage][10][32]) so that every access is a 256-byte coalesced row.
+//
+// A solve can be suspended at an iteration boundary and resumed later by any warp (DdpResume):
+// the kernel uses this to time-slice problems round-robin, so that the rare problems that need
+// hundreds of DDP iterations start early instead of forming a serial tail.
 #pragma once
 #include "boxqp_warp.cuh"
 
@@ -32,23 +36,33 @@ struct DdpCfg
   BoxQpCfg boxqp;
 };
 
+/** What survives between two visits of a suspended solve (everything else lives in the
+ *  trajectory / gain buffers in HBM or is rebuilt). */
+struct DdpResume
+{
+  double lambda, dlambda, J;
+  int cur, iter;
+};
+
 struct CentroidalParams
 {
   int N, B, S;
   double dt, mass;
-  const int * sched_id;  // [B]
-  const int * m;         // [S][N]
-  const double * tab;    // [S][N][6][32] packed stage tables: ridge xyz, vertex xyz (lane-contiguous)
+  const int * sched_id;   // [B]
+  const int * m;          // [S][N]
+  const double * tab;     // [S][N][6][32] packed stage tables: ridge xyz, vertex xyz (lane-contiguous)
   const double * ref_pos; // [S][N+1][3]
   double w_run[10], w_term[9];
   double u_lo, u_hi;
   const double * x0;     // [B][9]
   const double * u_init; // [B][N][32] or null
   DdpCfg cfg;
+  int chunk_iters; // > 0: suspend a solve after this many iterations per visit
   // workspace (device)
-  double * xbuf; // [2][B][N+1][9]  nominal / candidate state trajectories (ping-pong)
-  double * ubuf; // [2][B][N][32]
+  double * xbuf;  // [2][B][N+1][9]  nominal / candidate state trajectories (ping-pong)
+  double * ubuf;  // [2][B][N][32]
   double * gains; // [B][N][10][32]  k (row 0) and the 9 columns of K
+  DdpResume * resume; // [B]
   // outputs (device, nullable)
   double * out_x;
   double * out_u;
@@ -64,27 +78,28 @@ struct CentroidalParams
 // per-warp shared-memory slice, offsets in doubles
 namespace sm
 {
-constexpr int A = 0;                // 32 x kLda tile: upper+diag = Quu_F, strict lower = compact L
-constexpr int VB = A + 32 * kLda;   // 160 doubles: BoxQP column buffers (128) + publish vector (32)
-constexpr int VB0 = VB;             // outside BoxQP the same space serves as three 32-vectors
+constexpr int A = 0;                     // 32 x kLda tile: upper+diag = Quu_F, strict lower = compact L
+constexpr int VB = A + 32 * kLda;        // BoxQP column buffers (2 * kCbStride) + publish vector (32)
+constexpr int VB0 = VB;                  // outside BoxQP the same space serves as three 32-vectors
 constexpr int VB1 = VB + 32;
 constexpr int VB2 = VB + 64;
-constexpr int IDX = VB + 160;       // 32 ints: free list of the compact factor
-constexpr int VXX = IDX + 16;       // 9x9 (+1 pad)
-constexpr int VX = VXX + 82;        // 9 (+1)
-constexpr int FX = VX + 10;         // 9x9 dense Fx
-constexpr int T = FX + 82;          // Vxx * Fx
+constexpr int IDX = VB + 2 * kCbStride + 32; // 32 ints: free list of the compact factor
+constexpr int VXX = IDX + 16;            // 9x9 (+1 pad)
+constexpr int VX = VXX + 82;             // 9 (+1)
+constexpr int FX = VX + 10;              // 9x9 dense Fx
+constexpr int T = FX + 82;               // Vxx * Fx
 constexpr int QXX = T + 82;
-constexpr int S2 = QXX + 82;        // scratch 9x9
+constexpr int S2 = QXX + 82;             // scratch 9x9
 constexpr int QX = S2 + 82;
-constexpr int TOTAL = QX + 10;      // 1694 doubles = 13552 bytes
+constexpr int TOTAL = QX + 10;           // 1702 doubles = 13616 bytes
 // aliases inside A, valid while no factor is alive
-constexpr int WT = A;               // [32][6]  rows 3..8 of Vxx*Fu, transposed
-constexpr int KB = A;               // [32][10] K rows
-constexpr int ZB = A + 320;         // [32][10] (Quu K) rows
-constexpr int QB = A + 640;         // [32][10] Qux rows
+constexpr int WT = A;       // [32][6]  rows 3..8 of Vxx*Fu, transposed
+constexpr int KB = A;       // [32][10] K rows
+constexpr int ZB = A + 320; // [32][10] (Quu K) rows
+constexpr int QB = A + 640; // [32][10] Qux rows
 } // namespace sm
 
+template<bool kConstrained>
 struct CentroidalWarp
 {
   const CentroidalParams & P;
@@ -107,12 +122,13 @@ struct CentroidalWarp
   CCC_DEV const double * stage_tab(int k) const { return P.tab + ((size_t)sched * P.N + k) * 192; }
   CCC_DEV const double * ref(int k) const { return P.ref_pos + ((size_t)sched * (P.N + 1) + k) * 3; }
 
-  /** lanes 0..8 store the (warp-uniform) state vector; no dynamic register indexing. */
+  /** lanes 0..8 store the (warp-uniform) state vector: select chain, one predicated store. */
   CCC_DEV void store9(double * dst, const double (&x)[9]) const
   {
+    double v = x[0];
     CCC_UNROLL
-    for(int i = 0; i < 9; i++)
-      if(lane == i) dst[i] = x[i];
+    for(int i = 1; i < 9; i++) v = (lane == i) ? x[i] : v;
+    if(lane < 9) dst[lane] = v;
   }
 
   // ---- problem functions (src/DdpCentroidal.cpp:32-83) -----------------------------------
@@ -143,27 +159,29 @@ struct CentroidalWarp
       d[a] = (active ? ldg(tb + (3 + a) * 32 + lane) : 0.0) - x[a];
     }
     cross3(d, rho, cr);
-    double f[3], n[3];
+    // seven ridge reductions advanced together: force (3), moment (3), |u|^2
+    double r7[7];
     CCC_UNROLL
     for(int a = 0; a < 3; a++)
     {
-      f[a] = warp_sum(active ? u * rho[a] : 0.0);
-      n[a] = warp_sum(active ? u * cr[a] : 0.0);
+      r7[a] = active ? u * rho[a] : 0.0;
+      r7[3 + a] = active ? u * cr[a] : 0.0;
     }
-    const double usq = warp_sum(active ? u * u : 0.0);
+    r7[6] = active ? u * u : 0.0;
+    warp_sum_n<7>(r7);
     double rr[3];
     CCC_UNROLL
     for(int a = 0; a < 3; a++) rr[a] = ldg(ref(k) + a);
-    const double cost = dfma(0.5 * P.w_run[9], usq, 0.5 * quad9(P.w_run, x, rr));
+    const double cost = dfma(0.5 * P.w_run[9], r7[6], 0.5 * quad9(P.w_run, x, rr));
     double xdot[9];
     CCC_UNROLL
     for(int a = 0; a < 3; a++)
     {
       xdot[a] = ddiv(x[3 + a], P.mass);
-      xdot[3 + a] = f[a];
-      xdot[6 + a] = n[a];
+      xdot[3 + a] = r7[a];
+      xdot[6 + a] = r7[3 + a];
     }
-    xdot[5] = f[2] + (-1 * P.mass * 9.80665);
+    xdot[5] = r7[2] + (-1 * P.mass * 9.80665);
     CCC_UNROLL
     for(int i = 0; i < 9; i++) x[i] = dfma(P.dt, xdot[i], x[i]);
     return cost;
@@ -177,7 +195,7 @@ struct CentroidalWarp
     return 0.5 * quad9(P.w_term, x, rr);
   }
 
-  /** Initial rollout (alpha < 0) or line-search forward pass into trajectory buffer `dst`.
+  /** Initial rollout or line-search forward pass into trajectory buffer `dst`.
    *  Returns the summed cost of the produced trajectory. */
   CCC_DEV double rollout(int dst, double alpha, bool initial)
   {
@@ -216,7 +234,7 @@ struct CentroidalWarp
           for(int c = 0; c < 9; c++) fb = dfma(g[(1 + c) * 32 + lane], dx[c], fb);
         }
         u = dfma(alpha, kj, uj) + fb;
-        if(P.cfg.with_input_constraint) u = clampd(u, P.u_lo, P.u_hi);
+        if(kConstrained) u = clampd(u, P.u_lo, P.u_hi);
         if(!active) u = 0.0;
       }
       ud[(size_t)k * 32 + lane] = u;
@@ -230,16 +248,16 @@ struct CentroidalWarp
   }
 
   // ---- backward pass ----------------------------------------------------------------------
-  /** One stage of the backward recursion.  Returns false if BoxQP failed (retval < 1). */
+  /** One stage of the backward recursion.  Returns false if BoxQP / LLT failed. */
   CCC_DEV bool backward_stage(int k, double & k_next, int & m_next)
   {
     const int N = P.N;
     const int m = stage_m(k);
     const bool active = lane < m;
     const double * xn = xtraj(cur) + (size_t)k * 9;
-    double x[9];
+    double x3[3];
     CCC_UNROLL
-    for(int i = 0; i < 9; i++) x[i] = xn[i];
+    for(int i = 0; i < 3; i++) x3[i] = xn[i];
     const double u = active ? utraj(cur)[(size_t)k * 32 + lane] : 0.0;
     const double * tb = stage_tab(k);
     double rho[3], d[3], cr[3];
@@ -247,12 +265,13 @@ struct CentroidalWarp
     for(int a = 0; a < 3; a++)
     {
       rho[a] = active ? ldg(tb + a * 32 + lane) : 0.0;
-      d[a] = (active ? ldg(tb + (3 + a) * 32 + lane) : 0.0) - x[a];
+      d[a] = (active ? ldg(tb + (3 + a) * 32 + lane) : 0.0) - x3[a];
     }
     cross3(d, rho, cr);
     double f[3];
     CCC_UNROLL
-    for(int a = 0; a < 3; a++) f[a] = warp_sum(active ? u * rho[a] : 0.0);
+    for(int a = 0; a < 3; a++) f[a] = active ? u * rho[a] : 0.0;
+    warp_sum_n<3>(f);
 
     // Fx: only the cross-product block changes from stage to stage (rows 6..8, cols 0..2)
     warp_sync();
@@ -274,6 +293,7 @@ struct CentroidalWarp
     double * Qxx = s + sm::QXX;
     double * Qx = s + sm::QX;
     // T = Vxx Fx
+    CCC_NOUNROLL
     for(int e = lane; e < 81; e += 32)
     {
       const int i = e / 9, j = e - 9 * i;
@@ -294,6 +314,7 @@ struct CentroidalWarp
     }
     warp_sync();
     // Qxx = Lxx + Fx' T
+    CCC_NOUNROLL
     for(int e = lane; e < 81; e += 32)
     {
       const int i = e / 9, j = e - 9 * i;
@@ -309,6 +330,7 @@ struct CentroidalWarp
       warp_sync();
       double * Vxxw = s + sm::VXX;
       double * Vxw = s + sm::VX;
+      CCC_NOUNROLL
       for(int e = lane; e < 81; e += 32)
       {
         const int i = e / 9, j = e - 9 * i;
@@ -401,7 +423,7 @@ struct CentroidalWarp
     double K[9];
     unsigned clamped = 0;
     int * idxbuf = reinterpret_cast<int *>(s + sm::IDX);
-    if(P.cfg.with_input_constraint)
+    if(kConstrained)
     {
       const double lo = P.u_lo - u, hi = P.u_hi - u;
       // warm start: gain of the next stage if the dimensions agree (iLQG.m: k(:,min(i+1,N-1)))
@@ -486,7 +508,7 @@ struct CentroidalWarp
     double Z[9];
     CCC_UNROLL
     for(int c = 0; c < 9; c++) Z[c] = 0.0;
-    CCC_UNROLL_N(4)
+    CCC_UNROLL
     for(int j = 0; j < 32; j++)
     {
       if(j == 16 && m <= 16) break;
@@ -503,8 +525,12 @@ struct CentroidalWarp
       Z[7] = dfma(h, k67.y, Z[7]);
       Z[8] = dfma(h, k8, Z[8]);
     }
-    dV0 = dV0 + warp_sum(active ? kk * Qu : 0.0);
-    dV1 = dfma(0.5, warp_sum(active ? kk * Quuk : 0.0), dV1);
+    {
+      double dv[2] = {active ? kk * Qu : 0.0, active ? kk * Quuk : 0.0};
+      warp_sum_n<2>(dv);
+      dV0 = dV0 + dv[0];
+      dV1 = dfma(0.5, dv[1], dV1);
+    }
     CCC_UNROLL
     for(int c = 0; c < 9; c++)
     {
@@ -588,6 +614,7 @@ struct CentroidalWarp
     // terminal cost derivatives (src/DdpCentroidal.cpp:156-177)
     const double * xN = xtraj(cur) + (size_t)N * 9;
     warp_sync();
+    CCC_NOUNROLL
     for(int e = lane; e < 81; e += 32)
     {
       const int i = e / 9, j = e - 9 * i;
@@ -641,14 +668,17 @@ struct CentroidalWarp
 
   /** nmpc_ddp DDPSolver::solve + procOnce as one state machine, so that the forward pass
    *  (initial rollout and every line-search trial) and the backward pass each have a single
-   *  call site in the instruction stream.  a = -1: initial rollout; a >= 0: line-search index. */
-  CCC_DEV void solve()
+   *  call site in the instruction stream.  a = -1: initial rollout; a >= 0: line-search index.
+   *  resume = false: start the solve; true: continue a suspended one (state in P.resume[b]).
+   *  Returns true when the solve terminated (outputs written), false when it was suspended
+   *  after P.chunk_iters iterations of this visit. */
+  CCC_DEV bool solve(bool resume)
   {
     const int N = P.N;
-    lambda = P.cfg.initial_lambda;
-    dlambda = P.cfg.initial_dlambda;
-    // constant part of Fx: identity + (1/mass) dt on the (pos, momentum) block
+    // per-visit shared-memory state: constant part of Fx (identity + (1/mass) dt on the
+    // (pos, momentum) block) and a finite (zero) tile
     warp_sync();
+    CCC_NOUNROLL
     for(int e = lane; e < 82; e += 32)
     {
       const int i = e / 9, j = e - 9 * i;
@@ -656,59 +686,98 @@ struct CentroidalWarp
       if(i < 3 && j == i + 3) v = ddiv(1, P.mass) * P.dt;
       s[sm::FX + e] = v;
     }
-    // the BoxQP warm start of the last stage reads its own previous gain: zero it
-    gain(N - 1)[lane] = 0.0;
-    for(int i = lane; i < P.trace_len; i += 32)
-    {
-      size_t o = (size_t)b * P.trace_len + i;
-      if(P.out_alpha_idx) P.out_alpha_idx[o] = (signed char)-4;
-      if(P.out_lambda) P.out_lambda[o] = 0.0;
-    }
-    warp_sync();
-    cur = 0;
+    CCC_NOUNROLL
+    for(int e = lane; e < 32 * kLda; e += 32) s[sm::A + e] = 0.0;
     int rv = 0, iter = 0, a = -1;
+    bool need_rollout = true;
+    if(!resume)
+    {
+      lambda = P.cfg.initial_lambda;
+      dlambda = P.cfg.initial_dlambda;
+      cur = 0;
+      // the BoxQP warm start of the last stage reads its own previous gain: zero it
+      gain(N - 1)[lane] = 0.0;
+      CCC_NOUNROLL
+      for(int i = lane; i < P.trace_len; i += 32)
+      {
+        size_t o = (size_t)b * P.trace_len + i;
+        if(P.out_alpha_idx) P.out_alpha_idx[o] = (signed char)-4;
+        if(P.out_lambda) P.out_lambda[o] = 0.0;
+      }
+    }
+    else
+    {
+      const DdpResume st = P.resume[b];
+      lambda = st.lambda;
+      dlambda = st.dlambda;
+      J = st.J;
+      cur = st.cur;
+      iter = st.iter;
+      need_rollout = false;
+    }
+    const int iter_entry = iter;
+    warp_sync();
     CCC_NOUNROLL
     for(;;)
     {
-      const double alpha = a >= 0 ? P.cfg.alpha[a] : 0.0;
-      const double Jc = rollout(a >= 0 ? 1 - cur : 0, alpha, a < 0);
-      if(a < 0)
+      if(need_rollout)
       {
-        J = Jc;
-      }
-      else
-      {
-        const double actual = J - Jc;
-        const double expected = -(alpha * dfma(alpha, dV1, dV0));
-        double ratio;
-        if(expected > 0)
-          ratio = ddiv(actual, expected);
-        else
-          ratio = (double)((0 < actual) - (actual < 0));
-        if(ratio > P.cfg.cost_update_ratio_thre)
+        const double alpha = a >= 0 ? P.cfg.alpha[a] : 0.0;
+        const double Jc = rollout(a >= 0 ? 1 - cur : 0, alpha, a < 0);
+        if(a < 0)
         {
-          // accept the step
-          decrease_lambda();
-          cur = 1 - cur;
           J = Jc;
-          if(actual < P.cfg.cost_update_thre) rv = 1;
-          trace(iter, a);
-        }
-        else if(a + 1 < P.cfg.n_alpha)
-        {
-          a++;
-          continue;
         }
         else
         {
-          // line search failed for every alpha
-          increase_lambda();
-          if(lambda > P.cfg.lambda_max) rv = -1;
-          trace(iter, -1);
+          const double actual = J - Jc;
+          const double expected = -(alpha * dfma(alpha, dV1, dV0));
+          double ratio;
+          if(expected > 0)
+            ratio = ddiv(actual, expected);
+          else
+            ratio = (double)((0 < actual) - (actual < 0));
+          if(ratio > P.cfg.cost_update_ratio_thre)
+          {
+            // accept the step
+            decrease_lambda();
+            cur = 1 - cur;
+            J = Jc;
+            if(actual < P.cfg.cost_update_thre) rv = 1;
+            trace(iter, a);
+          }
+          else if(a + 1 < P.cfg.n_alpha)
+          {
+            a++;
+            continue;
+          }
+          else
+          {
+            // line search failed for every alpha
+            increase_lambda();
+            if(lambda > P.cfg.lambda_max) rv = -1;
+            trace(iter, -1);
+          }
         }
       }
+      need_rollout = true;
       // ---- next iteration: backward pass (with regularisation retries) ----
       if(rv != 0 || iter >= P.cfg.max_iter) break;
+      if(P.chunk_iters > 0 && iter - iter_entry >= P.chunk_iters)
+      {
+        if(lane == 0)
+        {
+          DdpResume st;
+          st.lambda = lambda;
+          st.dlambda = dlambda;
+          st.J = J;
+          st.cur = cur;
+          st.iter = iter;
+          P.resume[b] = st;
+        }
+        warp_sync();
+        return false;
+      }
       iter++;
       bool gave_up = false;
       while(!backward_pass())
@@ -741,15 +810,22 @@ struct CentroidalWarp
     const double * xs = xtraj(cur);
     const double * us = utraj(cur);
     if(P.out_x)
+    {
+      CCC_NOUNROLL
       for(int i = lane; i < (N + 1) * 9; i += 32) P.out_x[(size_t)b * (N + 1) * 9 + i] = xs[i];
+    }
     if(P.out_u)
+    {
+      CCC_NOUNROLL
       for(int k = 0; k < N; k++) P.out_u[((size_t)b * N + k) * 32 + lane] = us[(size_t)k * 32 + lane];
+    }
     if(lane == 0)
     {
       if(P.out_cost) P.out_cost[b] = J;
       if(P.out_iters) P.out_iters[b] = iter;
       if(P.out_status) P.out_status[b] = rv;
     }
+    return true;
   }
 };
 } // namespace ccc

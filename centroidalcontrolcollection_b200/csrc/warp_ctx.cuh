@@ -34,6 +34,7 @@ inline int warp_shfl_i(int v, int src) { return ccc_emu::shfl_i(v, src); }
 inline unsigned warp_ballot(bool p) { return ccc_emu::ballot(p); }
 inline double dfma(double a, double b, double c) { return std::fma(a, b, c); }
 inline double dsqrt(double a) { return std::sqrt(a); }
+inline double drcp(double a) { return 1.0 / a; }
 inline double dabs(double a) { return std::fabs(a); }
 template<class T>
 inline T ldg(const T * p) { return *p; }
@@ -57,6 +58,7 @@ CCC_DEV int warp_shfl_i(int v, int src) { return __shfl_sync(kFullMask, v, src);
 CCC_DEV unsigned warp_ballot(bool p) { return __ballot_sync(kFullMask, p); }
 CCC_DEV double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 CCC_DEV double dsqrt(double a) { return __dsqrt_rn(a); }
+CCC_DEV double drcp(double a) { return __drcp_rn(a); } // correctly rounded 1/a == IEEE 1.0 / a
 CCC_DEV double dabs(double a) { return fabs(a); }
 template<class T>
 CCC_DEV T ldg(const T * p) { return __ldg(p); }
@@ -76,6 +78,22 @@ CCC_DEV double warp_sum(double v)
   v = v + warp_shfl_xor(v, 2);
   v = v + warp_shfl_xor(v, 1);
   return v;
+}
+
+/** N independent pairwise-tree sums advanced level by level (same bits as N warp_sum calls,
+ *  but the 2N shuffles of a level are in flight together). */
+template<int N>
+CCC_DEV void warp_sum_n(double (&v)[N])
+{
+  CCC_UNROLL
+  for(int off = 16; off >= 1; off >>= 1)
+  {
+    double t[N];
+    CCC_UNROLL
+    for(int i = 0; i < N; i++) t[i] = warp_shfl_xor(v[i], off);
+    CCC_UNROLL
+    for(int i = 0; i < N; i++) v[i] = v[i] + t[i];
+  }
 }
 
 CCC_DEV double warp_max(double v)

@@ -49,6 +49,8 @@ def lib():
         L.ccc_ddp_centroidal_last_launches.argtypes = [C.c_void_p]
         L.ccc_ddp_centroidal_set_variant.restype = C.c_int32
         L.ccc_ddp_centroidal_set_variant.argtypes = [C.c_int32]
+        L.ccc_ddp_centroidal_set_chunk.restype = None
+        L.ccc_ddp_centroidal_set_chunk.argtypes = [C.c_int32]
         _LIB = L
     return _LIB
 
@@ -100,4 +102,10 @@ class DdpCentroidalEngine:
 
     @staticmethod
     def set_variant(v):
+        """Tuning hook: launch shape of the solve kernel (0: 16 warps/SM, 1: 12, 2: 8)."""
         return int(lib().ccc_ddp_centroidal_set_variant(int(v)))
+
+    @staticmethod
+    def set_chunk(iters):
+        """Tuning hook: DDP iterations per visit before a solve is suspended and re-queued (0 = never)."""
+        lib().ccc_ddp_centroidal_set_chunk(int(iters))

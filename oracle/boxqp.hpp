@@ -94,7 +94,7 @@ struct BoxQp
     double xHx[32], xg[32];
     for(int i = 0; i < m; i++)
     {
-      Hx[i] = dot_seq(H + i * m, 1, x, 1, m);
+      Hx[i] = dot4(H + i * m, 1, x, 1, m);
       xHx[i] = x[i] * Hx[i];
       xg[i] = x[i] * g[i];
     }
@@ -169,7 +169,7 @@ struct BoxQp
 
       // search direction
       for(int i = 0; i < m; i++) xc[i] = clamped[i] ? x[i] : 0.0;
-      for(int i = 0; i < m; i++) gc[i] = g[i] + dot_seq(H + i * m, 1, xc.data(), 1, m);
+      for(int i = 0; i < m; i++) gc[i] = g[i] + dot4(H + i * m, 1, xc.data(), 1, m);
       {
         int nf = llt.nf;
         std::vector<double> rhs(nf);

@@ -367,7 +367,7 @@ struct DdpSolver
       std::vector<double> Quuk(m), QuuK(m * nx), t1(m), t2(m);
       for(int i = 0; i < m; i++)
       {
-        Quuk[i] = dot_seq(Quu.data() + i * m, 1, kk.data(), 1, m);
+        Quuk[i] = dot4(Quu.data() + i * m, 1, kk.data(), 1, m);
         for(int c = 0; c < nx; c++) QuuK[i * nx + c] = dot_seq(Quu.data() + i * m, 1, KK.data() + c, nx, m);
         t1[i] = kk[i] * Qu[i];
         t2[i] = kk[i] * Quuk[i];

@@ -9,7 +9,8 @@
 //   * every multiply-accumulate is an explicit IEEE fma(); the file is compiled with
 //     -ffp-contract=off so the compiler adds or removes none;
 //   * inner products over a state index (<= 13 terms) and matrix products run as one
-//     sequential fma chain in ascending index order starting from +0.0;
+//     sequential fma chain in ascending index order starting from +0.0; matrix-vector products
+//     over the input index use four interleaved chains (dot4);
 //   * scalar / 3-vector reductions over the ridge (input) index use a fixed 32-leaf
 //     stride-halving pairwise tree (tree_sum32), zero padded;
 //   * divisions and square roots are IEEE correctly rounded operations.
@@ -30,6 +31,16 @@ inline double dot_seq(const double * a, int sa, const double * b, int sb, int n)
   double acc = 0.0;
   for(int i = 0; i < n; i++) acc = std::fma(a[i * sa], b[i * sb], acc);
   return acc;
+}
+
+/** Four interleaved fma chains (term i goes to chain i % 4, ascending i, each from +0.0),
+ *  combined as (s0 + s1) + (s2 + s3).  Used for the matrix-vector products over the input index
+ *  (H x in BoxQP, Quu k in the backward pass): the usual 4-way unrolled dot product. */
+inline double dot4(const double * a, int sa, const double * b, int sb, int n)
+{
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for(int i = 0; i < n; i++) s[i & 3] = std::fma(a[i * sa], b[i * sb], s[i & 3]);
+  return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 /** Pairwise tree over 32 zero-padded leaves: level strides 16, 8, 4, 2, 1. */

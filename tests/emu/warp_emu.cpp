@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <vector>
 
@@ -169,6 +170,17 @@ ccc::DdpCfg toCfg(const ccc_ddp_config_t * c)
 }
 } // namespace
 
+namespace
+{
+int g_chunk = 0;
+}
+
+/** Iterations per visit before a solve is suspended and re-queued (0 = never), as in the kernel. */
+extern "C" void ccc_emu_set_chunk(int32_t chunk)
+{
+  g_chunk = chunk;
+}
+
 extern "C" int32_t ccc_emu_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t * bt,
                                                 const ccc_ddp_config_t * c,
                                                 ccc_ddp_result_t * r)
@@ -225,13 +237,34 @@ extern "C" int32_t ccc_emu_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t
   P.out_alpha_idx = reinterpret_cast<signed char *>(r->alpha_idx);
   P.out_lambda = r->lambda_trace;
   P.out_clamped = r->clamped;
+  std::vector<ccc::DdpResume> resume(B);
+  P.resume = resume.data();
+  P.chunk_iters = g_chunk;
   std::vector<double> smem(ccc::sm::TOTAL + 2, 0.0);
-  for(int b = 0; b < B; b++)
+  // the kernel's round-robin queue, replayed by one emulated warp: (problem, resumed?) entries
+  std::deque<std::pair<int, bool>> queue;
+  for(int b = 0; b < B; b++) queue.emplace_back(b, false);
+  while(!queue.empty())
   {
+    const int b = queue.front().first;
+    const bool resumed = queue.front().second;
+    queue.pop_front();
+    bool finished = true;
     ccc_emu::run_warp([&]() {
-      ccc::CentroidalWarp w(P, smem.data(), b);
-      w.solve();
+      bool f;
+      if(P.cfg.with_input_constraint)
+      {
+        ccc::CentroidalWarp<true> w(P, smem.data(), b);
+        f = w.solve(resumed);
+      }
+      else
+      {
+        ccc::CentroidalWarp<false> w(P, smem.data(), b);
+        f = w.solve(resumed);
+      }
+      if(ccc_emu::lane() == 0) finished = f;
     });
+    if(!finished) queue.emplace_back(b, true);
   }
   if(r->u)
     for(size_t bk = 0; bk < (size_t)B * N; bk++)

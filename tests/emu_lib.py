@@ -17,7 +17,8 @@ def lib():
     return _LIB
 
 
-def ddp_centroidal_solve(problem_set, cfg, trace_len=0):
+def ddp_centroidal_solve(problem_set, cfg, trace_len=0, chunk=0):
+    lib().ccc_emu_set_chunk(int(chunk))
     res = problem_set.new_result(trace_len)
     bs, rs = problem_set.as_struct(), res.as_struct()
     rc = lib().ccc_emu_ddp_centroidal_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))

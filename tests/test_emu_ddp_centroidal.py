@@ -8,9 +8,9 @@ import emu_lib
 from parity import assert_ddp_parity
 
 
-def _run(oracle, ps, cfg, trace_len=16):
+def _run(oracle, ps, cfg, trace_len=16, chunk=0):
     ref = oracle.ddp_centroidal_solve(ps, cfg, trace_len=trace_len)
-    got = emu_lib.ddp_centroidal_solve(ps, cfg, trace_len=trace_len)
+    got = emu_lib.ddp_centroidal_solve(ps, cfg, trace_len=trace_len, chunk=chunk)
     assert_ddp_parity(ref, got)
     return ref
 
@@ -20,6 +20,15 @@ def test_short_horizon_to_convergence(oracle):
     ps = problem.DdpCentroidalProblemSet.from_workload(w)
     ref = _run(oracle, ps, problem.ddp_centroidal_config())
     assert (ref.status == 1).all()
+
+
+def test_suspend_and_resume_is_invisible(oracle):
+    """Round-robin time slicing: suspending every 1 or 2 iterations must not change a single bit."""
+    w = workloads.ddp_centroidal_config3(batch=3, horizon_steps=6)
+    ps = problem.DdpCentroidalProblemSet.from_workload(w)
+    for chunk in (1, 2):
+        ref = _run(oracle, ps, problem.ddp_centroidal_config(), chunk=chunk)
+        assert ref.iters.max() > 2
 
 
 def test_all_phase_kinds_few_iterations(oracle):

@@ -9,6 +9,8 @@ build.build()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 max_iter = int(sys.argv[3]) if len(sys.argv) > 3 else 500
+if len(sys.argv) > 4:
+    engine.DdpCentroidalEngine.set_chunk(int(sys.argv[4]))
 engine.DdpCentroidalEngine.set_variant(variant)
 w = workloads.ddp_centroidal_config3(batch=B)
 ps = problem.DdpCentroidalProblemSet.from_workload(w)
