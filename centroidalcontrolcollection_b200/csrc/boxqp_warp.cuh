@@ -39,8 +39,9 @@ CCC_DEV d2 ld2(const double * p)
 #endif
 }
 
-/** IEEE division / square root as shared out-of-line routines (each inline copy is ~40 SASS). */
-CCC_DEV_NOINLINE double ddiv(double a, double b)
+/** IEEE division (inline: an out-of-line routine far from its callers costs instruction-cache
+ *  locality in the hot loops). */
+CCC_DEV double ddiv(double a, double b)
 {
   return a / b;
 }
@@ -149,11 +150,15 @@ constexpr int kCbStride = 68; // one column buffer: 32 values (+1 shift) + zero 
  *  factor (row r > col c at A[r][c]); invd_c = 1 / L[lane][lane] (compact numbering).
  *  cb: 2 * kCbStride doubles of smem.  Column k is published at offset (k & 1) of buffer (k & 1),
  *  so that the trailing-update reads start at an even (16-byte aligned) index and pair up.
+ *  rhs_c (compact numbering): in b, out y = L^-1 b — the forward substitution is carried along
+ *  column by column in the oracle's order (acc_i = fma(-L[i][k], y_k, acc_i), k ascending).
  *  Returns false (warp-uniform) if a pivot is not > 0. */
-CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int nf, double & invd_c)
+CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int nf, double & invd_c, double & rhs_c)
 {
   const int lane = lane_id();
   bool ok = true;
+  double rhs = lane < nf ? rhs_c : 0.0;
+  double y = 0.0;
   warp_sync(); // earlier readers of cb and of A's lower triangle are done
   cb[32 + lane] = 0.0;                 // buffer 0: indices 32..63
   cb[kCbStride + 33 + lane] = 0.0;     // buffer 1: indices 33..64 (index 32 is lane 31's slot)
@@ -161,15 +166,22 @@ CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int n
   for(int k = 0; k < nf; k++)
   {
     const double piv = warp_shfl(Hc[0], k);
+    const double rk = warp_shfl(rhs, k);
     if(!(piv > 0.0))
     {
       ok = false;
       break;
     }
     const double inv = drcp(dsqrt(piv));
-    if(lane == k) invd_c = inv;
+    const double yk = rk * inv; // forward substitution rides along: y_k = acc_k / L[k][k]
+    if(lane == k)
+    {
+      invd_c = inv;
+      y = yk;
+    }
     const bool below = lane > k && lane < nf;
     const double l = below ? Hc[0] * inv : 0.0;
+    if(below) rhs = dfma(-l, yk, rhs);
     const int odd = k & 1;
     double * cbuf = cb + odd * kCbStride;
     cbuf[lane + odd] = l;
@@ -189,27 +201,36 @@ CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int n
     }
   }
   warp_sync();
+  rhs_c = y;
   return ok;
 }
 
-/** Solve (L L') s = rhs on the compact block: rhs/solution in compact numbering (lane r). */
-CCC_DEV double llt_solve_compact(double rhs_c, const double * A, int nf, double invd_c)
+/** Back substitution L' x = y on the compact block (y, x in compact numbering, lane r). */
+CCC_DEV double llt_back_compact(double y_c, const double * A, int nf, double invd_c)
 {
   const int lane = lane_id();
   const bool in = lane < nf;
-  double acc = in ? rhs_c : 0.0;
-  CCC_NOUNROLL
-  for(int j = 0; j < nf; j++)
-  {
-    const double yj = warp_shfl(acc * invd_c, j);
-    if(in && lane > j) acc = dfma(-A[lane * kLda + j], yj, acc);
-  }
-  acc = in ? acc * invd_c : 0.0;
-  CCC_NOUNROLL
+  double acc = in ? y_c : 0.0;
+  CCC_UNROLL_N(2)
   for(int j = nf - 1; j >= 0; j--)
   {
     const double xj = warp_shfl(acc * invd_c, j);
     if(in && lane < j) acc = dfma(-A[j * kLda + lane], xj, acc);
+  }
+  return in ? acc * invd_c : 0.0;
+}
+
+/** Forward substitution L y = b on the compact block (used when the factor is reused). */
+CCC_DEV double llt_fwd_compact(double rhs_c, const double * A, int nf, double invd_c)
+{
+  const int lane = lane_id();
+  const bool in = lane < nf;
+  double acc = in ? rhs_c : 0.0;
+  CCC_UNROLL_N(2)
+  for(int j = 0; j < nf; j++)
+  {
+    const double yj = warp_shfl(acc * invd_c, j);
+    if(in && lane > j) acc = dfma(-A[lane * kLda + j], yj, acc);
   }
   return in ? acc * invd_c : 0.0;
 }
@@ -360,12 +381,14 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     // borrows them (it does not depend on the factor)
     publish(pub, x, cl);
     const double gc = g + matvec32(H, pub, m);
+    double y_c;
     if(iter == 1 || clamped != old_clamped)
     {
       out.clamped = clamped;
       out.fs = make_free_set(clamped, m, idxbuf);
       load_compact_row(H, A, idxbuf, out.fs);
-      const bool ok = llt_factor_compact(H, A, vb, out.fs.nf, out.invd_c);
+      y_c = warp_shfl(gc, out.fs.idx);
+      const bool ok = llt_factor_compact(H, A, vb, out.fs.nf, out.invd_c, y_c);
       load_sym_row(H, A, m);
       if(!ok)
       {
@@ -373,6 +396,10 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
         break;
       }
       out.nfactor++;
+    }
+    else
+    {
+      y_c = llt_fwd_compact(warp_shfl(gc, out.fs.idx), A, out.fs.nf, out.invd_c);
     }
     old_clamped = clamped;
     const bool free_i = active && !cl;
@@ -382,8 +409,7 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
       out.retval = 5;
       break;
     }
-    const double rhs_c = warp_shfl(gc, out.fs.idx);
-    const double sol_c = llt_solve_compact(rhs_c, A, out.fs.nf, out.invd_c);
+    const double sol_c = llt_back_compact(y_c, A, out.fs.nf, out.invd_c);
     const double sol = warp_shfl(sol_c, out.fs.rank);
     search = free_i ? (-sol) - x : 0.0;
     sdotg = warp_sum(active ? search * grad : 0.0);

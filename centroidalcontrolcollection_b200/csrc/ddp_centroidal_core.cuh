@@ -159,8 +159,8 @@ struct CentroidalWarp
       d[a] = (active ? ldg(tb + (3 + a) * 32 + lane) : 0.0) - x[a];
     }
     cross3(d, rho, cr);
-    // seven ridge reductions advanced together: force (3), moment (3), |u|^2
-    double r7[7];
+    // seven ridge reductions in one transpose-reduce: force (3), moment (3), |u|^2
+    double r7[8];
     CCC_UNROLL
     for(int a = 0; a < 3; a++)
     {
@@ -168,7 +168,8 @@ struct CentroidalWarp
       r7[3 + a] = active ? u * cr[a] : 0.0;
     }
     r7[6] = active ? u * u : 0.0;
-    warp_sum_n<7>(r7);
+    r7[7] = 0.0;
+    warp_sum8(r7, s + sm::S2);
     double rr[3];
     CCC_UNROLL
     for(int a = 0; a < 3; a++) rr[a] = ldg(ref(k) + a);
@@ -462,7 +463,8 @@ struct CentroidalWarp
       FreeSet fs = make_free_set(0u, m, idxbuf);
       double invd_c = 1.0;
       load_compact_row(H, A, idxbuf, fs);
-      const bool ok = llt_factor_compact(H, A, s + sm::VB, fs.nf, invd_c);
+      double dummy = 0.0;
+      const bool ok = llt_factor_compact(H, A, s + sm::VB, fs.nf, invd_c, dummy);
       load_sym_row(H, A, m);
       if(!ok) return false;
       double r10[10];

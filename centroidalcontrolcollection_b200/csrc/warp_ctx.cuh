@@ -45,7 +45,8 @@ inline T ldg(const T * p) { return *p; }
 #  define CCC_DEV __device__ __forceinline__
 #  define CCC_DEV_NOINLINE __device__ __noinline__
 #  define CCC_UNROLL _Pragma("unroll")
-#  define CCC_UNROLL_N(n) _Pragma("unroll")
+#  define CCC_STR_(x) #x
+#  define CCC_UNROLL_N(n) _Pragma(CCC_STR_(unroll n))
 #  define CCC_NOUNROLL _Pragma("unroll 1")
 namespace ccc
 {
@@ -94,6 +95,50 @@ CCC_DEV void warp_sum_n(double (&v)[N])
     CCC_UNROLL
     for(int i = 0; i < N; i++) v[i] = v[i] + t[i];
   }
+}
+
+/** Eight pairwise-tree sums at once by halving the value set at each butterfly level
+ *  ("transpose-reduce"): level 16 exchanges 4 of the 8 values, level 8 two, level 4 one, levels
+ *  2 and 1 finish the single value a lane is left with — 9 shuffles instead of 40.  Every value
+ *  still goes through the same (16, 8, 4, 2, 1) pairwise tree as warp_sum, so the bits are
+ *  identical.  The 8 totals are then broadcast through `xch` (8 doubles of shared memory). */
+CCC_DEV void warp_sum8(double (&v)[8], double * xch)
+{
+  const int lane = lane_id();
+  {
+    const bool up = (lane & 16) != 0;
+    CCC_UNROLL
+    for(int i = 0; i < 4; i++)
+    {
+      const double send = up ? v[i] : v[4 + i];
+      const double keep = up ? v[4 + i] : v[i];
+      v[i] = keep + warp_shfl_xor(send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+    CCC_UNROLL
+    for(int i = 0; i < 2; i++)
+    {
+      const double send = up ? v[i] : v[2 + i];
+      const double keep = up ? v[2 + i] : v[i];
+      v[i] = keep + warp_shfl_xor(send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    const double send = up ? v[0] : v[1];
+    const double keep = up ? v[1] : v[0];
+    v[0] = keep + warp_shfl_xor(send, 4);
+  }
+  v[0] = v[0] + warp_shfl_xor(v[0], 2);
+  v[0] = v[0] + warp_shfl_xor(v[0], 1);
+  // lane holds the total of value ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)
+  warp_sync();
+  if((lane & 3) == 0) xch[((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = v[0];
+  warp_sync();
+  CCC_UNROLL
+  for(int i = 0; i < 8; i++) v[i] = xch[i];
 }
 
 CCC_DEV double warp_max(double v)
