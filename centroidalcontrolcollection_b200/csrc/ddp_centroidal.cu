@@ -100,7 +100,7 @@ const Variant kVariants[] = {
     CCC_VARIANT(8, 1), //  8 warps/SM, 255 registers
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-int g_variant = 0;
+int g_variant = 2; // measured best on B200 (profiles/r01_summary.md): 8 warps/SM, no spills, least I-cache pressure
 int g_chunk = 32; // DDP iterations per visit before a solve is suspended and re-queued
 
 /** ridge/vertex [S][N][m_max][3]  ->  tab [S][N][6][32] (component-major, lane-contiguous, zero padded). */
