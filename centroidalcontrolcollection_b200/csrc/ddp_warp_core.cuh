@@ -1,21 +1,21 @@
-// ddp_centroidal_core.cuh — one warp solves one DdpCentroidal problem (9 states, <= 32 ridge
-// force scales per stage, box limits), start to finish.
+// ddp_warp_core.cuh — one warp solves one DDP problem with ridge-force inputs (<= 32 per stage,
+// box limits) start to finish; generic over the dynamics model M (CentroidalModel: 9 states,
+// SrbModel: 12 states).
 //
 // Replaces (reference file:line):
-//   nmpc_ddp::DDPSolver<9,Dynamic>::solve         call sites src/DdpCentroidal.cpp:229,233
-//   DdpCentroidal::DdpProblem::stateEq            src/DdpCentroidal.cpp:32-64
-//   ...::runningCost / terminalCost               src/DdpCentroidal.cpp:66-83
-//   ...::calcStateEqDeriv                         src/DdpCentroidal.cpp:85-121
-//   ...::calcRunningCostDeriv / TerminalCostDeriv src/DdpCentroidal.cpp:123-177
-//   input limits                                  src/DdpCentroidal.cpp:202-210
-// Algorithm and evaluation order: oracle/ddp.hpp, oracle/centroidal.hpp (bit-exact).
+//   nmpc_ddp::DDPSolver<NX,Dynamic>::solve   call sites src/DdpCentroidal.cpp:229,233,
+//                                            src/DdpSingleRigidBody.cpp:299,303
+//   the DdpProblem callbacks it makes        src/DdpCentroidal.cpp:21-177,
+//                                            src/DdpSingleRigidBody.cpp:41-245  (model_*.cuh)
+//   input limits                             src/DdpCentroidal.cpp:202-210, src/DdpSingleRigidBody.cpp:272-280
+// Algorithm and evaluation order: oracle/ddp.hpp (bit-exact where the model uses no libm).
 //
 // Work split inside the warp: lane j owns input (ridge) j — its vertex/ridge pair, its
-// column of Fu, row j of Quu (32 FP64 registers), row j of Qux / K / Quu*K.  State-sized
-// objects (Vx, Vxx, Fx, Vxx*Fx, Qxx; 9x9) live in the warp's shared-memory slice and their
-// 81 entries are dealt round-robin to the lanes.  Derivatives Fx/Fu are rebuilt from (x,u)
-// and the stage tables in registers, never stored.  The gain lists k, K spill to HBM in a
-// lane-contiguous layout ([stage][10][32]) so that every access is a 256-byte coalesced row.
+// column of Fu (6 non-zero rows starting at M::R0), row j of Quu (32 FP64 registers), row j of
+// Qux / K / Quu*K.  State-sized objects (Vx, Vxx, Fx, Vxx*Fx, Qxx; NX x NX) live in the warp's
+// shared-memory slice and their entries are dealt round-robin to the lanes.  Derivatives Fx/Fu
+// are rebuilt from (x,u) and the stage tables in registers, never stored.  The gain lists k, K
+// spill to HBM in a lane-contiguous layout ([stage][1+NX][32]): every access is a 256-byte row.
 //
 // A solve can be suspended at an iteration boundary and resumed later by any warp (DdpResume):
 // the kernel uses this to time-slice problems round-robin, so that the rare problems that need
@@ -44,24 +44,26 @@ struct DdpResume
   int cur, iter;
 };
 
-struct CentroidalParams
+template<class M>
+struct DdpParams
 {
   int N, B, S;
-  double dt, mass;
   const int * sched_id;   // [B]
   const int * m;          // [S][N]
-  const double * tab;     // [S][N][6][32] packed stage tables: ridge xyz, vertex xyz (lane-contiguous)
-  const double * ref_pos; // [S][N+1][3]
-  double w_run[10], w_term[9];
+  const double * tab;     // [S][N][M::TAB_ROWS][32] packed stage tables (lane-contiguous rows)
+  const double * ref;     // [S][N+1][M::NREF] reference of the first NREF states
+  double w_run[M::NX + 1]; // diagonal running weights of the states, then the force weight
+  double w_term[M::NX];    // diagonal terminal weights
+  typename M::Params mp;   // model constants (dt, mass, ...)
   double u_lo, u_hi;
-  const double * x0;     // [B][9]
+  const double * x0;     // [B][NX]
   const double * u_init; // [B][N][32] or null
   DdpCfg cfg;
   int chunk_iters; // > 0: suspend a solve after this many iterations per visit
   // workspace (device)
-  double * xbuf;  // [2][B][N+1][9]  nominal / candidate state trajectories (ping-pong)
+  double * xbuf;  // [2][B][N+1][NX]  nominal / candidate state trajectories (ping-pong)
   double * ubuf;  // [2][B][N][32]
-  double * gains; // [B][N][10][32]  k (row 0) and the 9 columns of K
+  double * gains; // [B][N][1+NX][32]  k (row 0) and the NX columns of K
   DdpResume * resume; // [B]
   // outputs (device, nullable)
   double * out_x;
@@ -76,124 +78,101 @@ struct CentroidalParams
 };
 
 // per-warp shared-memory slice, offsets in doubles
-namespace sm
+template<int NX, int NXP>
+struct SmLayout
 {
-constexpr int A = 0;                     // 32 x kLda tile: upper+diag = Quu_F, strict lower = compact L
-constexpr int VB = A + 32 * kLda;        // BoxQP column buffers (2 * kCbStride) + publish vector (32)
-constexpr int VB0 = VB;                  // outside BoxQP the same space serves as three 32-vectors
-constexpr int VB1 = VB + 32;
-constexpr int VB2 = VB + 64;
-constexpr int IDX = VB + 2 * kCbStride + 32; // 32 ints: free list of the compact factor
-constexpr int VXX = IDX + 16;            // 9x9 (+1 pad)
-constexpr int VX = VXX + 82;             // 9 (+1)
-constexpr int FX = VX + 10;              // 9x9 dense Fx
-constexpr int T = FX + 82;               // Vxx * Fx
-constexpr int QXX = T + 82;
-constexpr int S2 = QXX + 82;             // scratch 9x9
-constexpr int QX = S2 + 82;
-constexpr int TOTAL = QX + 10;           // 1702 doubles = 13616 bytes
-// aliases inside A, valid while no factor is alive
-constexpr int WT = A;       // [32][6]  rows 3..8 of Vxx*Fu, transposed
-constexpr int KB = A;       // [32][10] K rows
-constexpr int ZB = A + 320; // [32][10] (Quu K) rows
-constexpr int QB = A + 640; // [32][10] Qux rows
-} // namespace sm
+  static constexpr int NN = NX * NX + ((NX * NX) & 1);         // NX x NX matrix, even-padded
+  static constexpr int NV = NX + (NX & 1);                      // NX vector, even-padded
+  static constexpr int A = 0;                                   // 32 x kLda tile: upper+diag = Quu_F, strict lower = compact L
+  static constexpr int VB = A + 32 * kLda;                      // BoxQP column buffers (2 * kCbStride) + publish vector (32)
+  static constexpr int IDX = VB + 2 * kCbStride + 32;           // 32 ints: free list of the compact factor
+  static constexpr int VXX = IDX + 16;
+  static constexpr int VX = VXX + NN;
+  static constexpr int FX = VX + NV;                            // dense Fx
+  static constexpr int T = FX + NN;                             // Vxx * Fx
+  static constexpr int QXX = T + NN;
+  static constexpr int S2 = QXX + NN;                           // scratch NX x NX
+  static constexpr int QX = S2 + NN;
+  static constexpr int TOTAL = QX + NV;
+  // aliases inside A (+ the start of VB), valid while no factor is alive
+  static constexpr int WT = A;                                  // [32][6]  the 6 live rows of Vxx*Fu, transposed
+  static constexpr int KB = A;                                  // [32][NXP] K rows
+  static constexpr int ZB = A + 32 * NXP;                       // [32][NXP] (Quu K) rows
+  static constexpr int QB = A + 64 * NXP;                       // [32][NXP] Qux rows
+  static constexpr int VB0 = A + 96 * NXP;                      // three 32-vectors: k, Quu k, Qu
+  static constexpr int VB1 = VB0 + 32;
+  static constexpr int VB2 = VB0 + 64;
+  static_assert(VB2 + 32 <= IDX, "cost-to-go scratch must fit in the tile + BoxQP buffers");
+  static_assert(NXP % 2 == 0 && NXP >= NX, "row stride of the K/Z/Q buffers");
+};
 
-template<bool kConstrained>
-struct CentroidalWarp
+template<class M, bool kConstrained>
+struct DdpWarp
 {
-  const CentroidalParams & P;
+  static constexpr int NX = M::NX, NXP = M::NXP, R0 = M::R0, NREF = M::NREF;
+  using sm = SmLayout<NX, NXP>;
+  const DdpParams<M> & P;
   double * s; // this warp's shared-memory slice
   int b, sched, lane;
   int cur; // index of the nominal trajectory buffer (0/1)
   double lambda, dlambda, dV0, dV1, J;
   double krel; // running max of |k|/(|u|+1) of the last backward pass (per lane)
 
-  CCC_DEV CentroidalWarp(const CentroidalParams & p, double * smem, int prob)
+  CCC_DEV DdpWarp(const DdpParams<M> & p, double * smem, int prob)
   : P(p), s(smem), b(prob), sched(p.sched_id[prob]), lane(lane_id()), cur(0), lambda(0), dlambda(0), dV0(0), dV1(0),
     J(0), krel(0)
   {
   }
 
-  CCC_DEV double * xtraj(int which) const { return P.xbuf + ((size_t)which * P.B + b) * (size_t)(P.N + 1) * 9; }
+  CCC_DEV double * xtraj(int which) const { return P.xbuf + ((size_t)which * P.B + b) * (size_t)(P.N + 1) * NX; }
   CCC_DEV double * utraj(int which) const { return P.ubuf + ((size_t)which * P.B + b) * (size_t)P.N * 32; }
-  CCC_DEV double * gain(int k) const { return P.gains + ((size_t)b * P.N + k) * 320; }
+  CCC_DEV double * gain(int k) const { return P.gains + ((size_t)b * P.N + k) * (32 * (1 + NX)); }
   CCC_DEV int stage_m(int k) const { return ldg(P.m + (size_t)sched * P.N + k); }
-  CCC_DEV const double * stage_tab(int k) const { return P.tab + ((size_t)sched * P.N + k) * 192; }
-  CCC_DEV const double * ref(int k) const { return P.ref_pos + ((size_t)sched * (P.N + 1) + k) * 3; }
+  CCC_DEV const double * stage_tab(int k) const { return P.tab + ((size_t)sched * P.N + k) * (32 * M::TAB_ROWS); }
+  CCC_DEV const double * ref(int k) const { return P.ref + ((size_t)sched * (P.N + 1) + k) * NREF; }
 
-  /** lanes 0..8 store the (warp-uniform) state vector: select chain, one predicated store. */
-  CCC_DEV void store9(double * dst, const double (&x)[9]) const
+  /** lanes 0..NX-1 store the (warp-uniform) state vector: select chain, one predicated store. */
+  CCC_DEV void storeX(double * dst, const double (&x)[NX]) const
   {
     double v = x[0];
     CCC_UNROLL
-    for(int i = 1; i < 9; i++) v = (lane == i) ? x[i] : v;
-    if(lane < 9) dst[lane] = v;
+    for(int i = 1; i < NX; i++) v = (lane == i) ? x[i] : v;
+    if(lane < NX) dst[lane] = v;
   }
 
-  // ---- problem functions (src/DdpCentroidal.cpp:32-83) -----------------------------------
-  CCC_DEV static double quad9(const double * w, const double * x, const double * r)
+  /** sum_a w[a] (x[a] - r[a])^2 over the referenced states, then sum_a w[a] x[a]^2 over the rest
+   *  (the diagonal quadratic costs of src/DdpCentroidal.cpp:66-83, src/DdpSingleRigidBody.cpp:93-113). */
+  CCC_DEV static double quad(const double * w, const double (&x)[NX], const double * r)
   {
     double c = 0.0;
     CCC_UNROLL
-    for(int a = 0; a < 3; a++)
+    for(int a = 0; a < NREF; a++)
     {
       double d = x[a] - r[a];
       c = dfma(w[a], d * d, c);
     }
     CCC_UNROLL
-    for(int a = 3; a < 9; a++) c = dfma(w[a], x[a] * x[a], c);
+    for(int a = NREF; a < NX; a++) c = dfma(w[a], x[a] * x[a], c);
     return c;
   }
 
   /** x <- stateEq(x, u); returns runningCost(x, u) of the stage (all lanes hold x; lane j holds u_j). */
-  CCC_DEV double step_and_cost(int k, int m, double (&x)[9], double u)
+  CCC_DEV double step_and_cost(int k, int m, double (&x)[NX], double u)
   {
-    const bool active = lane < m;
-    const double * tb = stage_tab(k);
-    double rho[3], d[3], cr[3];
+    double rr[NREF];
     CCC_UNROLL
-    for(int a = 0; a < 3; a++)
-    {
-      rho[a] = active ? ldg(tb + a * 32 + lane) : 0.0;
-      d[a] = (active ? ldg(tb + (3 + a) * 32 + lane) : 0.0) - x[a];
-    }
-    cross3(d, rho, cr);
-    // seven ridge reductions in one transpose-reduce: force (3), moment (3), |u|^2
-    double r7[8];
-    CCC_UNROLL
-    for(int a = 0; a < 3; a++)
-    {
-      r7[a] = active ? u * rho[a] : 0.0;
-      r7[3 + a] = active ? u * cr[a] : 0.0;
-    }
-    r7[6] = active ? u * u : 0.0;
-    r7[7] = 0.0;
-    warp_sum8(r7, s + sm::S2);
-    double rr[3];
-    CCC_UNROLL
-    for(int a = 0; a < 3; a++) rr[a] = ldg(ref(k) + a);
-    const double cost = dfma(0.5 * P.w_run[9], r7[6], 0.5 * quad9(P.w_run, x, rr));
-    double xdot[9];
-    CCC_UNROLL
-    for(int a = 0; a < 3; a++)
-    {
-      xdot[a] = ddiv(x[3 + a], P.mass);
-      xdot[3 + a] = r7[a];
-      xdot[6 + a] = r7[3 + a];
-    }
-    xdot[5] = r7[2] + (-1 * P.mass * 9.80665);
-    CCC_UNROLL
-    for(int i = 0; i < 9; i++) x[i] = dfma(P.dt, xdot[i], x[i]);
-    return cost;
+    for(int a = 0; a < NREF; a++) rr[a] = ldg(ref(k) + a);
+    const double q = quad(P.w_run, x, rr);
+    const double usq = M::step(*this, k, m, x, u);
+    return dfma(0.5 * P.w_run[NX], usq, 0.5 * q);
   }
 
-  CCC_DEV double terminal_cost(const double (&x)[9])
+  CCC_DEV double terminal_cost(const double (&x)[NX])
   {
-    double rr[3];
+    double rr[NREF];
     CCC_UNROLL
-    for(int a = 0; a < 3; a++) rr[a] = ldg(ref(P.N) + a);
-    return 0.5 * quad9(P.w_term, x, rr);
+    for(int a = 0; a < NREF; a++) rr[a] = ldg(ref(P.N) + a);
+    return 0.5 * quad(P.w_term, x, rr);
   }
 
   /** Initial rollout or line-search forward pass into trajectory buffer `dst`.
@@ -205,9 +184,9 @@ struct CentroidalWarp
     double * ud = utraj(dst);
     const double * xn = xtraj(cur);
     const double * un = utraj(cur);
-    double x[9];
+    double x[NX];
     CCC_UNROLL
-    for(int i = 0; i < 9; i++) x[i] = initial ? ldg(P.x0 + (size_t)b * 9 + i) : xn[i];
+    for(int i = 0; i < NX; i++) x[i] = initial ? ldg(P.x0 + (size_t)b * NX + i) : xn[i];
     double Jc = 0.0;
     CCC_NOUNROLL
     for(int k = 0; k < N; k++)
@@ -221,9 +200,9 @@ struct CentroidalWarp
       }
       else
       {
-        double dx[9];
+        double dx[NX];
         CCC_UNROLL
-        for(int c = 0; c < 9; c++) dx[c] = x[c] - xn[(size_t)k * 9 + c];
+        for(int c = 0; c < NX; c++) dx[c] = x[c] - xn[(size_t)k * NX + c];
         const double * g = gain(k);
         double fb = 0.0;
         double kj = 0.0, uj = 0.0;
@@ -232,18 +211,18 @@ struct CentroidalWarp
           kj = g[lane];
           uj = un[(size_t)k * 32 + lane];
           CCC_UNROLL
-          for(int c = 0; c < 9; c++) fb = dfma(g[(1 + c) * 32 + lane], dx[c], fb);
+          for(int c = 0; c < NX; c++) fb = dfma(g[(1 + c) * 32 + lane], dx[c], fb);
         }
         u = dfma(alpha, kj, uj) + fb;
         if(kConstrained) u = clampd(u, P.u_lo, P.u_hi);
         if(!active) u = 0.0;
       }
       ud[(size_t)k * 32 + lane] = u;
-      store9(xd + (size_t)k * 9, x);
+      storeX(xd + (size_t)k * NX, x);
       const double c = step_and_cost(k, m, x, u);
       Jc = Jc + c;
     }
-    store9(xd + (size_t)N * 9, x);
+    storeX(xd + (size_t)N * NX, x);
     Jc = Jc + terminal_cost(x);
     return Jc;
   }
@@ -255,38 +234,13 @@ struct CentroidalWarp
     const int N = P.N;
     const int m = stage_m(k);
     const bool active = lane < m;
-    const double * xn = xtraj(cur) + (size_t)k * 9;
-    double x3[3];
-    CCC_UNROLL
-    for(int i = 0; i < 3; i++) x3[i] = xn[i];
+    const double * xn = xtraj(cur) + (size_t)k * NX;
     const double u = active ? utraj(cur)[(size_t)k * 32 + lane] : 0.0;
-    const double * tb = stage_tab(k);
-    double rho[3], d[3], cr[3];
-    CCC_UNROLL
-    for(int a = 0; a < 3; a++)
-    {
-      rho[a] = active ? ldg(tb + a * 32 + lane) : 0.0;
-      d[a] = (active ? ldg(tb + (3 + a) * 32 + lane) : 0.0) - x3[a];
-    }
-    cross3(d, rho, cr);
-    double f[3];
-    CCC_UNROLL
-    for(int a = 0; a < 3; a++) f[a] = active ? u * rho[a] : 0.0;
-    warp_sum_n<3>(f);
 
-    // Fx: only the cross-product block changes from stage to stage (rows 6..8, cols 0..2)
-    warp_sync();
-    if(lane == 0)
-    {
-      double * Fx = s + sm::FX;
-      Fx[6 * 9 + 1] = -f[2] * P.dt;
-      Fx[6 * 9 + 2] = f[1] * P.dt;
-      Fx[7 * 9 + 0] = f[2] * P.dt;
-      Fx[7 * 9 + 2] = -f[0] * P.dt;
-      Fx[8 * 9 + 0] = -f[1] * P.dt;
-      Fx[8 * 9 + 1] = f[0] * P.dt;
-    }
-    warp_sync();
+    // model: this lane's column of Fu (rows R0..R0+5) and the stage-dependent entries of Fx
+    double Fu[6];
+    M::lane_derivs(*this, k, m, xn, u, Fu);
+
     const double * Fx = s + sm::FX;
     const double * Vxx = s + sm::VXX;
     const double * Vx = s + sm::VX;
@@ -295,33 +249,33 @@ struct CentroidalWarp
     double * Qx = s + sm::QX;
     // T = Vxx Fx
     CCC_NOUNROLL
-    for(int e = lane; e < 81; e += 32)
+    for(int e = lane; e < NX * NX; e += 32)
     {
-      const int i = e / 9, j = e - 9 * i;
+      const int i = e / NX, j = e - NX * i;
       double acc = 0.0;
       CCC_UNROLL
-      for(int c = 0; c < 9; c++) acc = dfma(Vxx[i * 9 + c], Fx[c * 9 + j], acc);
+      for(int c = 0; c < NX; c++) acc = dfma(Vxx[i * NX + c], Fx[c * NX + j], acc);
       T[e] = acc;
     }
-    if(lane < 9)
+    if(lane < NX)
     {
-      double rr = lane < 3 ? ldg(ref(k) + lane) : 0.0;
+      double rr = lane < NREF ? ldg(ref(k) + lane) : 0.0;
       double xl = xn[lane];
-      double lx = lane < 3 ? P.w_run[lane] * (xl - rr) : P.w_run[lane] * xl;
+      double lx = lane < NREF ? P.w_run[lane] * (xl - rr) : P.w_run[lane] * xl;
       double acc = 0.0;
       CCC_UNROLL
-      for(int c = 0; c < 9; c++) acc = dfma(Fx[c * 9 + lane], Vx[c], acc);
+      for(int c = 0; c < NX; c++) acc = dfma(Fx[c * NX + lane], Vx[c], acc);
       Qx[lane] = lx + acc;
     }
     warp_sync();
     // Qxx = Lxx + Fx' T
     CCC_NOUNROLL
-    for(int e = lane; e < 81; e += 32)
+    for(int e = lane; e < NX * NX; e += 32)
     {
-      const int i = e / 9, j = e - 9 * i;
+      const int i = e / NX, j = e - NX * i;
       double acc = 0.0;
       CCC_UNROLL
-      for(int c = 0; c < 9; c++) acc = dfma(Fx[c * 9 + i], T[c * 9 + j], acc);
+      for(int c = 0; c < NX; c++) acc = dfma(Fx[c * NX + i], T[c * NX + j], acc);
       Qxx[e] = (i == j ? P.w_run[i] : 0.0) + acc;
     }
 
@@ -332,12 +286,12 @@ struct CentroidalWarp
       double * Vxxw = s + sm::VXX;
       double * Vxw = s + sm::VX;
       CCC_NOUNROLL
-      for(int e = lane; e < 81; e += 32)
+      for(int e = lane; e < NX * NX; e += 32)
       {
-        const int i = e / 9, j = e - 9 * i;
-        Vxxw[e] = 0.5 * (Qxx[e] + Qxx[j * 9 + i]);
+        const int i = e / NX, j = e - NX * i;
+        Vxxw[e] = 0.5 * (Qxx[e] + Qxx[j * NX + i]);
       }
-      if(lane < 9) Vxw[lane] = Qx[lane];
+      if(lane < NX) Vxw[lane] = Qx[lane];
       if(P.out_clamped && lane == 0) P.out_clamped[(size_t)b * N + k] = 0u;
       warp_sync();
       k_next = 0.0;
@@ -345,23 +299,15 @@ struct CentroidalWarp
       return true;
     }
 
-    // Fu column of this lane (rows 3..8; rows 0..2 are zero)
-    double Fu[6];
-    CCC_UNROLL
-    for(int a = 0; a < 3; a++)
-    {
-      Fu[a] = rho[a] * P.dt;
-      Fu[3 + a] = cr[a] * P.dt;
-    }
     // Qu
     double Qu;
     {
       double acc = 0.0;
       CCC_UNROLL
-      for(int c = 0; c < 6; c++) acc = dfma(Fu[c], Vx[3 + c], acc);
-      Qu = P.w_run[9] * u + acc;
+      for(int c = 0; c < 6; c++) acc = dfma(Fu[c], Vx[R0 + c], acc);
+      Qu = P.w_run[NX] * u + acc;
     }
-    // W = Vxx Fu, rows 3..8, published transposed: WT[lane][0..5]
+    // W = Vxx Fu, rows R0..R0+5, published transposed: WT[lane][0..5]
     double * WT = s + sm::WT;
     {
       double w[6];
@@ -370,20 +316,20 @@ struct CentroidalWarp
       {
         double acc = 0.0;
         CCC_UNROLL
-        for(int c = 0; c < 6; c++) acc = dfma(Vxx[(3 + r) * 9 + 3 + c], Fu[c], acc);
+        for(int c = 0; c < 6; c++) acc = dfma(Vxx[(R0 + r) * NX + R0 + c], Fu[c], acc);
         w[r] = active ? acc : 0.0;
       }
       CCC_UNROLL
       for(int r = 0; r < 6; r++) WT[lane * 6 + r] = w[r];
     }
     // Qux row of this lane: Fu' (Vxx Fx)
-    double Qux[9];
+    double Qux[NX];
     CCC_UNROLL
-    for(int c = 0; c < 9; c++)
+    for(int c = 0; c < NX; c++)
     {
       double acc = 0.0;
       CCC_UNROLL
-      for(int r = 0; r < 6; r++) acc = dfma(Fu[r], T[(3 + r) * 9 + c], acc);
+      for(int r = 0; r < 6; r++) acc = dfma(Fu[r], T[(R0 + r) * NX + c], acc);
       Qux[c] = 0.0 + acc;
     }
     warp_sync();
@@ -403,7 +349,7 @@ struct CentroidalWarp
         acc = dfma(Fu[2 * r], w.x, acc);
         acc = dfma(Fu[2 * r + 1], w.y, acc);
       }
-      H[j] = (j == lane ? P.w_run[9] : 0.0) + acc;
+      H[j] = (j == lane ? P.w_run[NX] : 0.0) + acc;
     }
     double quu_diag = 0.0;
     CCC_UNROLL
@@ -421,7 +367,7 @@ struct CentroidalWarp
 
     // gains
     double kk = 0.0;
-    double K[9];
+    double K[NX];
     unsigned clamped = 0;
     int * idxbuf = reinterpret_cast<int *>(s + sm::IDX);
     if(kConstrained)
@@ -442,11 +388,11 @@ struct CentroidalWarp
       {
         // K[free,:] = -(Quu_F[free,free])^-1 Qux[free,:] with BoxQP's factor (compact numbering)
         CCC_UNROLL
-        for(int c = 0; c < 9; c++) K[c] = warp_shfl(Qux[c], r.fs.idx);
-        llt_solve_compactN<9>(K, A, r.fs.nf, r.invd_c);
+        for(int c = 0; c < NX; c++) K[c] = warp_shfl(Qux[c], r.fs.idx);
+        llt_solve_compactN<NX>(K, A, r.fs.nf, r.invd_c);
         const bool free_i = active && !((clamped >> lane) & 1u);
         CCC_UNROLL
-        for(int c = 0; c < 9; c++)
+        for(int c = 0; c < NX; c++)
         {
           const double v = warp_shfl(K[c], r.fs.rank);
           K[c] = free_i ? -v : 0.0;
@@ -455,7 +401,7 @@ struct CentroidalWarp
       else
       {
         CCC_UNROLL
-        for(int c = 0; c < 9; c++) K[c] = 0.0;
+        for(int c = 0; c < NX; c++) K[c] = 0.0;
       }
     }
     else
@@ -467,14 +413,14 @@ struct CentroidalWarp
       const bool ok = llt_factor_compact(H, A, s + sm::VB, fs.nf, invd_c, dummy);
       load_sym_row(H, A, m);
       if(!ok) return false;
-      double r10[10];
-      r10[0] = Qu;
+      double r1[NX + 1];
+      r1[0] = Qu;
       CCC_UNROLL
-      for(int c = 0; c < 9; c++) r10[1 + c] = Qux[c];
-      llt_solve_compactN<10>(r10, A, fs.nf, invd_c);
-      kk = active ? -r10[0] : 0.0;
+      for(int c = 0; c < NX; c++) r1[1 + c] = Qux[c];
+      llt_solve_compactN<NX + 1>(r1, A, fs.nf, invd_c);
+      kk = active ? -r1[0] : 0.0;
       CCC_UNROLL
-      for(int c = 0; c < 9; c++) K[c] = active ? -r10[1 + c] : 0.0;
+      for(int c = 0; c < NX; c++) K[c] = active ? -r1[1 + c] : 0.0;
     }
     if(P.out_clamped && lane == 0) P.out_clamped[(size_t)b * N + k] = clamped;
 
@@ -483,7 +429,7 @@ struct CentroidalWarp
       double * g = gain(k);
       g[lane] = kk;
       CCC_UNROLL
-      for(int c = 0; c < 9; c++) g[(1 + c) * 32 + lane] = K[c];
+      for(int c = 0; c < NX; c++) g[(1 + c) * 32 + lane] = K[c];
       if(active)
       {
         double r = ddiv(dabs(kk), dabs(u) + 1.0);
@@ -497,35 +443,32 @@ struct CentroidalWarp
     double * VB0 = s + sm::VB0;
     double * VB1 = s + sm::VB1;
     double * VB2 = s + sm::VB2;
-    warp_sync(); // the factor in A is dead from here on: KB/ZB/QB alias it
+    warp_sync(); // the factor in A and the BoxQP buffers are dead from here on: KB/ZB/QB/VB0-2 alias them
     double * KB = s + sm::KB;
     double * ZB = s + sm::ZB;
     double * QB = s + sm::QB;
     VB0[lane] = kk;
     CCC_UNROLL
-    for(int c = 0; c < 9; c++) KB[lane * 10 + c] = K[c];
-    KB[lane * 10 + 9] = 0.0;
+    for(int c = 0; c < NX; c++) KB[lane * NXP + c] = K[c];
+    if(NXP > NX) KB[lane * NXP + NX] = 0.0;
     warp_sync();
     const double Quuk = matvec32(H, VB0, m);
-    double Z[9];
+    double Z[NX];
     CCC_UNROLL
-    for(int c = 0; c < 9; c++) Z[c] = 0.0;
+    for(int c = 0; c < NX; c++) Z[c] = 0.0;
     CCC_UNROLL
     for(int j = 0; j < 32; j++)
     {
       if(j == 16 && m <= 16) break;
       const double h = H[j];
-      d2 k01 = ld2(KB + j * 10 + 0), k23 = ld2(KB + j * 10 + 2), k45 = ld2(KB + j * 10 + 4), k67 = ld2(KB + j * 10 + 6);
-      const double k8 = KB[j * 10 + 8];
-      Z[0] = dfma(h, k01.x, Z[0]);
-      Z[1] = dfma(h, k01.y, Z[1]);
-      Z[2] = dfma(h, k23.x, Z[2]);
-      Z[3] = dfma(h, k23.y, Z[3]);
-      Z[4] = dfma(h, k45.x, Z[4]);
-      Z[5] = dfma(h, k45.y, Z[5]);
-      Z[6] = dfma(h, k67.x, Z[6]);
-      Z[7] = dfma(h, k67.y, Z[7]);
-      Z[8] = dfma(h, k8, Z[8]);
+      CCC_UNROLL
+      for(int c = 0; c + 1 < NX; c += 2)
+      {
+        const d2 kc = ld2(KB + j * NXP + c);
+        Z[c] = dfma(h, kc.x, Z[c]);
+        Z[c + 1] = dfma(h, kc.y, Z[c + 1]);
+      }
+      if(NX & 1) Z[NX - 1] = dfma(h, KB[j * NXP + NX - 1], Z[NX - 1]);
     }
     {
       double dv[2] = {active ? kk * Qu : 0.0, active ? kk * Quuk : 0.0};
@@ -534,10 +477,10 @@ struct CentroidalWarp
       dV1 = dfma(0.5, dv[1], dV1);
     }
     CCC_UNROLL
-    for(int c = 0; c < 9; c++)
+    for(int c = 0; c < NX; c++)
     {
-      ZB[lane * 10 + c] = active ? Z[c] : 0.0;
-      QB[lane * 10 + c] = active ? Qux[c] : 0.0;
+      ZB[lane * NXP + c] = active ? Z[c] : 0.0;
+      QB[lane * NXP + c] = active ? Qux[c] : 0.0;
     }
     VB1[lane] = active ? Quuk : 0.0;
     VB2[lane] = active ? Qu : 0.0;
@@ -545,36 +488,37 @@ struct CentroidalWarp
     double * Vxw = s + sm::VX;
     double * Vxxw = s + sm::VXX;
     double * S2 = s + sm::S2;
-    if(lane < 9)
+    if(lane < NX)
     {
       double a1 = 0.0, a2 = 0.0, a3 = 0.0;
       CCC_NOUNROLL
       for(int j = 0; j < m; j++)
       {
-        const double kj = KB[j * 10 + lane];
+        const double kj = KB[j * NXP + lane];
         a1 = dfma(kj, VB1[j], a1);
         a2 = dfma(kj, VB2[j], a2);
-        a3 = dfma(QB[j * 10 + lane], VB0[j], a3);
+        a3 = dfma(QB[j * NXP + lane], VB0[j], a3);
       }
       Vxw[lane] = ((Qx[lane] + a1) + a2) + a3;
     }
-    double s1v[3], s2v[3];
+    constexpr int NQ = (NX * NX + 31) / 32;
+    double s1v[NQ], s2v[NQ];
     CCC_UNROLL
-    for(int q = 0; q < 3; q++)
+    for(int q = 0; q < NQ; q++)
     {
       const int e = lane + 32 * q;
       s1v[q] = 0.0;
       s2v[q] = 0.0;
-      if(e < 81)
+      if(e < NX * NX)
       {
-        const int a = e / 9, c = e - 9 * a;
+        const int a = e / NX, c = e - NX * a;
         double s1 = 0.0, s2 = 0.0;
         CCC_NOUNROLL
         for(int j = 0; j < m; j++)
         {
-          const double kj = KB[j * 10 + a];
-          s1 = dfma(kj, ZB[j * 10 + c], s1);
-          s2 = dfma(kj, QB[j * 10 + c], s2);
+          const double kj = KB[j * NXP + a];
+          s1 = dfma(kj, ZB[j * NXP + c], s1);
+          s2 = dfma(kj, QB[j * NXP + c], s2);
         }
         s1v[q] = s1;
         s2v[q] = s2;
@@ -584,24 +528,24 @@ struct CentroidalWarp
     warp_sync();
     // Vn = ((Qxx + K'QuuK) + K'Qux) + Qux'K   (Qux'K = (K'Qux)' bit for bit), staged in T
     CCC_UNROLL
-    for(int q = 0; q < 3; q++)
+    for(int q = 0; q < NQ; q++)
     {
       const int e = lane + 32 * q;
-      if(e < 81)
+      if(e < NX * NX)
       {
-        const int a = e / 9, c = e - 9 * a;
-        T[e] = ((Qxx[e] + s1v[q]) + s2v[q]) + S2[c * 9 + a];
+        const int a = e / NX, c = e - NX * a;
+        T[e] = ((Qxx[e] + s1v[q]) + s2v[q]) + S2[c * NX + a];
       }
     }
     warp_sync();
     CCC_UNROLL
-    for(int q = 0; q < 3; q++)
+    for(int q = 0; q < NQ; q++)
     {
       const int e = lane + 32 * q;
-      if(e < 81)
+      if(e < NX * NX)
       {
-        const int a = e / 9, c = e - 9 * a;
-        Vxxw[e] = 0.5 * (T[e] + T[c * 9 + a]);
+        const int a = e / NX, c = e - NX * a;
+        Vxxw[e] = 0.5 * (T[e] + T[c * NX + a]);
       }
     }
     warp_sync();
@@ -613,20 +557,20 @@ struct CentroidalWarp
   CCC_DEV bool backward_pass()
   {
     const int N = P.N;
-    // terminal cost derivatives (src/DdpCentroidal.cpp:156-177)
-    const double * xN = xtraj(cur) + (size_t)N * 9;
+    // terminal cost derivatives (src/DdpCentroidal.cpp:156-177, src/DdpSingleRigidBody.cpp:224-245)
+    const double * xN = xtraj(cur) + (size_t)N * NX;
     warp_sync();
     CCC_NOUNROLL
-    for(int e = lane; e < 81; e += 32)
+    for(int e = lane; e < NX * NX; e += 32)
     {
-      const int i = e / 9, j = e - 9 * i;
+      const int i = e / NX, j = e - NX * i;
       s[sm::VXX + e] = (i == j) ? P.w_term[i] : 0.0;
     }
-    if(lane < 9)
+    if(lane < NX)
     {
-      double rr = lane < 3 ? ldg(ref(N) + lane) : 0.0;
+      double rr = lane < NREF ? ldg(ref(N) + lane) : 0.0;
       double xv = xN[lane];
-      s[sm::VX + lane] = lane < 3 ? P.w_term[lane] * (xv - rr) : P.w_term[lane] * xv;
+      s[sm::VX + lane] = lane < NREF ? P.w_term[lane] * (xv - rr) : P.w_term[lane] * xv;
     }
     warp_sync();
     dV0 = 0.0;
@@ -677,19 +621,11 @@ struct CentroidalWarp
   CCC_DEV bool solve(bool resume)
   {
     const int N = P.N;
-    // per-visit shared-memory state: constant part of Fx (identity + (1/mass) dt on the
-    // (pos, momentum) block) and a finite (zero) tile
+    // per-visit shared-memory state: the stage-independent part of Fx and a finite (zero) tile
     warp_sync();
+    M::init_Fx(*this);
     CCC_NOUNROLL
-    for(int e = lane; e < 82; e += 32)
-    {
-      const int i = e / 9, j = e - 9 * i;
-      double v = (i == j && e < 81) ? 1.0 : 0.0;
-      if(i < 3 && j == i + 3) v = ddiv(1, P.mass) * P.dt;
-      s[sm::FX + e] = v;
-    }
-    CCC_NOUNROLL
-    for(int e = lane; e < 32 * kLda; e += 32) s[sm::A + e] = 0.0;
+    for(int e = lane; e < sm::IDX - sm::A; e += 32) s[sm::A + e] = 0.0;
     int rv = 0, iter = 0, a = -1;
     bool need_rollout = true;
     if(!resume)
@@ -814,7 +750,7 @@ struct CentroidalWarp
     if(P.out_x)
     {
       CCC_NOUNROLL
-      for(int i = lane; i < (N + 1) * 9; i += 32) P.out_x[(size_t)b * (N + 1) * 9 + i] = xs[i];
+      for(int i = lane; i < (N + 1) * NX; i += 32) P.out_x[(size_t)b * (N + 1) * NX + i] = xs[i];
     }
     if(P.out_u)
     {

@@ -10,7 +10,7 @@
 // collective (__syncwarp, shuffles, ballot) is a barrier over the live fibres.
 #define CCC_WARP_EMU 1
 #include "../../include/ccc_b200.h"
-#include "../../centroidalcontrolcollection_b200/csrc/ddp_centroidal_core.cuh"
+#include "../../centroidalcontrolcollection_b200/csrc/model_centroidal.cuh"
 
 #include <ucontext.h>
 
@@ -181,49 +181,53 @@ extern "C" void ccc_emu_set_chunk(int32_t chunk)
   g_chunk = chunk;
 }
 
-extern "C" int32_t ccc_emu_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t * bt,
-                                                const ccc_ddp_config_t * c,
-                                                ccc_ddp_result_t * r)
+/** Host-side replay of ccc_host::DdpEngine<M>::solve for one emulated warp. */
+template<class M, class FillExtra>
+int32_t emuSolve(int N, int B, int S, int mm, const int32_t * sched_id, const int32_t * m, const double * ridge,
+                 const double * vertex, const double * ref, const double * x0, const double * u_init_in,
+                 const double * w_run, const double * w_term, double u_lo, double u_hi, const typename M::Params & mp,
+                 const ccc_ddp_config_t * c, ccc_ddp_result_t * r, FillExtra && fill_extra)
 {
-  const int N = bt->horizon_steps, B = bt->batch, S = bt->n_sched, mm = bt->m_max;
+  constexpr int NX = M::NX;
+  using sm = ccc::SmLayout<M::NX, M::NXP>;
   if(mm > 32) return CCC_ERR_INVALID;
-  // pack stage tables [S][N][6][32] exactly as the engine's pack kernel does
-  std::vector<double> tab((size_t)S * N * 192, 0.0);
+  // pack stage tables [S][N][TAB_ROWS][32] exactly as the engine's pack kernels do
+  std::vector<double> tab((size_t)S * N * 32 * M::TAB_ROWS, 0.0);
   for(int s = 0; s < S; s++)
     for(int k = 0; k < N; k++)
       for(int j = 0; j < mm; j++)
         for(int a = 0; a < 3; a++)
         {
           size_t src = (((size_t)s * N + k) * mm + j) * 3 + a;
-          tab[((size_t)s * N + k) * 192 + a * 32 + j] = bt->ridge[src];
-          tab[((size_t)s * N + k) * 192 + (3 + a) * 32 + j] = bt->vertex[src];
+          tab[((size_t)s * N + k) * 32 * M::TAB_ROWS + a * 32 + j] = ridge[src];
+          tab[((size_t)s * N + k) * 32 * M::TAB_ROWS + (3 + a) * 32 + j] = vertex[src];
         }
+  fill_extra(tab.data());
   std::vector<double> u_init;
-  if(bt->u_init)
+  if(u_init_in)
   {
     u_init.assign((size_t)B * N * 32, 0.0);
     for(size_t bk = 0; bk < (size_t)B * N; bk++)
-      for(int j = 0; j < mm; j++) u_init[bk * 32 + j] = bt->u_init[bk * mm + j];
+      for(int j = 0; j < mm; j++) u_init[bk * 32 + j] = u_init_in[bk * mm + j];
   }
-  std::vector<double> xbuf((size_t)2 * B * (N + 1) * 9, 0.0), ubuf((size_t)2 * B * N * 32, 0.0),
-      gains((size_t)B * N * 320, 0.0), out_u((size_t)B * N * 32, 0.0);
-  ccc::CentroidalParams P;
+  std::vector<double> xbuf((size_t)2 * B * (N + 1) * NX, 0.0), ubuf((size_t)2 * B * N * 32, 0.0),
+      gains((size_t)B * N * 32 * (1 + NX), 0.0), out_u((size_t)B * N * 32, 0.0);
+  ccc::DdpParams<M> P;
   std::memset(&P, 0, sizeof(P));
   P.N = N;
   P.B = B;
   P.S = S;
-  P.dt = bt->dt;
-  P.mass = bt->mass;
-  P.sched_id = bt->sched_id;
-  P.m = bt->m;
+  P.sched_id = sched_id;
+  P.m = m;
   P.tab = tab.data();
-  P.ref_pos = bt->ref_pos;
-  for(int i = 0; i < 10; i++) P.w_run[i] = bt->w_run[i];
-  for(int i = 0; i < 9; i++) P.w_term[i] = bt->w_term[i];
-  P.u_lo = bt->u_lo;
-  P.u_hi = bt->u_hi;
-  P.x0 = bt->x0;
-  P.u_init = bt->u_init ? u_init.data() : nullptr;
+  P.ref = ref;
+  for(int i = 0; i <= NX; i++) P.w_run[i] = w_run[i];
+  for(int i = 0; i < NX; i++) P.w_term[i] = w_term[i];
+  P.mp = mp;
+  P.u_lo = u_lo;
+  P.u_hi = u_hi;
+  P.x0 = x0;
+  P.u_init = u_init_in ? u_init.data() : nullptr;
   P.cfg = toCfg(c);
   P.xbuf = xbuf.data();
   P.ubuf = ubuf.data();
@@ -240,7 +244,7 @@ extern "C" int32_t ccc_emu_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t
   std::vector<ccc::DdpResume> resume(B);
   P.resume = resume.data();
   P.chunk_iters = g_chunk;
-  std::vector<double> smem(ccc::sm::TOTAL + 2, 0.0);
+  std::vector<double> smem(sm::TOTAL + 2, 0.0);
   // the kernel's round-robin queue, replayed by one emulated warp: (problem, resumed?) entries
   std::deque<std::pair<int, bool>> queue;
   for(int b = 0; b < B; b++) queue.emplace_back(b, false);
@@ -254,12 +258,12 @@ extern "C" int32_t ccc_emu_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t
       bool f;
       if(P.cfg.with_input_constraint)
       {
-        ccc::CentroidalWarp<true> w(P, smem.data(), b);
+        ccc::DdpWarp<M, true> w(P, smem.data(), b);
         f = w.solve(resumed);
       }
       else
       {
-        ccc::CentroidalWarp<false> w(P, smem.data(), b);
+        ccc::DdpWarp<M, false> w(P, smem.data(), b);
         f = w.solve(resumed);
       }
       if(ccc_emu::lane() == 0) finished = f;
@@ -270,4 +274,16 @@ extern "C" int32_t ccc_emu_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t
     for(size_t bk = 0; bk < (size_t)B * N; bk++)
       for(int j = 0; j < mm; j++) r->u[bk * mm + j] = out_u[bk * 32 + j];
   return CCC_OK;
+}
+
+extern "C" int32_t ccc_emu_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t * bt,
+                                                const ccc_ddp_config_t * c,
+                                                ccc_ddp_result_t * r)
+{
+  ccc::CentroidalModel::Params mp;
+  mp.dt = bt->dt;
+  mp.mass = bt->mass;
+  return emuSolve<ccc::CentroidalModel>(bt->horizon_steps, bt->batch, bt->n_sched, bt->m_max, bt->sched_id, bt->m,
+                                        bt->ridge, bt->vertex, bt->ref_pos, bt->x0, bt->u_init, bt->w_run, bt->w_term,
+                                        bt->u_lo, bt->u_hi, mp, c, r, [](double *) {});
 }
