@@ -83,6 +83,31 @@ class DdpCentroidalBatch(C.Structure):
     ]
 
 
+class DdpSrbBatch(C.Structure):
+    """ccc_ddp_srb_batch_t"""
+
+    _fields_ = [
+        ("horizon_steps", C.c_int32),
+        ("batch", C.c_int32),
+        ("n_sched", C.c_int32),
+        ("m_max", C.c_int32),
+        ("dt", C.c_double),
+        ("mass", C.c_double),
+        ("sched_id", C.c_void_p),
+        ("m", C.c_void_p),
+        ("ridge", C.c_void_p),
+        ("vertex", C.c_void_p),
+        ("inertia", C.c_void_p),
+        ("ref", C.c_void_p),
+        ("w_run", C.c_double * 13),
+        ("w_term", C.c_double * 12),
+        ("u_lo", C.c_double),
+        ("u_hi", C.c_double),
+        ("x0", C.c_void_p),
+        ("u_init", C.c_void_p),
+    ]
+
+
 def ptr(a):
     """Address of a C-contiguous numpy array (or None)."""
     if a is None:

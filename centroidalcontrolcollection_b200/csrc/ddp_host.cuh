@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
   }
 }
 
-__global__ void init_queue_kernel(SolveQueue q, int B)
+static __global__ void init_queue_kernel(SolveQueue q, int B)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i < q.capacity) q.slot[i] = i < B ? i : -1;
@@ -93,7 +93,7 @@ __global__ void init_queue_kernel(SolveQueue q, int B)
 
 /** ridge/vertex [S][N][m_max][3] -> rows 0..5 of tab [S][N][rows][32] (component-major,
  *  lane-contiguous, zero padded).  Rows >= 6 are model specific and filled separately. */
-__global__ void pack_tables_kernel(const double * __restrict__ ridge,
+static __global__ void pack_tables_kernel(const double * __restrict__ ridge,
                                    const double * __restrict__ vertex,
                                    double * __restrict__ tab,
                                    int stages,
@@ -114,7 +114,7 @@ __global__ void pack_tables_kernel(const double * __restrict__ ridge,
 }
 
 /** copy rows of `cols` doubles between two row strides (zero-fills dst columns >= cols). */
-__global__ void restride_kernel(const double * __restrict__ src, int sstride, double * __restrict__ dst, int dstride, size_t rows, int cols)
+static __global__ void restride_kernel(const double * __restrict__ src, int sstride, double * __restrict__ dst, int dstride, size_t rows, int cols)
 {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(idx >= rows * (size_t)dstride) return;

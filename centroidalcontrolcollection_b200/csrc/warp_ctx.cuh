@@ -35,6 +35,7 @@ inline unsigned warp_ballot(bool p) { return ccc_emu::ballot(p); }
 inline double dfma(double a, double b, double c) { return std::fma(a, b, c); }
 inline double dsqrt(double a) { return std::sqrt(a); }
 inline double drcp(double a) { return 1.0 / a; }
+inline double drint(double a) { return std::nearbyint(a); }
 inline double dabs(double a) { return std::fabs(a); }
 template<class T>
 inline T ldg(const T * p) { return *p; }
@@ -60,6 +61,7 @@ CCC_DEV unsigned warp_ballot(bool p) { return __ballot_sync(kFullMask, p); }
 CCC_DEV double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 CCC_DEV double dsqrt(double a) { return __dsqrt_rn(a); }
 CCC_DEV double drcp(double a) { return __drcp_rn(a); } // correctly rounded 1/a == IEEE 1.0 / a
+CCC_DEV double drint(double a) { return rint(a); }
 CCC_DEV double dabs(double a) { return fabs(a); }
 template<class T>
 CCC_DEV T ldg(const T * p) { return __ldg(p); }
@@ -156,6 +158,33 @@ CCC_DEV double clampd(double v, double lo, double hi)
 {
   double r = v < lo ? lo : v;
   return r > hi ? hi : r;
+}
+
+/** sin and cos from +,-,*,fma and rint only (oracle/num.hpp sincos_canon, same sequence). */
+CCC_DEV void sincos_canon(double x, double & s_out, double & c_out)
+{
+  const double j = drint(x * 6.36619772367581382433e-01);
+  double r = dfma(-j, 1.57079632673412561417e+00, x);
+  r = dfma(-j, 6.07710050650619224932e-11, r);
+  r = dfma(-j, 2.02226624879595063154e-21, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = dfma(ps, z, -2.50507602534068634195e-08);
+  ps = dfma(ps, z, 2.75573137070700676789e-06);
+  ps = dfma(ps, z, -1.98412698298579493134e-04);
+  ps = dfma(ps, z, 8.33333333332248946124e-03);
+  ps = dfma(ps, z, -1.66666666666666324348e-01);
+  const double sr = dfma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = dfma(pc, z, 2.08757232129817482790e-09);
+  pc = dfma(pc, z, -2.75573143513906633035e-07);
+  pc = dfma(pc, z, 2.48015872894767294178e-05);
+  pc = dfma(pc, z, -1.38888888888741095749e-03);
+  pc = dfma(pc, z, 4.16666666666666019037e-02);
+  const double cr = dfma(z * z, pc, dfma(-0.5, z, 1.0));
+  const long long q = static_cast<long long>(j) & 3;
+  s_out = q == 0 ? sr : q == 1 ? cr : q == 2 ? -sr : -cr;
+  c_out = q == 0 ? cr : q == 1 ? -sr : q == 2 ? -cr : sr;
 }
 
 /** cross product: one rounded product + one fma per component (oracle/num.hpp cross3). */

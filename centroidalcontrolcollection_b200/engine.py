@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 from . import _abi
-from .problem import DdpCentroidalProblemSet, DdpResultArrays
+from .problem import DdpCentroidalProblemSet, DdpResultArrays, DdpSrbProblemSet
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libccc_b200.so")
@@ -19,6 +19,7 @@ EXPORTS = [
     "ccc_abi_version", "ccc_device_count", "ccc_last_error", "ccc_ddp_config_default",
     "ccc_ddp_centroidal_create", "ccc_ddp_centroidal_destroy", "ccc_ddp_centroidal_solve",
     "ccc_ddp_centroidal_last_launches",
+    "ccc_ddp_srb_create", "ccc_ddp_srb_destroy", "ccc_ddp_srb_solve", "ccc_ddp_srb_last_launches",
 ]
 
 
@@ -51,6 +52,14 @@ def lib():
         L.ccc_ddp_centroidal_set_variant.argtypes = [C.c_int32]
         L.ccc_ddp_centroidal_set_chunk.restype = None
         L.ccc_ddp_centroidal_set_chunk.argtypes = [C.c_int32]
+        L.ccc_ddp_srb_create.restype = C.c_void_p
+        L.ccc_ddp_srb_create.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.ccc_ddp_srb_destroy.argtypes = [C.c_void_p]
+        L.ccc_ddp_srb_destroy.restype = None
+        L.ccc_ddp_srb_solve.restype = C.c_int32
+        L.ccc_ddp_srb_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ccc_ddp_srb_last_launches.restype = C.c_int32
+        L.ccc_ddp_srb_last_launches.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -64,41 +73,56 @@ def _check(rc, what):
         raise EngineError(f"{what} failed with code {rc}: {last_error()}")
 
 
-class DdpCentroidalEngine:
-    """Batched counterpart of CCC::DdpCentroidal's solver object (reference
-    include/CCC/DdpCentroidal.h:342-365): owns the device workspace, solves batches."""
+class _DdpEngineBase:
+    """Owns one device workspace of the C-ABI and solves batches with it."""
+
+    _prefix = None
 
     def __init__(self, horizon_steps, max_batch, max_sched=16):
-        self._h = lib().ccc_ddp_centroidal_create(int(horizon_steps), int(max_batch), int(max_sched))
+        self._fn = lambda name: getattr(lib(), f"{self._prefix}_{name}")
+        self._h = self._fn("create")(int(horizon_steps), int(max_batch), int(max_sched))
         if not self._h:
-            raise EngineError(f"ccc_ddp_centroidal_create failed: {last_error()}")
+            raise EngineError(f"{self._prefix}_create failed: {last_error()}")
         self.N, self.max_batch, self.max_sched = horizon_steps, max_batch, max_sched
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().ccc_ddp_centroidal_destroy(self._h)
+            self._fn("destroy")(self._h)
             self._h = None
 
     __del__ = close
 
-    def solve(self, problem_set: DdpCentroidalProblemSet, cfg, trace_len=0, result=None):
+    def solve(self, problem_set, cfg, trace_len=0, result=None):
         """Host buffers in, host buffers out (H2D + solve + D2H, synchronous)."""
         res = result if result is not None else problem_set.new_result(trace_len)
         bs, rs = problem_set.as_struct(), res.as_struct()
-        rc = lib().ccc_ddp_centroidal_solve(self._h, C.addressof(bs), C.addressof(cfg), C.addressof(rs),
-                                            _abi.CCC_MEM_HOST, None)
-        _check(rc, "ccc_ddp_centroidal_solve")
+        rc = self._fn("solve")(self._h, C.addressof(bs), C.addressof(cfg), C.addressof(rs), _abi.CCC_MEM_HOST, None)
+        _check(rc, f"{self._prefix}_solve")
         return res
 
     def solve_device(self, batch_struct, cfg, result_struct, stream=0):
         """Device pointers in/out; only enqueues work on `stream` (an int cudaStream_t)."""
-        rc = lib().ccc_ddp_centroidal_solve(self._h, C.addressof(batch_struct), C.addressof(cfg),
-                                            C.addressof(result_struct), _abi.CCC_MEM_DEVICE, C.c_void_p(stream))
-        _check(rc, "ccc_ddp_centroidal_solve")
+        rc = self._fn("solve")(self._h, C.addressof(batch_struct), C.addressof(cfg), C.addressof(result_struct),
+                               _abi.CCC_MEM_DEVICE, C.c_void_p(stream))
+        _check(rc, f"{self._prefix}_solve")
 
     @property
     def last_launches(self):
-        return int(lib().ccc_ddp_centroidal_last_launches(self._h))
+        return int(self._fn("last_launches")(self._h))
+
+
+class DdpSrbEngine(_DdpEngineBase):
+    """Batched counterpart of CCC::DdpSingleRigidBody's solver object (reference
+    include/CCC/DdpSingleRigidBody.h:382-405)."""
+
+    _prefix = "ccc_ddp_srb"
+
+
+class DdpCentroidalEngine(_DdpEngineBase):
+    """Batched counterpart of CCC::DdpCentroidal's solver object (reference
+    include/CCC/DdpCentroidal.h:342-365): owns the device workspace, solves batches."""
+
+    _prefix = "ccc_ddp_centroidal"
 
     @staticmethod
     def set_variant(v):

@@ -44,6 +44,11 @@ def ddp_config(with_input_constraint=False, **overrides):
     return c
 
 
+def ddp_srb_config(**overrides):
+    """Solver configuration of CCC::DdpSingleRigidBody's constructor (reference src/DdpSingleRigidBody.cpp:267-271)."""
+    return ddp_centroidal_config(**overrides)
+
+
 def ddp_centroidal_config(**overrides):
     """Solver configuration of CCC::DdpCentroidal's constructor (reference src/DdpCentroidal.cpp:197-201)."""
     kw = dict(initial_lambda=1e-6, lambda_min=1e-8, lambda_thre=1e-7)
@@ -134,3 +139,53 @@ class DdpCentroidalProblemSet:
 
     def new_result(self, trace_len=0):
         return DdpResultArrays(self.batch, self.N, 9, self.m_max, trace_len)
+
+
+class DdpSrbProblemSet:
+    """A batch of DdpSingleRigidBody problems: shared schedules + per-problem initial states (12)."""
+
+    nx = 12
+
+    def __init__(self, sched, sched_id, x0, mass, dt, w_run, w_term, u_lo=0.0, u_hi=1e6, u_init=None):
+        self.sched = sched
+        self.sched_id = np.ascontiguousarray(sched_id, dtype=np.int32)
+        self.x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        self.mass, self.dt = float(mass), float(dt)
+        self.w_run = np.asarray(w_run, dtype=np.float64)
+        self.w_term = np.asarray(w_term, dtype=np.float64)
+        self.u_lo, self.u_hi = float(u_lo), float(u_hi)
+        self.u_init = None if u_init is None else np.ascontiguousarray(u_init, dtype=np.float64)
+        assert self.x0.shape == (len(self.sched_id), 12)
+        assert self.w_run.shape == (13,) and self.w_term.shape == (12,)
+
+    @classmethod
+    def from_workload(cls, w):
+        return cls(w["sched"], w["sched_id"], w["x0"], w["mass"], w["dt"], w["w_run"], w["w_term"], w["u_lo"], w["u_hi"])
+
+    batch = property(lambda s: len(s.sched_id))
+    N = property(lambda s: s.sched.N)
+    m_max = property(lambda s: s.sched.m_max)
+
+    def subset(self, idx):
+        idx = np.asarray(idx)
+        return DdpSrbProblemSet(self.sched, self.sched_id[idx], self.x0[idx], self.mass, self.dt, self.w_run, self.w_term,
+                                self.u_lo, self.u_hi, None if self.u_init is None else self.u_init[idx])
+
+    def as_struct(self):
+        b = _abi.DdpSrbBatch()
+        s = self.sched
+        b.horizon_steps, b.batch, b.n_sched, b.m_max = s.N, self.batch, s.S, s.m_max
+        b.dt, b.mass = self.dt, self.mass
+        b.sched_id, b.m = ptr(self.sched_id), ptr(s.m)
+        b.ridge, b.vertex, b.inertia, b.ref = ptr(s.ridge), ptr(s.vertex), ptr(s.inertia), ptr(s.ref)
+        for i in range(13):
+            b.w_run[i] = self.w_run[i]
+        for i in range(12):
+            b.w_term[i] = self.w_term[i]
+        b.u_lo, b.u_hi = self.u_lo, self.u_hi
+        b.x0 = ptr(self.x0)
+        b.u_init = ptr(self.u_init)
+        return b
+
+    def new_result(self, trace_len=0):
+        return DdpResultArrays(self.batch, self.N, 12, self.m_max, trace_len)

@@ -40,3 +40,36 @@ class CentroidalSchedule:
             self.vertex[s, k, j:] = 0.0
             self.ridge[s, k, j:] = 0.0
         return self
+
+
+class SrbSchedule(CentroidalSchedule):
+    """Stage tables for CCC::DdpSingleRigidBody: contacts + inertia matrix per stage, pos/ori reference."""
+
+    def __init__(self, n_sched, horizon_steps, m_max=CCC_DDP_M_MAX):
+        super().__init__(n_sched, horizon_steps, m_max)
+        self.inertia = np.tile(np.eye(3).reshape(1, 1, 9), (n_sched, horizon_steps, 1))
+        self.ref = np.zeros((n_sched, horizon_steps + 1, 6))
+
+    def sample(self, s, motion_param_func, ref_data_func, current_time, dt):
+        """motion_param_func(t) -> (contacts, inertia[3,3]); ref_data_func(t) -> (pos[3], ori[3])."""
+        inertias = {}
+
+        def contacts_only(t):
+            contacts, inertia = motion_param_func(t)
+            inertias[t] = inertia
+            return contacts
+
+        refs = {}
+
+        def pos_only(t):
+            pos, ori = ref_data_func(t)
+            refs[t] = (pos, ori)
+            return pos
+
+        super().sample(s, contacts_only, pos_only, current_time, dt)
+        for k in range(self.N + 1):
+            t = current_time + k * dt
+            self.ref[s, k, 0:3], self.ref[s, k, 3:6] = refs[t]
+            if k < self.N:
+                self.inertia[s, k] = np.asarray(inertias[t], dtype=np.float64).reshape(9)
+        return self

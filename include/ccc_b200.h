@@ -135,6 +135,49 @@ int32_t ccc_ddp_centroidal_solve(ccc_ddp_centroidal_ws_t * ws,
 /* Number of kernels the last solve on this workspace launched (bench.py's gpu_launches). */
 int32_t ccc_ddp_centroidal_last_launches(const ccc_ddp_centroidal_ws_t * ws);
 
+/* ---- CCC::DdpSingleRigidBody -----------------------------------------------------------------
+ * Flat form of what DdpSingleRigidBody::planOnce (reference src/DdpSingleRigidBody.cpp:283-307) reads
+ * through its callbacks at t_k = current_time + k*dt: MotionParam.{contact_list, inertia_mat}
+ * (include/CCC/DdpSingleRigidBody.h:25-34) and RefData.{pos, ori} (:37-46).  State (12):
+ * pos, ZYX Euler angles (Z, Y, X order), linear velocity, angular velocity
+ * (InitialParam::toState, src/DdpSingleRigidBody.cpp:255-260). */
+typedef struct
+{
+  int32_t horizon_steps; /* N */
+  int32_t batch;         /* B */
+  int32_t n_sched;       /* S */
+  int32_t m_max;         /* row stride of ridge/vertex/u tables, <= CCC_DDP_M_MAX */
+  double dt;             /* horizon_dt [s] */
+  double mass;           /* [kg] */
+  const int32_t * sched_id; /* [B] */
+  const int32_t * m;        /* [S][N] */
+  const double * ridge;     /* [S][N][m_max][3] */
+  const double * vertex;    /* [S][N][m_max][3] */
+  const double * inertia;   /* [S][N][9] inertia_mat, row-major, symmetric positive definite */
+  const double * ref;       /* [S][N+1][6] pos, ori */
+  double w_run[13];  /* running_pos, running_ori, running_linear_vel, running_angular_vel (3 each), running_force */
+  double w_term[12]; /* terminal_pos, terminal_ori, terminal_linear_vel, terminal_angular_vel */
+  double u_lo, u_hi; /* force_scale_limits_ */
+  const double * x0;     /* [B][12] */
+  const double * u_init; /* [B][N][m_max] or NULL */
+} ccc_ddp_srb_batch_t;
+
+typedef struct ccc_ddp_srb_ws ccc_ddp_srb_ws_t;
+
+ccc_ddp_srb_ws_t * ccc_ddp_srb_create(int32_t horizon_steps, int32_t max_batch, int32_t max_sched);
+void ccc_ddp_srb_destroy(ccc_ddp_srb_ws_t * ws);
+
+/* Replaces: nmpc_ddp::DDPSolver<12,Dynamic>::solve as called at reference
+ * src/DdpSingleRigidBody.cpp:299,303 together with the DdpProblem callbacks at :41-245.
+ * result->x is [B][N+1][12]. */
+int32_t ccc_ddp_srb_solve(ccc_ddp_srb_ws_t * ws,
+                          const ccc_ddp_srb_batch_t * batch,
+                          const ccc_ddp_config_t * cfg,
+                          ccc_ddp_result_t * result,
+                          int32_t mem,
+                          void * stream);
+int32_t ccc_ddp_srb_last_launches(const ccc_ddp_srb_ws_t * ws);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 int32_t ccc_abi_version(void);
 int32_t ccc_device_count(void);

@@ -31,6 +31,10 @@ def lib():
         _LIB.ccc_oracle_centroidal_eval.restype = C.c_int32
         _LIB.ccc_oracle_centroidal_eval.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 10
         _LIB.ccc_oracle_hardware_threads.restype = C.c_int32
+        _LIB.ccc_oracle_ddp_srb_solve.restype = C.c_int32
+        _LIB.ccc_oracle_ddp_srb_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        _LIB.ccc_oracle_srb_eval.restype = C.c_int32
+        _LIB.ccc_oracle_srb_eval.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 10
     return _LIB
 
 
@@ -43,6 +47,16 @@ def ddp_centroidal_solve(problem_set, cfg, trace_len=0, n_threads=1):
     res = problem_set.new_result(trace_len)
     bs, rs = problem_set.as_struct(), res.as_struct()
     rc = lib().ccc_oracle_ddp_centroidal_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs), int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return res
+
+
+def ddp_srb_solve(problem_set, cfg, trace_len=0, n_threads=1):
+    """Run the oracle on a centroidalcontrolcollection_b200.problem.DdpSrbProblemSet."""
+    res = problem_set.new_result(trace_len)
+    bs, rs = problem_set.as_struct(), res.as_struct()
+    rc = lib().ccc_oracle_ddp_srb_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs), int(n_threads))
     if rc != 0:
         raise RuntimeError(f"oracle returned {rc}")
     return res

@@ -8,6 +8,7 @@
 // include/ccc_b200.h, so the same buffers can be handed to the oracle and to the engine.
 #include "../include/ccc_b200.h"
 #include "centroidal.hpp"
+#include "srb.hpp"
 
 #include <atomic>
 #include <thread>
@@ -213,6 +214,90 @@ int32_t ccc_oracle_centroidal_eval(const ccc_ddp_centroidal_batch_t * bt,
 void ccc_oracle_stats(int64_t * out)
 {
   for(int i = 0; i < 6; i++) out[i] = g_stats[i].exchange(0);
+}
+
+static void bindSrb(SrbProblem & p, const ccc_ddp_srb_batch_t * bt, int sched)
+{
+  const int N = bt->horizon_steps, mm = bt->m_max;
+  p.N = N;
+  p.dt = bt->dt;
+  p.mass = bt->mass;
+  p.m_max = mm;
+  p.m_tab = bt->m + static_cast<size_t>(sched) * N;
+  p.ridge = bt->ridge + static_cast<size_t>(sched) * N * mm * 3;
+  p.vertex = bt->vertex + static_cast<size_t>(sched) * N * mm * 3;
+  p.inertia = bt->inertia + static_cast<size_t>(sched) * N * 9;
+  p.ref = bt->ref + static_cast<size_t>(sched) * (N + 1) * 6;
+  for(int i = 0; i < 13; i++) p.w_run[i] = bt->w_run[i];
+  for(int i = 0; i < 12; i++) p.w_term[i] = bt->w_term[i];
+  p.u_lo = bt->u_lo;
+  p.u_hi = bt->u_hi;
+}
+
+/** Same contract as ccc_ddp_srb_solve with host pointers; n_threads host threads. */
+int32_t ccc_oracle_ddp_srb_solve(const ccc_ddp_srb_batch_t * bt, const ccc_ddp_config_t * c, ccc_ddp_result_t * r, int32_t n_threads)
+{
+  if(!bt || !c || !r || bt->m_max > 32 || bt->m_max < 0) return CCC_ERR_INVALID;
+  const int N = bt->horizon_steps, mm = bt->m_max;
+  DdpConfig cfg = toConfig(c);
+  parallelFor(bt->batch, n_threads, [&](int b) {
+    SrbProblem p;
+    bindSrb(p, bt, bt->sched_id[b]);
+    DdpSolver s(p);
+    s.cfg = cfg;
+    std::vector<std::vector<double>> u0(N);
+    for(int k = 0; k < N; k++)
+    {
+      int m = p.inputDim(k);
+      u0[k].assign(m, 0.0);
+      if(bt->u_init)
+        for(int j = 0; j < m; j++) u0[k][j] = bt->u_init[(static_cast<size_t>(b) * N + k) * mm + j];
+    }
+    s.solve(bt->x0 + static_cast<size_t>(b) * 12, u0);
+    storeResult(s, b, N, 12, mm, r);
+    for(int i = 0; i < 6; i++) g_stats[i] += s.stats[i];
+  });
+  return CCC_OK;
+}
+
+/** Problem functions of stage k of schedule 0 at (x, u): derivative known-answer tests
+ *  (reference tests/src/TestDdpSingleRigidBody.cpp:197-308).  Fx 12x12, Fu 12xm row-major. */
+int32_t ccc_oracle_srb_eval(const ccc_ddp_srb_batch_t * bt, int32_t k, const double * x, const double * u, double * xn,
+                            double * running_cost, double * terminal_cost, double * Fx, double * Fu, double * Lx,
+                            double * Lu, double * Vx)
+{
+  SrbProblem p;
+  bindSrb(p, bt, 0);
+  const int m = p.inputDim(k);
+  if(xn) p.stateEq(k, x, u, xn);
+  if(running_cost) *running_cost = p.runningCost(k, x, u);
+  if(terminal_cost) *terminal_cost = p.terminalCost(x);
+  if(Fx || Fu)
+  {
+    std::vector<double> fx(144), fu(12 * m);
+    p.stateEqDeriv(k, x, u, fx.data(), fu.data());
+    if(Fx) std::copy(fx.begin(), fx.end(), Fx);
+    if(Fu) std::copy(fu.begin(), fu.end(), Fu);
+  }
+  if(Lx || Lu)
+  {
+    std::vector<double> lx(12), lu(m), lxx(144), luu(m * m), lxu(12 * m);
+    p.runningCostDeriv(k, x, u, lx.data(), lu.data(), lxx.data(), luu.data(), lxu.data());
+    if(Lx) std::copy(lx.begin(), lx.end(), Lx);
+    if(Lu) std::copy(lu.begin(), lu.end(), Lu);
+  }
+  if(Vx)
+  {
+    std::vector<double> vxx(144);
+    p.terminalCostDeriv(x, Vx, vxx.data());
+  }
+  return CCC_OK;
+}
+
+/** sincos_canon(x) for accuracy tests. */
+void ccc_oracle_sincos(double x, double * s, double * c)
+{
+  sincos_canon(x, s, c);
 }
 
 int32_t ccc_oracle_hardware_threads(void)

@@ -61,6 +61,36 @@ inline void cross3(const double * a, const double * b, double * out)
   out[2] = std::fma(a[0], b[1], -(a[1] * b[0]));
 }
 
+/** sin and cos from +,-,*,fma and rint only, so that a GPU implementation of the same sequence
+ *  gives the same bits (libm's sin/cos differ between glibc and CUDA by up to 1-2 ulp):
+ *  Cody-Waite reduction by pi/2 in three parts, fdlibm's degree-13/14 minimax kernels on
+ *  [-pi/4, pi/4], quadrant fix-up.  Error vs the true value is ~1 ulp for |x| < 1e5. */
+inline void sincos_canon(double x, double * s_out, double * c_out)
+{
+  const double j = std::nearbyint(x * 6.36619772367581382433e-01);
+  double r = std::fma(-j, 1.57079632673412561417e+00, x);
+  r = std::fma(-j, 6.07710050650619224932e-11, r);
+  r = std::fma(-j, 2.02226624879595063154e-21, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = std::fma(ps, z, -2.50507602534068634195e-08);
+  ps = std::fma(ps, z, 2.75573137070700676789e-06);
+  ps = std::fma(ps, z, -1.98412698298579493134e-04);
+  ps = std::fma(ps, z, 8.33333333332248946124e-03);
+  ps = std::fma(ps, z, -1.66666666666666324348e-01);
+  const double sr = std::fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = std::fma(pc, z, 2.08757232129817482790e-09);
+  pc = std::fma(pc, z, -2.75573143513906633035e-07);
+  pc = std::fma(pc, z, 2.48015872894767294178e-05);
+  pc = std::fma(pc, z, -1.38888888888741095749e-03);
+  pc = std::fma(pc, z, 4.16666666666666019037e-02);
+  const double cr = std::fma(z * z, pc, std::fma(-0.5, z, 1.0));
+  const long long q = static_cast<long long>(j) & 3;
+  *s_out = q == 0 ? sr : q == 1 ? cr : q == 2 ? -sr : -cr;
+  *c_out = q == 0 ? cr : q == 1 ? -sr : q == 2 ? -cr : sr;
+}
+
 inline double clampd(double v, double lo, double hi)
 {
   // cwiseMax(lo).cwiseMin(hi)

@@ -11,6 +11,7 @@
 #define CCC_WARP_EMU 1
 #include "../../include/ccc_b200.h"
 #include "../../centroidalcontrolcollection_b200/csrc/model_centroidal.cuh"
+#include "../../centroidalcontrolcollection_b200/csrc/model_srb.cuh"
 
 #include <ucontext.h>
 
@@ -286,4 +287,31 @@ extern "C" int32_t ccc_emu_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t
   return emuSolve<ccc::CentroidalModel>(bt->horizon_steps, bt->batch, bt->n_sched, bt->m_max, bt->sched_id, bt->m,
                                         bt->ridge, bt->vertex, bt->ref_pos, bt->x0, bt->u_init, bt->w_run, bt->w_term,
                                         bt->u_lo, bt->u_hi, mp, c, r, [](double *) {});
+}
+
+extern "C" int32_t ccc_emu_ddp_srb_solve(const ccc_ddp_srb_batch_t * bt, const ccc_ddp_config_t * c, ccc_ddp_result_t * r)
+{
+  ccc::SrbModel::Params mp;
+  mp.dt = bt->dt;
+  mp.mass = bt->mass;
+  const int stages = bt->n_sched * bt->horizon_steps;
+  return emuSolve<ccc::SrbModel>(bt->horizon_steps, bt->batch, bt->n_sched, bt->m_max, bt->sched_id, bt->m, bt->ridge,
+                                 bt->vertex, bt->ref, bt->x0, bt->u_init, bt->w_run, bt->w_term, bt->u_lo, bt->u_hi, mp, c, r,
+                                 [&](double * tab) {
+                                   // srb_pack_inertia_kernel, on the host
+                                   for(int st = 0; st < stages; st++)
+                                   {
+                                     ccc::Inertia3 in;
+                                     for(int i = 0; i < 9; i++) in.I[i] = bt->inertia[(size_t)st * 9 + i];
+                                     in.factor();
+                                     double * row = tab + ((size_t)st * ccc::SrbModel::TAB_ROWS + 6) * 32;
+                                     for(int i = 0; i < 9; i++) row[i] = in.I[i];
+                                     row[9] = in.l10;
+                                     row[10] = in.l20;
+                                     row[11] = in.l21;
+                                     row[12] = in.i0;
+                                     row[13] = in.i1;
+                                     row[14] = in.i2;
+                                   }
+                                 });
 }

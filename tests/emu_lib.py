@@ -14,6 +14,8 @@ def lib():
         _LIB = C.CDLL(os.path.join(_HERE, "emu", "libccc_emu.so"))
         _LIB.ccc_emu_ddp_centroidal_solve.restype = C.c_int32
         _LIB.ccc_emu_ddp_centroidal_solve.argtypes = [C.c_void_p] * 3
+        _LIB.ccc_emu_ddp_srb_solve.restype = C.c_int32
+        _LIB.ccc_emu_ddp_srb_solve.argtypes = [C.c_void_p] * 3
     return _LIB
 
 
@@ -22,5 +24,14 @@ def ddp_centroidal_solve(problem_set, cfg, trace_len=0, chunk=0):
     res = problem_set.new_result(trace_len)
     bs, rs = problem_set.as_struct(), res.as_struct()
     rc = lib().ccc_emu_ddp_centroidal_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))
+    assert rc == 0
+    return res
+
+
+def ddp_srb_solve(problem_set, cfg, trace_len=0, chunk=0):
+    lib().ccc_emu_set_chunk(int(chunk))
+    res = problem_set.new_result(trace_len)
+    bs, rs = problem_set.as_struct(), res.as_struct()
+    rc = lib().ccc_emu_ddp_srb_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))
     assert rc == 0
     return res
