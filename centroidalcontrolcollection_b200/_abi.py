@@ -108,6 +108,21 @@ class DdpSrbBatch(C.Structure):
     ]
 
 
+class QpBatch(C.Structure):
+    """ccc_qp_batch_t"""
+
+    _fields_ = [("n", C.c_int32), ("n_eq", C.c_int32), ("n_ineq", C.c_int32), ("batch", C.c_int32),
+                ("Q", C.c_void_p), ("A", C.c_void_p), ("C", C.c_void_p),
+                ("c", C.c_void_p), ("b", C.c_void_p), ("d", C.c_void_p)]
+
+
+class QpResult(C.Structure):
+    """ccc_qp_result_t"""
+
+    _fields_ = [("x", C.c_void_p), ("iters", C.c_void_p), ("status", C.c_void_p), ("n_active", C.c_void_p),
+                ("active", C.c_void_p)]
+
+
 def ptr(a):
     """Address of a C-contiguous numpy array (or None)."""
     if a is None:

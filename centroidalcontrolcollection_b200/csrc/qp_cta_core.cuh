@@ -1,0 +1,592 @@
+// qp_cta_core.cuh — one CTA (128 threads) solves one strictly convex dense QP with the
+// Goldfarb-Idnani dual active-set method; Q, A, C are shared by the batch.
+//
+//   min 0.5 x'Qx + c'x   s.t.  A x = b,  C x <= d        n <= 128, n_ineq <= 256
+//
+// Replaces: QpSolverCollection::QpSolver::solve(QpCoeff &) as called at reference
+// src/LinearMpcZmp.cpp:69 and src/IntrinsicallyStableMpc.cpp:93.  Algorithm and evaluation order:
+// oracle/qp.hpp (bit-exact): thread i owns variable i / row i of J = L^-T Q_givens, thread j column
+// sums, sequential fma chains in the oracle's order; scalar products through a fixed 128-leaf tree;
+// the small triangular solve R r = d runs as a column sweep on warp 0.
+//
+// Shared memory per CTA: J and R (n x ld doubles each, ld odd so that both row- and column-wise
+// accesses are conflict free) + a few vectors: 170 KB at n = 100, one CTA per SM.
+#pragma once
+#include "warp_ctx.cuh"
+
+namespace ccc
+{
+constexpr int kQpThreads = 128;
+
+struct QpParams
+{
+  int n, me, mi, B, ld;
+  const double * J0; // [n][n]  L^-T of Q (setup kernel)
+  const double * At; // [n][me] transposed equality matrix
+  const double * Ct; // [n][mi] transposed inequality matrix
+  const double * c;  // [B][n] or null
+  const double * b;  // [B][me]
+  const double * d;  // [B][mi]
+  const int * setup_ok;
+  int max_iter;
+  double viol_tol;
+  double * out_x;
+  int * out_iters;
+  int * out_status;
+  int * out_n_active;
+  int * out_active; // [B][n]
+};
+
+CCC_DEV double givens_hypot(double a, double b)
+{
+  const double a1 = dabs(a), b1 = dabs(b);
+  if(a1 > b1)
+  {
+    const double t = a1 > 0 ? b1 / a1 : 0.0;
+    return a1 * dsqrt(dfma(t, t, 1.0));
+  }
+  if(b1 > a1)
+  {
+    const double t = a1 / b1;
+    return b1 * dsqrt(dfma(t, t, 1.0));
+  }
+  return a1 * dsqrt(2.0);
+}
+
+/** Shared-memory layout of one QP (offsets in doubles). */
+struct QpSm
+{
+  int n, ld;
+  CCC_DEV QpSm(int n_, int ld_) : n(n_), ld(ld_) {}
+  CCC_DEV int J() const { return 0; }
+  CCC_DEV int R() const { return n * ld; }
+  CCC_DEV int vec(int k) const { return 2 * n * ld + k * 128; } // x, z, d, np, r, u(+1 in next), tmp
+  CCC_DEV int red() const { return vec(8); }                     // 256 doubles: two trees / argmin values
+  CCC_DEV int ints() const { return vec(8) + 256; }              // int area (as doubles): A[129], is_active[264], ctrl
+  static size_t bytes(int n, int ld) { return (size_t)(2 * n * ld + 8 * 128 + 256 + 512) * sizeof(double); }
+};
+
+struct QpCtrl
+{
+  double t, s_ip;
+  int action; // 0: done/stop, 1: dual step only, 2: full step, 3: partial step
+  int l, ip, status;
+};
+
+struct QpCta
+{
+  const QpParams & P;
+  double * sm;
+  int b, tid, n, me, mi, ld;
+  double *J, *R, *x, *z, *d, *np, *r, *u, *tmp, *red;
+  int *A, *red_i;
+  unsigned char * is_active;
+  QpCtrl * ctrl;
+  int q;
+  double R_norm;
+
+  CCC_DEV QpCta(const QpParams & p, double * smem, int prob)
+  : P(p), sm(smem), b(prob), tid(thread_id()), n(p.n), me(p.me), mi(p.mi), ld(p.ld), q(0), R_norm(1.0)
+  {
+    QpSm L(n, ld);
+    J = sm + L.J();
+    R = sm + L.R();
+    x = sm + L.vec(0);
+    z = sm + L.vec(1);
+    d = sm + L.vec(2);
+    np = sm + L.vec(3);
+    r = sm + L.vec(4);
+    u = sm + L.vec(5); // 129 entries: spills one double into vec(6)'s first slot
+    tmp = sm + L.vec(7);
+    red = sm + L.red();
+    int * ib = reinterpret_cast<int *>(sm + L.ints());
+    A = ib;                                                        // 129 ints
+    red_i = ib + 132;                                              // 256 ints
+    is_active = reinterpret_cast<unsigned char *>(ib + 132 + 256); // 264 bytes
+    ctrl = reinterpret_cast<QpCtrl *>(ib + 132 + 256 + 72);
+  }
+
+  CCC_DEV double normal(int id, int j) const
+  {
+    return id < me ? ldg(P.At + (size_t)j * me + id) : -ldg(P.Ct + (size_t)j * mi + (id - me));
+  }
+
+  /** n_id . x + offset (>= 0 when satisfied) */
+  CCC_DEV double slack(int id) const
+  {
+    double acc = 0.0;
+    for(int j = 0; j < n; j++) acc = dfma(normal(id, j), x[j], acc);
+    return id < me ? acc - ldg(P.b + (size_t)b * me + id) : acc + ldg(P.d + (size_t)b * mi + (id - me));
+  }
+
+  /** two 128-leaf pairwise trees at once over (z.z, z.np); results in red[0], red[128] */
+  CCC_DEV void dot_trees()
+  {
+    red[tid] = tid < n ? z[tid] * z[tid] : 0.0;
+    red[128 + tid] = tid < n ? z[tid] * np[tid] : 0.0;
+    cta_sync();
+    for(int off = 64; off >= 1; off >>= 1)
+    {
+      if(tid < off)
+      {
+        red[tid] = red[tid] + red[tid + off];
+        red[128 + tid] = red[128 + tid] + red[128 + tid + off];
+      }
+      cta_sync();
+    }
+  }
+
+  /** d = J' np, z = J[:, q:] d[q:], r = R^-1 d[:q] */
+  CCC_DEV void compute_dzr()
+  {
+    if(tid < n)
+    {
+      double acc = 0.0;
+      for(int i = 0; i < n; i++) acc = dfma(J[i * ld + tid], np[i], acc);
+      d[tid] = acc;
+    }
+    cta_sync();
+    if(tid < n)
+    {
+      double acc = 0.0;
+      for(int j = q; j < n; j++) acc = dfma(J[tid * ld + j], d[j], acc);
+      z[tid] = acc;
+    }
+    if(tid < 32)
+    {
+      // column sweep of the back substitution on warp 0: lane owns rows lane, lane+32, lane+64, lane+96
+      double a0 = tid < q ? d[tid] : 0.0, a1 = tid + 32 < q ? d[tid + 32] : 0.0;
+      double a2 = tid + 64 < q ? d[tid + 64] : 0.0, a3 = tid + 96 < q ? d[tid + 96] : 0.0;
+      for(int i = q - 1; i >= 0; i--)
+      {
+        if((i & 31) == tid)
+        {
+          const int slot = i >> 5;
+          const double a = slot == 0 ? a0 : slot == 1 ? a1 : slot == 2 ? a2 : a3;
+          r[i] = a / R[i * ld + i];
+        }
+        warp_sync();
+        const double ri = r[i];
+        if(tid < i) a0 = dfma(-R[tid * ld + i], ri, a0);
+        if(tid + 32 < i) a1 = dfma(-R[(tid + 32) * ld + i], ri, a1);
+        if(tid + 64 < i) a2 = dfma(-R[(tid + 64) * ld + i], ri, a2);
+        if(tid + 96 < i) a3 = dfma(-R[(tid + 96) * ld + i], ri, a3);
+      }
+    }
+    cta_sync();
+  }
+
+  /** Givens sweep that turns d into (d[0..q-1], +-|d[q..]|, 0...) and rotates J; appends the column to R.
+   *  Returns false if the new constraint is linearly dependent on the active ones. */
+  CCC_DEV bool add_constraint()
+  {
+    const double eps = 2.220446049250313e-16;
+    double dj = d[n - 1];
+    if(tid < n)
+    {
+      double * row = J + tid * ld;
+      for(int j = n - 1; j >= q + 1; j--)
+      {
+        double cc = d[j - 1], ss = dj;
+        const double h = givens_hypot(cc, ss);
+        if(dabs(h) < eps)
+        {
+          dj = cc;
+          continue;
+        }
+        ss = ss / h;
+        cc = cc / h;
+        if(cc < 0.0)
+        {
+          cc = -cc;
+          ss = -ss;
+          dj = -h;
+        }
+        else
+          dj = h;
+        const double xny = ss / (1.0 + cc);
+        const double t1 = row[j - 1], t2 = row[j];
+        const double a = dfma(t2, ss, t1 * cc);
+        row[j - 1] = a;
+        row[j] = dfma(xny, t1 + a, -t2);
+      }
+    }
+    else
+    {
+      // threads beyond n only need the final value of the scalar chain
+      for(int j = n - 1; j >= q + 1; j--)
+      {
+        double cc = d[j - 1], ss = dj;
+        const double h = givens_hypot(cc, ss);
+        if(dabs(h) < eps)
+        {
+          dj = cc;
+          continue;
+        }
+        cc = cc / h;
+        dj = cc < 0.0 ? -h : h;
+      }
+    }
+    cta_sync();
+    if(tid < q) R[tid * ld + q] = d[tid];
+    if(tid == 0) R[q * ld + q] = dj;
+    q++;
+    const bool ok = !(dabs(dj) <= eps * R_norm);
+    if(ok) R_norm = R_norm < dabs(dj) ? dabs(dj) : R_norm;
+    cta_sync();
+    return ok;
+  }
+
+  CCC_DEV void delete_constraint(int l)
+  {
+    const double eps = 2.220446049250313e-16;
+    int qq = -1;
+    for(int i = me; i < q; i++)
+      if(A[i] == l)
+      {
+        qq = i;
+        break;
+      }
+    cta_sync();
+    if(qq < 0) return;
+    if(tid < n)
+    {
+      for(int i = qq; i < q - 1; i++) R[tid * ld + i] = R[tid * ld + i + 1];
+    }
+    if(tid == 0)
+    {
+      for(int i = qq; i < q - 1; i++)
+      {
+        A[i] = A[i + 1];
+        u[i] = u[i + 1];
+      }
+      A[q - 1] = A[q];
+      u[q - 1] = u[q];
+      A[q] = -1;
+      u[q] = 0.0;
+    }
+    cta_sync();
+    if(tid < q) R[tid * ld + q - 1] = 0.0;
+    q--;
+    cta_sync();
+    if(q == 0) return;
+    for(int j = qq; j < q; j++)
+    {
+      double cc = R[j * ld + j], ss = R[(j + 1) * ld + j];
+      cta_sync(); // everyone has read the pivot pair before it is rewritten
+      const double h = givens_hypot(cc, ss);
+      if(dabs(h) < eps) continue;
+      cc = cc / h;
+      ss = ss / h;
+      double rjj;
+      if(cc < 0.0)
+      {
+        rjj = -h;
+        cc = -cc;
+        ss = -ss;
+      }
+      else
+        rjj = h;
+      const double xny = ss / (1.0 + cc);
+      if(tid == 0)
+      {
+        R[(j + 1) * ld + j] = 0.0;
+        R[j * ld + j] = rjj;
+      }
+      if(tid > j && tid < q)
+      {
+        const double t1 = R[j * ld + tid], t2 = R[(j + 1) * ld + tid];
+        const double a = dfma(t2, ss, t1 * cc);
+        R[j * ld + tid] = a;
+        R[(j + 1) * ld + tid] = dfma(xny, t1 + a, -t2);
+      }
+      if(tid < n)
+      {
+        const double t1 = J[tid * ld + j], t2 = J[tid * ld + j + 1];
+        const double a = dfma(t2, ss, t1 * cc);
+        J[tid * ld + j] = a;
+        J[tid * ld + j + 1] = dfma(xny, t1 + a, -t2);
+      }
+      cta_sync();
+    }
+  }
+
+  CCC_DEV void solve()
+  {
+    const double inf = 1.0 / 0.0;
+    const double eps = 2.220446049250313e-16;
+    int status = 0, iter = 0;
+    if(ldg(P.setup_ok) == 0)
+    {
+      if(tid < n && P.out_x) P.out_x[(size_t)b * n + tid] = 0.0;
+      if(tid == 0)
+      {
+        if(P.out_iters) P.out_iters[b] = 0;
+        if(P.out_status) P.out_status[b] = 3;
+        if(P.out_n_active) P.out_n_active[b] = 0;
+      }
+      if(tid < n && P.out_active) P.out_active[(size_t)b * n + tid] = -1;
+      return;
+    }
+    // load the shared factor, reset the bookkeeping
+    for(int e = tid; e < n * n; e += kQpThreads) J[(e / n) * ld + (e % n)] = ldg(P.J0 + e);
+    for(int e = tid; e < me + mi; e += kQpThreads) is_active[e] = 0;
+    for(int e = tid; e <= n; e += kQpThreads)
+    {
+      A[e] = -1;
+      u[e] = 0.0;
+    }
+    cta_sync();
+    // unconstrained minimiser x = -J (J' c)
+    if(tid < n)
+    {
+      double acc = 0.0;
+      if(P.c)
+        for(int i = 0; i < n; i++) acc = dfma(J[i * ld + tid], ldg(P.c + (size_t)b * n + i), acc);
+      tmp[tid] = acc;
+    }
+    cta_sync();
+    if(tid < n)
+    {
+      double acc = 0.0;
+      for(int j = 0; j < n; j++) acc = dfma(J[tid * ld + j], tmp[j], acc);
+      x[tid] = -acc;
+    }
+    cta_sync();
+
+    // equality constraints: always active, one full step each
+    for(int e = 0; e < me && status == 0; e++)
+    {
+      if(tid < n) np[tid] = normal(e, tid);
+      cta_sync();
+      compute_dzr();
+      dot_trees();
+      if(tid == 0)
+      {
+        double t2 = 0.0;
+        if(dabs(red[0]) > eps) t2 = (-slack(e)) / red[128];
+        ctrl->t = t2;
+      }
+      cta_sync();
+      const double t2 = ctrl->t;
+      if(tid < n) x[tid] = dfma(t2, z[tid], x[tid]);
+      if(tid < q) u[tid] = dfma(-t2, r[tid], u[tid]);
+      if(tid == 0)
+      {
+        u[q] = t2;
+        A[q] = e;
+        is_active[e] = 1;
+      }
+      cta_sync();
+      if(!add_constraint()) status = 1;
+    }
+
+    bool need_pick = true;
+    int ip = -1;
+    double s_ip = 0.0;
+    while(status == 0)
+    {
+      if(need_pick)
+      {
+        // most violated inactive inequality, lowest index on ties
+        double best = -P.viol_tol;
+        int best_i = -1;
+        for(int i = tid; i < mi; i += kQpThreads)
+        {
+          if(is_active[me + i]) continue;
+          const double s = slack(me + i);
+          if(s < best)
+          {
+            best = s;
+            best_i = i;
+          }
+        }
+        red[tid] = best;
+        red_i[tid] = best_i;
+        cta_sync();
+        for(int off = 64; off >= 1; off >>= 1)
+        {
+          if(tid < off)
+          {
+            const double so = red[tid + off];
+            const int io = red_i[tid + off];
+            const double sa = red[tid];
+            const int ia = red_i[tid];
+            const bool take = io >= 0 && (ia < 0 || so < sa || (so == sa && io < ia));
+            if(take)
+            {
+              red[tid] = so;
+              red_i[tid] = io;
+            }
+          }
+          cta_sync();
+        }
+        const int pick = red_i[0];
+        const double worst = red[0];
+        cta_sync();
+        if(pick < 0) break; // optimal
+        if(q >= n)
+        {
+          status = 4;
+          break;
+        }
+        iter++;
+        if(iter > P.max_iter)
+        {
+          status = 2;
+          break;
+        }
+        ip = me + pick;
+        s_ip = worst;
+        if(tid < n) np[tid] = normal(ip, tid);
+        if(tid == 0)
+        {
+          u[q] = 0.0;
+          A[q] = ip;
+        }
+        cta_sync();
+      }
+      compute_dzr();
+      dot_trees();
+      if(tid == 0)
+      {
+        int l = -1;
+        double t1 = inf;
+        for(int k = me; k < q; k++)
+          if(r[k] > 0.0)
+          {
+            const double ratio = u[k] / r[k];
+            if(ratio < t1)
+            {
+              t1 = ratio;
+              l = A[k];
+            }
+          }
+        double t2 = inf;
+        if(dabs(red[0]) > eps) t2 = (-s_ip) / red[128];
+        const double t = t1 < t2 ? t1 : t2;
+        ctrl->t = t;
+        ctrl->l = l;
+        if(!(t < inf))
+          ctrl->action = 0; // infeasible
+        else if(!(t2 < inf))
+          ctrl->action = 1;
+        else if(t == t2)
+          ctrl->action = 2;
+        else
+          ctrl->action = 3;
+      }
+      cta_sync();
+      const double t = ctrl->t;
+      const int action = ctrl->action, l = ctrl->l;
+      if(action == 0)
+      {
+        status = 1;
+        break;
+      }
+      if(action == 1)
+      {
+        if(tid < q) u[tid] = dfma(-t, r[tid], u[tid]);
+        if(tid == 0)
+        {
+          u[q] = u[q] + t;
+          is_active[l] = 0;
+        }
+        cta_sync();
+        delete_constraint(l);
+        need_pick = false;
+        continue;
+      }
+      if(tid < n) x[tid] = dfma(t, z[tid], x[tid]);
+      if(tid < q) u[tid] = dfma(-t, r[tid], u[tid]);
+      if(tid == 0) u[q] = u[q] + t;
+      cta_sync();
+      if(action == 2)
+      {
+        if(!add_constraint())
+        {
+          status = 1;
+          break;
+        }
+        if(tid == 0) is_active[ip] = 1;
+        cta_sync();
+        need_pick = true;
+      }
+      else
+      {
+        if(tid == 0) is_active[l] = 0;
+        cta_sync();
+        delete_constraint(l);
+        if(tid == 0) ctrl->s_ip = slack(ip);
+        cta_sync();
+        s_ip = ctrl->s_ip;
+        need_pick = false;
+      }
+    }
+    cta_sync();
+    if(tid < n)
+    {
+      if(P.out_x) P.out_x[(size_t)b * n + tid] = x[tid];
+      if(P.out_active) P.out_active[(size_t)b * n + tid] = tid < q ? A[tid] : -1;
+    }
+    if(tid == 0)
+    {
+      if(P.out_iters) P.out_iters[b] = iter;
+      if(P.out_status) P.out_status[b] = status;
+      if(P.out_n_active) P.out_n_active[b] = q;
+    }
+    cta_sync();
+  }
+};
+} // namespace ccc
+
+namespace ccc
+{
+/** Batch-invariant setup, one CTA: L = chol(Q) (scratch Lg), J0 = L^-T, transposed A and C.
+ *  Evaluation order: oracle/qp.hpp DenseQpShared::setup. */
+CCC_DEV void qp_setup_cta(int n, int me, int mi, const double * Q, const double * A, const double * C, double * Lg,
+                          double * invd, double * J0, double * At, double * Ct, int * ok_flag)
+{
+  const int tid = thread_id();
+  if(tid == 0) *ok_flag = 1;
+  cta_sync();
+  for(int k = 0; k < n; k++)
+  {
+    if(tid == 0)
+    {
+      double acc = Q[k * n + k];
+      for(int j = 0; j < k; j++) acc = dfma(-Lg[k * n + j], Lg[k * n + j], acc);
+      if(!(acc > 0.0))
+      {
+        *ok_flag = 0;
+        acc = 1.0;
+      }
+      const double dd = dsqrt(acc);
+      Lg[k * n + k] = dd;
+      invd[k] = 1.0 / dd;
+    }
+    cta_sync();
+    for(int i = k + 1 + tid; i < n; i += kQpThreads)
+    {
+      double a = Q[i * n + k];
+      for(int j = 0; j < k; j++) a = dfma(-Lg[i * n + j], Lg[k * n + j], a);
+      Lg[i * n + k] = a * invd[k];
+    }
+    cta_sync();
+  }
+  // row i of J0 = L^-1 e_i (forward substitution), one thread per row; z lives in row i of J0
+  for(int i = tid; i < n; i += kQpThreads)
+  {
+    double * zrow = J0 + (size_t)i * n;
+    for(int r = 0; r < n; r++)
+    {
+      double acc = r == i ? 1.0 : 0.0;
+      for(int j = 0; j < r; j++) acc = dfma(-Lg[r * n + j], zrow[j], acc);
+      zrow[r] = acc * invd[r];
+    }
+  }
+  for(int e = tid; e < n * me; e += kQpThreads) At[e] = A[(e % me) * n + e / me];
+  for(int e = tid; e < n * mi; e += kQpThreads) Ct[e] = C[(size_t)(e % mi) * n + e / mi];
+  cta_sync();
+}
+} // namespace ccc

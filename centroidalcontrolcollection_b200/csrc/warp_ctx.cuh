@@ -13,7 +13,9 @@
 namespace ccc_emu
 {
 int lane();
+int tid();
 void syncwarp();
+void syncthreads();
 double shfl(double v, int src);
 double shfl_xor(double v, int mask);
 int shfl_i(int v, int src);
@@ -28,6 +30,8 @@ namespace ccc
 {
 inline int lane_id() { return ccc_emu::lane(); }
 inline void warp_sync() { ccc_emu::syncwarp(); }
+inline int thread_id() { return ccc_emu::tid(); }
+inline void cta_sync() { ccc_emu::syncthreads(); }
 inline double warp_shfl(double v, int src) { return ccc_emu::shfl(v, src); }
 inline double warp_shfl_xor(double v, int mask) { return ccc_emu::shfl_xor(v, mask); }
 inline int warp_shfl_i(int v, int src) { return ccc_emu::shfl_i(v, src); }
@@ -54,6 +58,8 @@ namespace ccc
 constexpr unsigned kFullMask = 0xffffffffu;
 CCC_DEV int lane_id() { return static_cast<int>(threadIdx.x & 31u); }
 CCC_DEV void warp_sync() { __syncwarp(); }
+CCC_DEV int thread_id() { return static_cast<int>(threadIdx.x); }
+CCC_DEV void cta_sync() { __syncthreads(); }
 CCC_DEV double warp_shfl(double v, int src) { return __shfl_sync(kFullMask, v, src); }
 CCC_DEV double warp_shfl_xor(double v, int mask) { return __shfl_xor_sync(kFullMask, v, mask); }
 CCC_DEV int warp_shfl_i(int v, int src) { return __shfl_sync(kFullMask, v, src); }

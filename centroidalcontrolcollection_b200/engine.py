@@ -20,6 +20,7 @@ EXPORTS = [
     "ccc_ddp_centroidal_create", "ccc_ddp_centroidal_destroy", "ccc_ddp_centroidal_solve",
     "ccc_ddp_centroidal_last_launches",
     "ccc_ddp_srb_create", "ccc_ddp_srb_destroy", "ccc_ddp_srb_solve", "ccc_ddp_srb_last_launches",
+    "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches",
 ]
 
 
@@ -60,6 +61,14 @@ def lib():
         L.ccc_ddp_srb_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_ddp_srb_last_launches.restype = C.c_int32
         L.ccc_ddp_srb_last_launches.argtypes = [C.c_void_p]
+        L.ccc_qp_create.restype = C.c_void_p
+        L.ccc_qp_create.argtypes = [C.c_int32] * 4
+        L.ccc_qp_destroy.argtypes = [C.c_void_p]
+        L.ccc_qp_destroy.restype = None
+        L.ccc_qp_solve.restype = C.c_int32
+        L.ccc_qp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ccc_qp_last_launches.restype = C.c_int32
+        L.ccc_qp_last_launches.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -133,3 +142,51 @@ class DdpCentroidalEngine(_DdpEngineBase):
     def set_chunk(iters):
         """Tuning hook: DDP iterations per visit before a solve is suspended and re-queued (0 = never)."""
         lib().ccc_ddp_centroidal_set_chunk(int(iters))
+
+
+class QpEngine:
+    """Batched counterpart of QpSolverCollection::QpSolver (reference src/LinearMpcZmp.cpp:21,69,
+    src/IntrinsicallyStableMpc.cpp:28,93): one workspace per problem shape, solves batches that share Q, A, C."""
+
+    def __init__(self, n, n_eq, n_ineq, max_batch):
+        self._h = lib().ccc_qp_create(int(n), int(n_eq), int(n_ineq), int(max_batch))
+        if not self._h:
+            raise EngineError(f"ccc_qp_create failed: {last_error()}")
+        self.shape = (n, n_eq, n_ineq)
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ccc_qp_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def solve(self, problem_set, result=None):
+        """Host buffers in/out (H2D + setup + solve + D2H, synchronous)."""
+        res = result if result is not None else problem_set.new_result()
+        bs, rs = problem_set.as_struct(), res.as_struct()
+        _check(lib().ccc_qp_solve(self._h, C.addressof(bs), C.addressof(rs), _abi.CCC_MEM_HOST, None), "ccc_qp_solve")
+        return res
+
+    def solve_device(self, batch_struct, result_struct, stream=0):
+        _check(lib().ccc_qp_solve(self._h, C.addressof(batch_struct), C.addressof(result_struct), _abi.CCC_MEM_DEVICE,
+                                  C.c_void_p(stream)), "ccc_qp_solve")
+
+    @property
+    def last_launches(self):
+        return int(lib().ccc_qp_last_launches(self._h))
+
+
+def qp_solver_for(engines=None):
+    """-> qp_solve(QpProblemSet) callable backed by QpEngine workspaces cached per shape."""
+    engines = {} if engines is None else engines
+
+    def qp_solve(ps):
+        key = (ps.n, ps.n_eq, ps.n_ineq)
+        eng = engines.get(key)
+        if eng is None or eng.max_batch < ps.batch:
+            eng = engines[key] = QpEngine(ps.n, ps.n_eq, ps.n_ineq, max(ps.batch, 1))
+        return eng.solve(ps)
+
+    return qp_solve

@@ -149,3 +149,81 @@ def ddp_srb_config4(batch=65536, horizon_steps=100, dt=0.03, seed=20260103):
     return dict(name=f"DdpSingleRigidBody N={horizon_steps} dt={dt} A-flight-B schedule batch={batch}", mass=100.0, dt=dt,
                 N=horizon_steps, sched=sched, sched_id=np.zeros(batch, dtype=np.int32), x0=x0, w_run=w_run,
                 w_term=w_term, u_lo=0.0, u_hi=1e6)
+
+
+# ---- QP-based ZMP methods (configs 2 and 5) --------------------------------------------------------
+def _walking_limits(step_length, step_width, t0, horizon_steps, horizon_dt, eps_reps):
+    """ZMP limits and reference ZMP of the six-step walking plan (reference
+    tests/src/TestLinearMpcZmp.cpp:30-41) over a horizon starting at t0.  Self-contained restatement of the
+    schedule the reference's FootstepManager produces (tests/footstep_manager.py is the fixture copy used to
+    cross-check it): returns (ref_zmp[N][2], lim_min[N][2], lim_max[N][2])."""
+    foot_size = np.array([0.1, 0.05])
+    L, w = step_length, 0.5 * step_width
+    stance = {0: np.array([0.0, w]), 1: np.array([0.0, -w])}
+    steps = [(0, (L, w), 2.0), (1, (2 * L, -w), 3.0), (0, (3 * L, w), 4.0), (1, (4 * L, -w), 5.0), (0, (3 * L, w), 6.0),
+             (1, (3 * L, -w), 7.0)]
+    transit, swing = 0.2, 0.8
+    mid = lambda st: next(iter(st.values())) if len(st) == 1 else 0.5 * (st[0] + st[1])
+    zmp_knots, stance_knots = [(-1e9, mid(stance))], [(-1e9, dict(stance))]
+    tmp = dict(stance)
+    for foot, pos, ts in steps:
+        pos = np.array(pos)
+        t_sw0, t_sw1, t_end = ts + 0.5 * transit, ts + 0.5 * transit + swing, ts + transit + swing
+        zmp_knots.append((ts, mid(tmp)))
+        stance_knots.append((ts, dict(tmp)))
+        tmp.pop(foot)
+        zmp_knots.append((t_sw0, tmp[1 - foot].copy()))
+        stance_knots.append((t_sw0, dict(tmp)))
+        tmp[foot] = pos
+        zmp_knots.append((t_sw1, tmp[1 - foot].copy()))
+        stance_knots.append((t_sw1, dict(tmp)))
+        zmp_knots.append((t_end, mid(tmp)))
+    zmp_knots.append((1e9, mid(tmp)))
+    ref, lo, hi = np.zeros((horizon_steps, 2)), np.zeros((horizon_steps, 2)), np.zeros((horizon_steps, 2))
+    zt = [k[0] for k in zmp_knots]
+    stt = [k[0] for k in stance_knots]
+    for i in range(horizon_steps):
+        t = t0 + i * horizon_dt + eps_reps * EPS_T
+        j = int(np.searchsorted(zt, t, side="right"))
+        (ta, za), (tb, zb) = zmp_knots[j - 1], zmp_knots[j]
+        ratio = 0.0 if tb - ta > 1e8 else (t - ta) / (tb - ta)
+        ref[i] = (1 - ratio) * za + ratio * zb
+        st = stance_knots[int(np.searchsorted(stt, t, side="right")) - 1][1]
+        pts = np.array(list(st.values()))
+        lo[i], hi[i] = pts.min(axis=0) - 0.5 * foot_size, pts.max(axis=0) + 0.5 * foot_size
+    return ref, lo, hi
+
+
+def linear_mpc_zmp_config2(batch=4096, t0=1.8, seed=20260101):
+    """Config 2: LinearMpcZmp, h = 1.0, N = 100, dt = 0.01, control_dt = 0.005, one shared footstep plan sampled
+    at t0 (the horizon contains a support change), perturbed ICs around mid-stance."""
+    h, N, dt = 1.0, 100, 0.01
+    _, lo, hi = _walking_limits(0.2, 0.2, t0, N, dt, eps_reps=2)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mid = np.array([0.0, 0.0])
+    pos = mid + rng.uniform(-0.03, 0.03, (batch, 2))
+    vel = rng.uniform(-0.15, 0.15, (batch, 2))
+    acc = 9.80665 / h * (pos - mid)
+    return dict(name=f"LinearMpcZmp N={N} dt={dt} batch={batch} (x2 axes)", com_height=h, horizon_duration=N * dt,
+                horizon_dt=dt, control_dt=0.005, pos=pos, vel=vel, acc=acc, lim_min=np.tile(lo[None], (batch, 1, 1)),
+                lim_max=np.tile(hi[None], (batch, 1, 1)))
+
+
+def ismpc_config5(n_plans=256, n_perturb=512, t0=1.8, seed=20260104):
+    """Config 5: IntrinsicallyStableMpc, h = 1.0, N = 100 (2.0 / 0.02), control_dt = 0.005; n_plans footstep plans
+    (16 step lengths x 16 step widths for the default 256) x n_perturb capture-point perturbations."""
+    h, N, dt = 1.0, 100, 0.02
+    rng = np.random.Generator(np.random.PCG64(seed))
+    side = int(round(np.sqrt(n_plans)))
+    lengths, widths = rng.uniform(0.1, 0.3, side), rng.uniform(0.16, 0.24, max(n_plans // side, 1))
+    refs, los, his = [], [], []
+    for p in range(n_plans):
+        r, lo, hi = _walking_limits(lengths[p % side], widths[(p // side) % len(widths)], t0, N, dt, eps_reps=2)
+        refs.append(r), los.append(lo), his.append(hi)
+    plan = np.repeat(np.arange(n_plans), n_perturb)
+    B = n_plans * n_perturb
+    cp = rng.uniform(-0.04, 0.04, (B, 2))
+    return dict(name=f"IntrinsicallyStableMpc N={N} dt={dt} {n_plans} plans x {n_perturb} perturbations (x2 axes)",
+                com_height=h, horizon_duration=N * dt, horizon_dt=dt, control_dt=0.005, capture_point=cp,
+                planned_zmp=np.zeros((B, 2)), ref_zmp=np.array(refs)[plan], lim_min=np.array(los)[plan],
+                lim_max=np.array(his)[plan])

@@ -178,6 +178,40 @@ int32_t ccc_ddp_srb_solve(ccc_ddp_srb_ws_t * ws,
                           void * stream);
 int32_t ccc_ddp_srb_last_launches(const ccc_ddp_srb_ws_t * ws);
 
+/* ---- QpSolverCollection::QpSolver::solve(QpCoeff &) -------------------------------------------
+ * Batched strictly convex dense QP with the matrices shared by the batch:
+ *     min 0.5 x'Qx + c'x   s.t.  A x = b,  C x <= d
+ * Replaces: qp_solver_->solve(qp_coeff_) at reference src/LinearMpcZmp.cpp:69 (Q = I, c = 0, no
+ * equality, C = [-B_seq; B_seq]) and src/IntrinsicallyStableMpc.cpp:93 (Q = w_vel I + w_zmp P'P, one
+ * equality, C = [-P; P]).  QpCoeff fields: obj_mat_ = Q, obj_vec_ = c, eq_mat_/eq_vec_ = A/b,
+ * ineq_mat_/ineq_vec_ = C/d; x_min_/x_max_ are +-1e10 on this path and not represented.
+ * Limits of the kernel: n <= 128, n_ineq <= 256, n_eq <= 8. */
+typedef struct
+{
+  int32_t n, n_eq, n_ineq, batch;
+  const double * Q; /* [n][n]       shared */
+  const double * A; /* [n_eq][n]    shared (NULL if n_eq = 0) */
+  const double * C; /* [n_ineq][n]  shared */
+  const double * c; /* [B][n]       or NULL = 0 */
+  const double * b; /* [B][n_eq]    (NULL if n_eq = 0) */
+  const double * d; /* [B][n_ineq] */
+} ccc_qp_batch_t;
+
+typedef struct
+{
+  double * x;         /* [B][n] minimiser */
+  int32_t * iters;    /* [B] constraints picked by the dual active-set loop */
+  int32_t * status;   /* [B] 0 solved, 1 infeasible, 2 iteration limit, 3 Q not positive definite, 4 active set full */
+  int32_t * n_active; /* [B] size of the final active set (equalities included) */
+  int32_t * active;   /* [B][n] ids in activation order (0..n_eq-1 equalities, n_eq + i inequality i), -1 padded */
+} ccc_qp_result_t;
+
+typedef struct ccc_qp_ws ccc_qp_ws_t;
+ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max_batch);
+void ccc_qp_destroy(ccc_qp_ws_t * ws);
+int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * batch, ccc_qp_result_t * result, int32_t mem, void * stream);
+int32_t ccc_qp_last_launches(const ccc_qp_ws_t * ws);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 int32_t ccc_abi_version(void);
 int32_t ccc_device_count(void);

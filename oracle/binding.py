@@ -60,3 +60,16 @@ def ddp_srb_solve(problem_set, cfg, trace_len=0, n_threads=1):
     if rc != 0:
         raise RuntimeError(f"oracle returned {rc}")
     return res
+
+
+def qp_solve(problem_set, n_threads=1):
+    """Run the oracle on a centroidalcontrolcollection_b200.qp.QpProblemSet."""
+    L = lib()
+    L.ccc_oracle_qp_solve.restype = C.c_int32
+    L.ccc_oracle_qp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    res = problem_set.new_result()
+    bs, rs = problem_set.as_struct(), res.as_struct()
+    rc = L.ccc_oracle_qp_solve(C.addressof(bs), C.addressof(rs), int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return res

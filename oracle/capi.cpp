@@ -9,6 +9,7 @@
 #include "../include/ccc_b200.h"
 #include "centroidal.hpp"
 #include "srb.hpp"
+#include "qp.hpp"
 
 #include <atomic>
 #include <thread>
@@ -291,6 +292,35 @@ int32_t ccc_oracle_srb_eval(const ccc_ddp_srb_batch_t * bt, int32_t k, const dou
     std::vector<double> vxx(144);
     p.terminalCostDeriv(x, Vx, vxx.data());
   }
+  return CCC_OK;
+}
+
+/** Same contract as ccc_qp_solve with host pointers; n_threads host threads. */
+int32_t ccc_oracle_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t * r, int32_t n_threads)
+{
+  if(!bt || !r || bt->n <= 0 || bt->n > 128) return CCC_ERR_INVALID;
+  const int n = bt->n, me = bt->n_eq, mi = bt->n_ineq;
+  DenseQpShared S;
+  S.n = n;
+  S.me = me;
+  S.mi = mi;
+  S.Q.assign(bt->Q, bt->Q + static_cast<size_t>(n) * n);
+  if(me) S.A.assign(bt->A, bt->A + static_cast<size_t>(me) * n);
+  S.C.assign(bt->C, bt->C + static_cast<size_t>(mi) * n);
+  S.setup();
+  parallelFor(bt->batch, n_threads, [&](int b) {
+    DenseQpSolver solver(S);
+    DenseQpResult res = solver.solve(bt->c ? bt->c + static_cast<size_t>(b) * n : nullptr,
+                                     me ? bt->b + static_cast<size_t>(b) * me : nullptr, bt->d + static_cast<size_t>(b) * mi);
+    if(r->x)
+      for(int i = 0; i < n; i++) r->x[static_cast<size_t>(b) * n + i] = res.x[i];
+    if(r->iters) r->iters[b] = res.iters;
+    if(r->status) r->status[b] = res.status;
+    if(r->n_active) r->n_active[b] = static_cast<int32_t>(res.active.size());
+    if(r->active)
+      for(int i = 0; i < n; i++)
+        r->active[static_cast<size_t>(b) * n + i] = i < static_cast<int>(res.active.size()) ? res.active[i] : -1;
+  });
   return CCC_OK;
 }
 

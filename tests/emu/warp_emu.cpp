@@ -12,6 +12,7 @@
 #include "../../include/ccc_b200.h"
 #include "../../centroidalcontrolcollection_b200/csrc/model_centroidal.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/model_srb.cuh"
+#include "../../centroidalcontrolcollection_b200/csrc/qp_cta_core.cuh"
 
 #include <ucontext.h>
 
@@ -26,24 +27,26 @@ namespace ccc_emu
 {
 namespace
 {
-constexpr int kLanes = 32;
+constexpr int kMaxThreads = 128;
 constexpr size_t kStack = 1 << 20;
-ucontext_t g_main, g_ctx[kLanes];
+ucontext_t g_main, g_ctx[kMaxThreads];
 std::vector<char> g_stacks;
-bool g_done[kLanes];
-int g_cur = 0, g_alive = 0, g_arrived = 0;
-unsigned long g_gen = 0;
-double g_xd[kLanes];
-int g_xi[kLanes];
+bool g_done[kMaxThreads];
+int g_cur = 0, g_nthreads = 32, g_alive = 0;
+// barrier groups: 0..3 = the four warps, 4 = the whole CTA
+int g_arrived[5] = {0, 0, 0, 0, 0};
+unsigned long g_gen[5] = {0, 0, 0, 0, 0};
+double g_xd[kMaxThreads];
+int g_xi[kMaxThreads];
 std::function<void()> g_body;
 
 void yield()
 {
   int from = g_cur;
   int nxt = from;
-  for(int s = 1; s <= kLanes; s++)
+  for(int s = 1; s <= g_nthreads; s++)
   {
-    int c = (from + s) % kLanes;
+    int c = (from + s) % g_nthreads;
     if(!g_done[c])
     {
       nxt = c;
@@ -55,18 +58,24 @@ void yield()
   swapcontext(&g_ctx[from], &g_ctx[nxt]);
 }
 
-void barrier()
+void barrier(int group, int size)
 {
-  unsigned long gen = g_gen;
-  if(++g_arrived == g_alive)
+  unsigned long gen = g_gen[group];
+  if(++g_arrived[group] == size)
   {
-    g_arrived = 0;
-    g_gen++;
+    g_arrived[group] = 0;
+    g_gen[group]++;
   }
   else
   {
-    while(g_gen == gen) yield();
+    while(g_gen[group] == gen) yield();
   }
+}
+
+int warp_size_of(int w)
+{
+  int lo = w * 32, hi = lo + 32 < g_nthreads ? lo + 32 : g_nthreads;
+  return hi - lo;
 }
 
 void trampoline()
@@ -74,14 +83,13 @@ void trampoline()
   g_body();
   g_done[g_cur] = true;
   g_alive--;
-  if(g_arrived == g_alive && g_alive > 0 && g_arrived > 0)
+  if(g_arrived[4] > 0 && g_alive > 0)
   {
-    // a lane exited while the others wait at a collective: divergence bug in the kernel
-    std::fprintf(stderr, "ccc_emu: lane %d exited while %d lanes wait at a warp collective\n", g_cur, g_arrived);
+    // a thread exited while others wait at a CTA barrier: divergence bug in the kernel
+    std::fprintf(stderr, "ccc_emu: thread %d exited while %d threads wait at __syncthreads\n", g_cur, g_arrived[4]);
     std::abort();
   }
-  // switch to any live fibre, or back to main
-  for(int c = 0; c < kLanes; c++)
+  for(int c = 0; c < g_nthreads; c++)
     if(!g_done[c])
     {
       int from = g_cur;
@@ -92,44 +100,50 @@ void trampoline()
 }
 } // namespace
 
-int lane() { return g_cur; }
-void syncwarp() { barrier(); }
+int tid() { return g_cur; }
+int lane() { return g_cur & 31; }
+void syncwarp() { barrier(g_cur >> 5, warp_size_of(g_cur >> 5)); }
+void syncthreads() { barrier(4, g_nthreads); }
 double shfl(double v, int src)
 {
+  const int w = g_cur >> 5;
   g_xd[g_cur] = v;
-  barrier();
-  double r = g_xd[src & 31];
-  barrier();
+  barrier(w, warp_size_of(w));
+  double r = g_xd[w * 32 + (src & 31)];
+  barrier(w, warp_size_of(w));
   return r;
 }
-double shfl_xor(double v, int mask) { return shfl(v, g_cur ^ mask); }
+double shfl_xor(double v, int mask) { return shfl(v, (g_cur & 31) ^ mask); }
 int shfl_i(int v, int src)
 {
+  const int w = g_cur >> 5;
   g_xi[g_cur] = v;
-  barrier();
-  int r = g_xi[src & 31];
-  barrier();
+  barrier(w, warp_size_of(w));
+  int r = g_xi[w * 32 + (src & 31)];
+  barrier(w, warp_size_of(w));
   return r;
 }
 unsigned ballot(bool p)
 {
+  const int w = g_cur >> 5;
   g_xi[g_cur] = p ? 1 : 0;
-  barrier();
+  barrier(w, warp_size_of(w));
   unsigned r = 0;
-  for(int i = 0; i < kLanes; i++)
-    if(g_xi[i]) r |= (1u << i);
-  barrier();
+  for(int i = 0; i < warp_size_of(w); i++)
+    if(g_xi[w * 32 + i]) r |= (1u << i);
+  barrier(w, warp_size_of(w));
   return r;
 }
 
-/** Run `body` once on each of the 32 lanes in lock step. */
-void run_warp(const std::function<void()> & body)
+/** Run `body` once on each of `nthreads` (<= 128) threads of one CTA in lock step. */
+void run_cta(int nthreads, const std::function<void()> & body)
 {
-  if(g_stacks.empty()) g_stacks.resize(kStack * kLanes);
+  if(g_stacks.empty()) g_stacks.resize(kStack * kMaxThreads);
   g_body = body;
-  g_alive = kLanes;
-  g_arrived = 0;
-  for(int i = 0; i < kLanes; i++)
+  g_nthreads = nthreads;
+  g_alive = nthreads;
+  for(int g = 0; g < 5; g++) g_arrived[g] = 0;
+  for(int i = 0; i < nthreads; i++)
   {
     g_done[i] = false;
     getcontext(&g_ctx[i]);
@@ -140,6 +154,11 @@ void run_warp(const std::function<void()> & body)
   }
   g_cur = 0;
   swapcontext(&g_main, &g_ctx[0]);
+}
+
+void run_warp(const std::function<void()> & body)
+{
+  run_cta(32, body);
 }
 } // namespace ccc_emu
 
@@ -314,4 +333,43 @@ extern "C" int32_t ccc_emu_ddp_srb_solve(const ccc_ddp_srb_batch_t * bt, const c
                                      row[14] = in.i2;
                                    }
                                  });
+}
+
+extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t * r)
+{
+  const int n = bt->n, me = bt->n_eq, mi = bt->n_ineq, B = bt->batch, ld = n | 1;
+  if(n > 128 || mi > 256) return CCC_ERR_INVALID;
+  std::vector<double> Lg((size_t)n * n, 0.0), invd(n), J0((size_t)n * n), At((size_t)n * (me ? me : 1)), Ct((size_t)n * mi);
+  int ok_flag = 0;
+  ccc_emu::run_cta(ccc::kQpThreads, [&]() {
+    ccc::qp_setup_cta(n, me, mi, bt->Q, bt->A, bt->C, Lg.data(), invd.data(), J0.data(), At.data(), Ct.data(), &ok_flag);
+  });
+  ccc::QpParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.n = n;
+  P.me = me;
+  P.mi = mi;
+  P.B = B;
+  P.ld = ld;
+  P.J0 = J0.data();
+  P.At = At.data();
+  P.Ct = Ct.data();
+  P.c = bt->c;
+  P.b = bt->b;
+  P.d = bt->d;
+  P.setup_ok = &ok_flag;
+  P.max_iter = 1000;
+  P.viol_tol = 1e-10;
+  P.out_x = r->x;
+  P.out_iters = r->iters;
+  P.out_status = r->status;
+  P.out_n_active = r->n_active;
+  P.out_active = r->active;
+  std::vector<double> smem(ccc::QpSm::bytes(n, ld) / sizeof(double) + 2, 0.0);
+  for(int b = 0; b < B; b++)
+    ccc_emu::run_cta(ccc::kQpThreads, [&]() {
+      ccc::QpCta cta(P, smem.data(), b);
+      cta.solve();
+    });
+  return CCC_OK;
 }

@@ -35,3 +35,13 @@ def ddp_srb_solve(problem_set, cfg, trace_len=0, chunk=0):
     rc = lib().ccc_emu_ddp_srb_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))
     assert rc == 0
     return res
+
+
+def qp_solve(problem_set):
+    L = lib()
+    L.ccc_emu_qp_solve.restype = C.c_int32
+    L.ccc_emu_qp_solve.argtypes = [C.c_void_p] * 2
+    res = problem_set.new_result()
+    bs, rs = problem_set.as_struct(), res.as_struct()
+    assert L.ccc_emu_qp_solve(C.addressof(bs), C.addressof(rs)) == 0
+    return res

@@ -37,3 +37,27 @@ class CentroidalSim:
     def add_disturb(self, lin_impulse_per_mass, ang_impulse_per_mass):
         self.x[6:9] += lin_impulse_per_mass
         self.x[9:12] += ang_impulse_per_mass
+
+
+class ComZmpSim2d:
+    """reference tests/src/SimModels.h:11-138: x'' = omega^2 (x - zmp) per axis, exact ZOH
+    (Ad = [[ch, sh/w], [w sh, ch]], Bd = (1 - ch, -w sh))."""
+
+    def __init__(self, com_height, sim_dt):
+        w = np.sqrt(G / com_height)
+        ch, sh = np.cosh(w * sim_dt), np.sinh(w * sim_dt)
+        self.Ad = np.array([[ch, sh / w], [w * sh, ch]])
+        self.Bd = np.array([1 - ch, -w * sh])
+        self.x, self.y = np.zeros(2), np.zeros(2)
+
+    pos = property(lambda s: np.array([s.x[0], s.y[0]]))
+    vel = property(lambda s: np.array([s.x[1], s.y[1]]))
+
+    def update(self, zmp):
+        self.x = self.Ad @ self.x + self.Bd * zmp[0]
+        self.y = self.Ad @ self.y + self.Bd * zmp[1]
+
+    def add_disturb(self, impulse_per_mass):
+        # the reference adds impulse.x() to both axes (SimModels.h:127-128)
+        self.x[1] += impulse_per_mass[0]
+        self.y[1] += impulse_per_mass[0]

@@ -1,0 +1,49 @@
+"""CPU tier: the CUDA QP core (qp_cta_core.cuh) executed by the 128-fibre CTA emulator reproduces the
+oracle bit for bit, incl. equality constraints, constraint drops and the LinearMpcZmp / IS-MPC structure."""
+import numpy as np
+
+from centroidalcontrolcollection_b200 import linear_mpc, workloads
+from centroidalcontrolcollection_b200.qp import QpProblemSet
+
+import emu_lib
+
+FIELDS = ("x", "iters", "status", "n_active", "active")
+
+
+def _same(oracle, ps):
+    ref, got = oracle.qp_solve(ps), emu_lib.qp_solve(ps)
+    for f in FIELDS:
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+    return ref
+
+
+def test_random_qps_with_equalities_and_drops(oracle):
+    rng = np.random.default_rng(0)
+    n, mi, B = 24, 60, 8
+    M = rng.standard_normal((n, n))
+    ps = QpProblemSet(M @ M.T + np.eye(n), rng.standard_normal((mi, n)), rng.uniform(0.05, 0.6, (B, mi)),
+                      rng.standard_normal((2, n)), 0.1 * rng.standard_normal((B, 2)), 4 * rng.standard_normal((B, n)))
+    ref = _same(oracle, ps)
+    assert (ref.status == 0).all()
+    assert (ref.iters > ref.n_active - 2).any()  # at least one problem dropped a constraint on the way
+    viol, dual = zip(*ps.kkt_residuals(ref.x))
+    assert max(viol) < 1e-9 and max(dual) < 1e-8
+
+
+def test_linear_mpc_zmp_structure(oracle):
+    w = workloads.linear_mpc_zmp_config2(batch=3)
+    mpc = linear_mpc.LinearMpcZmp1d(w["com_height"], 0.3, w["horizon_dt"])  # N = 30 keeps the emulator quick
+    N = mpc.horizon_steps
+    ip = np.stack([w["pos"][:, 0], w["vel"][:, 0], w["acc"][:, 0]], axis=1)
+    lim = np.stack([w["lim_min"][:, :N, 0], w["lim_max"][:, :N, 0]], axis=2)
+    _same(oracle, mpc.build_qp(ip, lim))
+
+
+def test_ismpc_structure(oracle):
+    w = workloads.ismpc_config5(n_plans=1, n_perturb=3)
+    mpc = linear_mpc.IntrinsicallyStableMpc1d(w["com_height"], 0.5, w["horizon_dt"])  # N = 25
+    N = mpc.horizon_steps
+    ps = mpc.build_qp(w["capture_point"][:, 1], w["planned_zmp"][:, 1], w["ref_zmp"][:, :N, 1],
+                      np.stack([w["lim_min"][:, :N, 1], w["lim_max"][:, :N, 1]], axis=2))
+    ref = _same(oracle, ps)
+    assert (ref.status == 0).all() and (ref.n_active >= 1).all()

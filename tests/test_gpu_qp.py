@@ -1,0 +1,83 @@
+"""GPU tier: ccc_qp_solve (CUDA) vs the oracle — solutions, iteration counts and active sets bit-exact —
+on configs 2 (LinearMpcZmp) and 5 (IntrinsicallyStableMpc), plus the reference's closed-loop tests."""
+import numpy as np
+import pytest
+
+from centroidalcontrolcollection_b200 import linear_mpc, workloads
+from centroidalcontrolcollection_b200.qp import QpProblemSet
+
+from test_linear_mpc_cpu import _closed_loop
+
+pytestmark = pytest.mark.gpu
+FIELDS = ("x", "iters", "status", "n_active", "active")
+
+
+@pytest.fixture(scope="module")
+def qp_solve():
+    from centroidalcontrolcollection_b200 import build, engine
+
+    build.build()
+    assert engine.lib().ccc_device_count() > 0
+    return engine.qp_solver_for()
+
+
+def _parity(oracle, qp_solve, ps, rel_tol=1e-6):
+    ref = oracle.qp_solve(ps, n_threads=max(1, oracle.hardware_threads()))
+    got = qp_solve(ps)
+    assert np.array_equal(ref.status, got.status) and np.array_equal(ref.iters, got.iters)
+    assert ref.active_sets() == got.active_sets()
+    assert np.abs(ref.x - got.x).max() <= rel_tol * max(1.0, np.abs(ref.x).max())
+    for f in FIELDS:
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+    return ref
+
+
+def test_random_qps(oracle, qp_solve):
+    rng = np.random.default_rng(1)
+    n, mi, B = 40, 100, 300
+    M = rng.standard_normal((n, n))
+    ps = QpProblemSet(M @ M.T + np.eye(n), rng.standard_normal((mi, n)), rng.uniform(0.05, 0.6, (B, mi)),
+                      rng.standard_normal((3, n)), 0.1 * rng.standard_normal((B, 3)), 4 * rng.standard_normal((B, n)))
+    ref = _parity(oracle, qp_solve, ps)
+    viol, dual = zip(*ps.subset(np.arange(20)).kkt_residuals(ref.x[:20]))
+    assert max(viol) < 1e-9 and max(dual) < 1e-8
+
+
+def test_config2_linear_mpc_zmp(oracle, qp_solve):
+    """Config 2 at full size: 4096 ICs x 2 axes = 8192 QPs (n = 100, 200 inequalities)."""
+    w = workloads.linear_mpc_zmp_config2()
+    mpc = linear_mpc.LinearMpcZmp(w["com_height"], w["horizon_duration"], w["horizon_dt"])
+    zmp = mpc.plan_batch(qp_solve, w["pos"], w["vel"], w["acc"], w["lim_min"], w["lim_max"], w["control_dt"])
+    got = mpc.mpc_1d.last_result
+    assert (got.status == 0).all()
+    assert (zmp >= w["lim_min"][:, 0] - 1e-12).all() and (zmp <= w["lim_max"][:, 0] + 1e-12).all()
+    zmp_o = mpc.plan_batch(lambda ps: oracle.qp_solve(ps, n_threads=max(1, oracle.hardware_threads())), w["pos"], w["vel"],
+                           w["acc"], w["lim_min"], w["lim_max"], w["control_dt"])
+    ref = mpc.mpc_1d.last_result
+    for f in FIELDS:
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+    assert np.array_equal(zmp, zmp_o)
+
+
+def test_config5_ismpc_sample(oracle, qp_solve):
+    """Config 5 sample: 16 plans x 64 perturbations x 2 axes = 2048 QPs with the equality constraint."""
+    w = workloads.ismpc_config5(n_plans=16, n_perturb=64)
+    mpc = linear_mpc.IntrinsicallyStableMpc(w["com_height"], w["horizon_duration"], w["horizon_dt"])
+    args = (w["capture_point"], w["planned_zmp"], w["ref_zmp"], w["lim_min"], w["lim_max"], w["control_dt"])
+    zmp = mpc.plan_batch(qp_solve, *args)
+    got = mpc.mpc_1d.last_result
+    zmp_o = mpc.plan_batch(lambda ps: oracle.qp_solve(ps, n_threads=max(1, oracle.hardware_threads())), *args)
+    ref = mpc.mpc_1d.last_result
+    for f in FIELDS:
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+    assert np.array_equal(zmp, zmp_o)
+    assert (got.status == 0).mean() > 0.99
+
+
+def test_closed_loops(qp_solve):
+    """reference tests/src/TestLinearMpcZmp.cpp and TestIntrinsicallyStableMpc.cpp through the engine."""
+    for kind in ("lmpc", "ismpc"):
+        ok, planned, pos, zl = _closed_loop(kind, qp_solve, end_time=10.0)
+        assert ok
+        assert (planned - zl[0] >= 0).all() and (zl[1] - planned >= 0).all()
+        assert (pos - zl[0] >= 0).all() and (zl[1] - pos >= 0).all()
