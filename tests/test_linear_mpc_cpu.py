@@ -105,6 +105,8 @@ def test_workload_schedule_matches_footstep_manager():
     for t0 in (0.0, 1.8, 2.35, 4.9, 7.7):
         fm = walking_plan(0.2, 0.2)
         fm.horizon_duration = 2.0
+        for tick in range(int(round(t0 / 0.005)) + 1):  # the manager must be updated every control cycle
+            fm.update(tick * 0.005)
         fm.update(t0)
         ref, lo, hi = _walking_limits(0.2, 0.2, t0, 100, 0.02, eps_reps=2)
         for i in range(100):
