@@ -20,7 +20,7 @@ EXPORTS = [
     "ccc_ddp_centroidal_create", "ccc_ddp_centroidal_destroy", "ccc_ddp_centroidal_solve",
     "ccc_ddp_centroidal_last_launches",
     "ccc_ddp_srb_create", "ccc_ddp_srb_destroy", "ccc_ddp_srb_solve", "ccc_ddp_srb_last_launches",
-    "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches",
+    "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
 ]
 
 
@@ -69,6 +69,8 @@ def lib():
         L.ccc_qp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_qp_last_launches.restype = C.c_int32
         L.ccc_qp_last_launches.argtypes = [C.c_void_p]
+        L.ccc_preview_input.restype = C.c_int32
+        L.ccc_preview_input.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -190,3 +192,18 @@ def qp_solver_for(engines=None):
         return eng.solve(ps)
 
     return qp_solve
+
+
+def preview_gemv(K, F, x, ref_seq):
+    """jerk[b] = -K x[b] + F ref_seq[b] on the GPU (ccc_preview_input, host buffers); plugs into
+    preview_control.PreviewControlZmp1d.proc_once(gemv=...)."""
+    import numpy as np
+
+    K = np.ascontiguousarray(K, dtype=np.float64).reshape(-1)
+    F = np.ascontiguousarray(F, dtype=np.float64).reshape(-1)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    ref_seq = np.ascontiguousarray(ref_seq, dtype=np.float64)
+    u = np.zeros(len(x))
+    _check(lib().ccc_preview_input(len(x), len(F), K.ctypes.data, F.ctypes.data, x.ctypes.data, ref_seq.ctypes.data,
+                                   u.ctypes.data, _abi.CCC_MEM_HOST, None), "ccc_preview_input")
+    return u

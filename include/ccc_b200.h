@@ -212,6 +212,21 @@ void ccc_qp_destroy(ccc_qp_ws_t * ws);
 int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * batch, ccc_qp_result_t * result, int32_t mem, void * stream);
 int32_t ccc_qp_last_launches(const ccc_qp_ws_t * ws);
 
+/* ---- CCC::PreviewControl<3,1,1>::calcOptimalInput ------------------------------------------------
+ * Batched online part of preview control:  u[b] = -K x[b] + F ref_seq[b]   (gains K (1x3), F (1xN) shared).
+ * Replaces: PreviewControl::calcOptimalInput (reference include/CCC/PreviewControl.h:86-89) as called from
+ * PreviewControlZmp1d::procOnce (src/PreviewControlZmp.cpp:37).  The gains come from the host-side setup
+ * (DARE, include/CCC/PreviewControl.h:93-172).  Stateless: no workspace. */
+int32_t ccc_preview_input(int32_t batch,
+                          int32_t horizon_steps,
+                          const double * K,       /* [3]      */
+                          const double * F,       /* [N]      */
+                          const double * x,       /* [B][3]   */
+                          const double * ref_seq, /* [B][N]   */
+                          double * u,             /* [B]      */
+                          int32_t mem,
+                          void * stream);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 int32_t ccc_abi_version(void);
 int32_t ccc_device_count(void);

@@ -324,6 +324,27 @@ int32_t ccc_oracle_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t * r, int3
   return CCC_OK;
 }
 
+/** u[b] = -K x[b] + F ref_seq[b] (reference include/CCC/PreviewControl.h:86-89) in canonical order:
+ *  F.ref as 32 lane-strided sequential fma chains combined by tree_sum32, K.x as one chain. */
+int32_t ccc_oracle_preview_input(int32_t batch, int32_t N, const double * K, const double * F, const double * x,
+                                 const double * ref_seq, double * u)
+{
+  for(int b = 0; b < batch; b++)
+  {
+    double part[32];
+    for(int l = 0; l < 32; l++)
+    {
+      double acc = 0.0;
+      for(int i = l; i < N; i += 32) acc = std::fma(F[i], ref_seq[static_cast<size_t>(b) * N + i], acc);
+      part[l] = acc;
+    }
+    double kx = 0.0;
+    for(int i = 0; i < 3; i++) kx = std::fma(K[i], x[static_cast<size_t>(b) * 3 + i], kx);
+    u[b] = (-kx) + tree_sum32(part, 32);
+  }
+  return CCC_OK;
+}
+
 /** sincos_canon(x) for accuracy tests. */
 void ccc_oracle_sincos(double x, double * s, double * c)
 {

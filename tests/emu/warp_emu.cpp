@@ -13,6 +13,7 @@
 #include "../../centroidalcontrolcollection_b200/csrc/model_centroidal.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/model_srb.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/qp_cta_core.cuh"
+#include "../../centroidalcontrolcollection_b200/csrc/preview_core.cuh"
 
 #include <ucontext.h>
 
@@ -370,6 +371,17 @@ extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t *
     ccc_emu::run_cta(ccc::kQpThreads, [&]() {
       ccc::QpCta cta(P, smem.data(), b);
       cta.solve();
+    });
+  return CCC_OK;
+}
+
+extern "C" int32_t ccc_emu_preview_input(int32_t B, int32_t N, const double * K, const double * F, const double * x,
+                                         const double * ref_seq, double * u)
+{
+  for(int b = 0; b < B; b++)
+    ccc_emu::run_warp([&]() {
+      const double v = ccc::preview_row(N, K, F, x + (size_t)b * 3, ref_seq + (size_t)b * N);
+      if(ccc_emu::lane() == 0) u[b] = v;
     });
   return CCC_OK;
 }
