@@ -108,6 +108,14 @@ class DdpSrbBatch(C.Structure):
     ]
 
 
+class DdpZmpBatch(C.Structure):
+    """ccc_ddp_zmp_batch_t"""
+
+    _fields_ = [("horizon_steps", C.c_int32), ("batch", C.c_int32), ("n_sched", C.c_int32), ("reserved0", C.c_int32),
+                ("dt", C.c_double), ("mass", C.c_double), ("sched_id", C.c_void_p), ("ref_zmp", C.c_void_p),
+                ("com_z", C.c_void_p), ("w", C.c_double * 6), ("x0", C.c_void_p), ("u_init", C.c_void_p)]
+
+
 class QpBatch(C.Structure):
     """ccc_qp_batch_t"""
 

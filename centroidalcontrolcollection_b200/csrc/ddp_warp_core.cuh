@@ -305,7 +305,7 @@ struct DdpWarp
       double acc = 0.0;
       CCC_UNROLL
       for(int c = 0; c < 6; c++) acc = dfma(Fu[c], Vx[R0 + c], acc);
-      Qu = P.w_run[NX] * u + acc;
+      Qu = M::lu(*this, k, u) + acc;
     }
     // W = Vxx Fu, rows R0..R0+5, published transposed: WT[lane][0..5]
     double * WT = s + sm::WT;
@@ -334,6 +334,7 @@ struct DdpWarp
     }
     warp_sync();
     // Quu row (lower triangle is the definition; mirrored through A's upper triangle)
+    const double luu = M::luu(*this);
     double H[32];
     CCC_UNROLL
     for(int j = 0; j < 32; j++) H[j] = 0.0;
@@ -349,7 +350,7 @@ struct DdpWarp
         acc = dfma(Fu[2 * r], w.x, acc);
         acc = dfma(Fu[2 * r + 1], w.y, acc);
       }
-      H[j] = (j == lane ? P.w_run[NX] : 0.0) + acc;
+      H[j] = (j == lane ? luu : 0.0) + acc;
     }
     double quu_diag = 0.0;
     CCC_UNROLL

@@ -20,6 +20,18 @@ struct CentroidalModel
     double dt, mass;
   };
 
+  /** Input cost: 0.5 w_force |u|^2, so Lu = w_force u and Luu = w_force I. */
+  template<class W>
+  CCC_DEV static double lu(const W & w, int, double u)
+  {
+    return w.P.w_run[NX] * u;
+  }
+  template<class W>
+  CCC_DEV static double luu(const W & w)
+  {
+    return w.P.w_run[NX];
+  }
+
   /** Stage-independent part of Fx: identity + (1/mass) dt on the (c, P) block (:100, :118-119). */
   template<class W>
   CCC_DEV static void init_Fx(W & w)

@@ -20,6 +20,7 @@ EXPORTS = [
     "ccc_ddp_centroidal_create", "ccc_ddp_centroidal_destroy", "ccc_ddp_centroidal_solve",
     "ccc_ddp_centroidal_last_launches",
     "ccc_ddp_srb_create", "ccc_ddp_srb_destroy", "ccc_ddp_srb_solve", "ccc_ddp_srb_last_launches",
+    "ccc_ddp_zmp_create", "ccc_ddp_zmp_destroy", "ccc_ddp_zmp_solve", "ccc_ddp_zmp_last_launches",
     "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
 ]
 
@@ -61,6 +62,14 @@ def lib():
         L.ccc_ddp_srb_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_ddp_srb_last_launches.restype = C.c_int32
         L.ccc_ddp_srb_last_launches.argtypes = [C.c_void_p]
+        L.ccc_ddp_zmp_create.restype = C.c_void_p
+        L.ccc_ddp_zmp_create.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.ccc_ddp_zmp_destroy.argtypes = [C.c_void_p]
+        L.ccc_ddp_zmp_destroy.restype = None
+        L.ccc_ddp_zmp_solve.restype = C.c_int32
+        L.ccc_ddp_zmp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ccc_ddp_zmp_last_launches.restype = C.c_int32
+        L.ccc_ddp_zmp_last_launches.argtypes = [C.c_void_p]
         L.ccc_qp_create.restype = C.c_void_p
         L.ccc_qp_create.argtypes = [C.c_int32] * 4
         L.ccc_qp_destroy.argtypes = [C.c_void_p]
@@ -127,6 +136,12 @@ class DdpSrbEngine(_DdpEngineBase):
     include/CCC/DdpSingleRigidBody.h:382-405)."""
 
     _prefix = "ccc_ddp_srb"
+
+
+class DdpZmpEngine(_DdpEngineBase):
+    """Batched counterpart of CCC::DdpZmp's solver object (reference include/CCC/DdpZmp.h:276-300)."""
+
+    _prefix = "ccc_ddp_zmp"
 
 
 class DdpCentroidalEngine(_DdpEngineBase):

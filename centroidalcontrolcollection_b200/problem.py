@@ -189,3 +189,40 @@ class DdpSrbProblemSet:
 
     def new_result(self, trace_len=0):
         return DdpResultArrays(self.batch, self.N, 12, self.m_max, trace_len)
+
+
+class DdpZmpProblemSet:
+    """A batch of DdpZmp problems: shared reference schedules (ref ZMP, CoM height) + initial states (6)."""
+
+    nx = 6
+    m_max = 3
+
+    def __init__(self, ref_zmp, com_z, sched_id, x0, mass, dt, weights=(1e2, 1e-1, 1e-4, 1.0, 1e2, 1.0), u_init=None):
+        """ref_zmp [S][N+1][3], com_z [S][N+1]; weights = DdpZmp::WeightParam defaults (reference
+        include/CCC/DdpZmp.h:71-76): running_com_pos_z, running_zmp, running_force_z, terminal_com_pos_xy,
+        terminal_com_pos_z, terminal_com_vel."""
+        self.ref_zmp = np.ascontiguousarray(ref_zmp, dtype=np.float64)
+        self.com_z = np.ascontiguousarray(com_z, dtype=np.float64)
+        self.sched_id = np.ascontiguousarray(sched_id, dtype=np.int32)
+        self.x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        self.mass, self.dt = float(mass), float(dt)
+        self.weights = np.asarray(weights, dtype=np.float64)
+        self.u_init = None if u_init is None else np.ascontiguousarray(u_init, dtype=np.float64)
+        self.S, self.N = self.ref_zmp.shape[0], self.ref_zmp.shape[1] - 1
+        assert self.ref_zmp.shape == (self.S, self.N + 1, 3) and self.com_z.shape == (self.S, self.N + 1)
+        assert self.x0.shape == (len(self.sched_id), 6)
+
+    batch = property(lambda s: len(s.sched_id))
+
+    def as_struct(self):
+        b = _abi.DdpZmpBatch()
+        b.horizon_steps, b.batch, b.n_sched = self.N, self.batch, self.S
+        b.dt, b.mass = self.dt, self.mass
+        b.sched_id, b.ref_zmp, b.com_z = ptr(self.sched_id), ptr(self.ref_zmp), ptr(self.com_z)
+        for i in range(6):
+            b.w[i] = self.weights[i]
+        b.x0, b.u_init = ptr(self.x0), ptr(self.u_init)
+        return b
+
+    def new_result(self, trace_len=0):
+        return DdpResultArrays(self.batch, self.N, 6, 3, trace_len)

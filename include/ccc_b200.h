@@ -178,6 +178,40 @@ int32_t ccc_ddp_srb_solve(ccc_ddp_srb_ws_t * ws,
                           void * stream);
 int32_t ccc_ddp_srb_last_launches(const ccc_ddp_srb_ws_t * ws);
 
+/* ---- CCC::DdpZmp --------------------------------------------------------------------------------
+ * Flat form of what DdpZmp::planOnce (reference src/DdpZmp.cpp:152-174) reads through ref_data_func at
+ * t_k = current_time + k*dt: RefData.{zmp, com_z} (include/CCC/DdpZmp.h:20-28).  State (6):
+ * (pos_x, vel_x, pos_y, vel_y, pos_z, vel_z) (InitialParam::toState, src/DdpZmp.cpp:145-150); input (3):
+ * (zmp_x, zmp_y, force_z); no input limits (cfg->with_input_constraint must be 0). */
+typedef struct
+{
+  int32_t horizon_steps; /* N */
+  int32_t batch;         /* B */
+  int32_t n_sched;       /* S */
+  int32_t reserved0;
+  double dt;             /* horizon_dt [s] */
+  double mass;           /* [kg] */
+  const int32_t * sched_id; /* [B] */
+  const double * ref_zmp;   /* [S][N+1][3] */
+  const double * com_z;     /* [S][N+1] */
+  double w[6]; /* WeightParam: running_com_pos_z, running_zmp, running_force_z, terminal_com_pos_xy, terminal_com_pos_z, terminal_com_vel */
+  const double * x0;     /* [B][6] */
+  const double * u_init; /* [B][N][3] or NULL = zeros */
+} ccc_ddp_zmp_batch_t;
+
+typedef struct ccc_ddp_zmp_ws ccc_ddp_zmp_ws_t;
+ccc_ddp_zmp_ws_t * ccc_ddp_zmp_create(int32_t horizon_steps, int32_t max_batch, int32_t max_sched);
+void ccc_ddp_zmp_destroy(ccc_ddp_zmp_ws_t * ws);
+/* Replaces: nmpc_ddp::DDPSolver<6,3>::solve as called at reference src/DdpZmp.cpp:160-171 together with the
+ * DdpProblem callbacks at :8-143.  result->x is [B][N+1][6], result->u is [B][N][3]; clamped is all zero. */
+int32_t ccc_ddp_zmp_solve(ccc_ddp_zmp_ws_t * ws,
+                          const ccc_ddp_zmp_batch_t * batch,
+                          const ccc_ddp_config_t * cfg,
+                          ccc_ddp_result_t * result,
+                          int32_t mem,
+                          void * stream);
+int32_t ccc_ddp_zmp_last_launches(const ccc_ddp_zmp_ws_t * ws);
+
 /* ---- QpSolverCollection::QpSolver::solve(QpCoeff &) -------------------------------------------
  * Batched strictly convex dense QP with the matrices shared by the batch:
  *     min 0.5 x'Qx + c'x   s.t.  A x = b,  C x <= d

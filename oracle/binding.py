@@ -73,3 +73,16 @@ def qp_solve(problem_set, n_threads=1):
     if rc != 0:
         raise RuntimeError(f"oracle returned {rc}")
     return res
+
+
+def ddp_zmp_solve(problem_set, cfg, trace_len=0, n_threads=1):
+    """Run the oracle on a centroidalcontrolcollection_b200.problem.DdpZmpProblemSet."""
+    L = lib()
+    L.ccc_oracle_ddp_zmp_solve.restype = C.c_int32
+    L.ccc_oracle_ddp_zmp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    res = problem_set.new_result(trace_len)
+    bs, rs = problem_set.as_struct(), res.as_struct()
+    rc = L.ccc_oracle_ddp_zmp_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs), int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return res

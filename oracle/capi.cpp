@@ -10,6 +10,7 @@
 #include "centroidal.hpp"
 #include "srb.hpp"
 #include "qp.hpp"
+#include "zmp.hpp"
 
 #include <atomic>
 #include <thread>
@@ -290,6 +291,76 @@ int32_t ccc_oracle_srb_eval(const ccc_ddp_srb_batch_t * bt, int32_t k, const dou
   if(Vx)
   {
     std::vector<double> vxx(144);
+    p.terminalCostDeriv(x, Vx, vxx.data());
+  }
+  return CCC_OK;
+}
+
+static void bindZmp(ZmpProblem & p, const ccc_ddp_zmp_batch_t * bt, int sched)
+{
+  const int N = bt->horizon_steps;
+  p.N = N;
+  p.dt = bt->dt;
+  p.mass = bt->mass;
+  p.ref_zmp = bt->ref_zmp + static_cast<size_t>(sched) * (N + 1) * 3;
+  p.com_z = bt->com_z + static_cast<size_t>(sched) * (N + 1);
+  p.w_run_com_z = bt->w[0];
+  p.w_run_zmp = bt->w[1];
+  p.w_run_fz = bt->w[2];
+  p.w_term_xy = bt->w[3];
+  p.w_term_z = bt->w[4];
+  p.w_term_vel = bt->w[5];
+}
+
+/** Same contract as ccc_ddp_zmp_solve with host pointers; n_threads host threads. */
+int32_t ccc_oracle_ddp_zmp_solve(const ccc_ddp_zmp_batch_t * bt, const ccc_ddp_config_t * c, ccc_ddp_result_t * r, int32_t n_threads)
+{
+  if(!bt || !c || !r) return CCC_ERR_INVALID;
+  const int N = bt->horizon_steps;
+  DdpConfig cfg = toConfig(c);
+  parallelFor(bt->batch, n_threads, [&](int b) {
+    ZmpProblem p;
+    bindZmp(p, bt, bt->sched_id[b]);
+    DdpSolver s(p);
+    s.cfg = cfg;
+    std::vector<std::vector<double>> u0(N, std::vector<double>(3, 0.0));
+    if(bt->u_init)
+      for(int k = 0; k < N; k++)
+        for(int j = 0; j < 3; j++) u0[k][j] = bt->u_init[(static_cast<size_t>(b) * N + k) * 3 + j];
+    s.solve(bt->x0 + static_cast<size_t>(b) * 6, u0);
+    storeResult(s, b, N, 6, 3, r);
+  });
+  return CCC_OK;
+}
+
+/** Problem functions of stage k of schedule 0 at (x, u): derivative known-answer tests
+ *  (reference tests/src/TestDdpZmp.cpp:153-248).  Fx 6x6, Fu 6x3 row-major. */
+int32_t ccc_oracle_zmp_eval(const ccc_ddp_zmp_batch_t * bt, int32_t k, const double * x, const double * u, double * xn,
+                            double * running_cost, double * terminal_cost, double * Fx, double * Fu, double * Lx, double * Lu,
+                            double * Vx)
+{
+  ZmpProblem p;
+  bindZmp(p, bt, 0);
+  if(xn) p.stateEq(k, x, u, xn);
+  if(running_cost) *running_cost = p.runningCost(k, x, u);
+  if(terminal_cost) *terminal_cost = p.terminalCost(x);
+  if(Fx || Fu)
+  {
+    std::vector<double> fx(36), fu(18);
+    p.stateEqDeriv(k, x, u, fx.data(), fu.data());
+    if(Fx) std::copy(fx.begin(), fx.end(), Fx);
+    if(Fu) std::copy(fu.begin(), fu.end(), Fu);
+  }
+  if(Lx || Lu)
+  {
+    std::vector<double> lx(6), lu(3), lxx(36), luu(9), lxu(18);
+    p.runningCostDeriv(k, x, u, lx.data(), lu.data(), lxx.data(), luu.data(), lxu.data());
+    if(Lx) std::copy(lx.begin(), lx.end(), Lx);
+    if(Lu) std::copy(lu.begin(), lu.end(), Lu);
+  }
+  if(Vx)
+  {
+    std::vector<double> vxx(36);
     p.terminalCostDeriv(x, Vx, vxx.data());
   }
   return CCC_OK;

@@ -12,6 +12,7 @@
 #include "../../include/ccc_b200.h"
 #include "../../centroidalcontrolcollection_b200/csrc/model_centroidal.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/model_srb.cuh"
+#include "../../centroidalcontrolcollection_b200/csrc/model_zmp.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/qp_cta_core.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/preview_core.cuh"
 
@@ -384,4 +385,43 @@ extern "C" int32_t ccc_emu_preview_input(int32_t B, int32_t N, const double * K,
       if(ccc_emu::lane() == 0) u[b] = v;
     });
   return CCC_OK;
+}
+
+extern "C" int32_t ccc_emu_ddp_zmp_solve(const ccc_ddp_zmp_batch_t * bt, const ccc_ddp_config_t * c, ccc_ddp_result_t * r)
+{
+  const int N = bt->horizon_steps, S = bt->n_sched;
+  ccc::ZmpModel::Params mp;
+  mp.dt = bt->dt;
+  mp.mass = bt->mass;
+  mp.w_u[0] = bt->w[1];
+  mp.w_u[1] = bt->w[1];
+  mp.w_u[2] = bt->w[2];
+  const double w_run[7] = {0, 0, 0, 0, bt->w[0], 0, 1.0};
+  const double w_term[6] = {bt->w[3], bt->w[5], bt->w[3], bt->w[5], bt->w[4], bt->w[5]};
+  std::vector<int32_t> m((size_t)S * N, 3);
+  std::vector<double> zero((size_t)S * N * 9, 0.0), ref((size_t)S * (N + 1) * 6, 0.0);
+  for(int s = 0; s < S; s++)
+    for(int k = 0; k <= N; k++)
+    {
+      const size_t idx = (size_t)s * (N + 1) + k;
+      if(k == N)
+      {
+        ref[idx * 6 + 0] = bt->ref_zmp[idx * 3];
+        ref[idx * 6 + 2] = bt->ref_zmp[idx * 3 + 1];
+      }
+      ref[idx * 6 + 4] = bt->com_z[idx];
+    }
+  return emuSolve<ccc::ZmpModel>(N, bt->batch, S, 3, bt->sched_id, m.data(), zero.data(), zero.data(), ref.data(), bt->x0,
+                                 bt->u_init, w_run, w_term, 0.0, 0.0, mp, c, r, [&](double * tab) {
+                                   for(int st = 0; st < S * N; st++)
+                                   {
+                                     const int s = st / N, k = st - s * N;
+                                     const double * z = bt->ref_zmp + ((size_t)s * (N + 1) + k) * 3;
+                                     double * row = tab + ((size_t)st * ccc::ZmpModel::TAB_ROWS + 6) * 32;
+                                     row[0] = z[0];
+                                     row[1] = z[1];
+                                     row[2] = bt->mass * 9.80665;
+                                     row[3] = z[2];
+                                   }
+                                 });
 }

@@ -45,3 +45,14 @@ def qp_solve(problem_set):
     bs, rs = problem_set.as_struct(), res.as_struct()
     assert L.ccc_emu_qp_solve(C.addressof(bs), C.addressof(rs)) == 0
     return res
+
+
+def ddp_zmp_solve(problem_set, cfg, trace_len=0, chunk=0):
+    L = lib()
+    L.ccc_emu_ddp_zmp_solve.restype = C.c_int32
+    L.ccc_emu_ddp_zmp_solve.argtypes = [C.c_void_p] * 3
+    L.ccc_emu_set_chunk(int(chunk))
+    res = problem_set.new_result(trace_len)
+    bs, rs = problem_set.as_struct(), res.as_struct()
+    assert L.ccc_emu_ddp_zmp_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs)) == 0
+    return res

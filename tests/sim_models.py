@@ -61,3 +61,28 @@ class ComZmpSim2d:
         # the reference adds impulse.x() to both axes (SimModels.h:127-128)
         self.x[1] += impulse_per_mass[0]
         self.y[1] += impulse_per_mass[0]
+
+
+class ComZmpSim3d:
+    """reference tests/src/SimModels.h:140-226: per tick the horizontal model is rebuilt with the current
+    CoM height; the vertical model is a double integrator with gravity (exact ZOH)."""
+
+    def __init__(self, mass, sim_dt):
+        self.mass, self.dt = mass, sim_dt
+        self.x, self.y, self.z = np.zeros(2), np.zeros(2), np.zeros(2)
+
+    pos = property(lambda s: np.array([s.x[0], s.y[0], s.z[0]]))
+    vel = property(lambda s: np.array([s.x[1], s.y[1], s.z[1]]))
+
+    def update(self, zmp, force_z):
+        w = np.sqrt(G / self.z[0])
+        ch, sh = np.cosh(w * self.dt), np.sinh(w * self.dt)
+        Ad, Bd = np.array([[ch, sh / w], [w * sh, ch]]), np.array([1 - ch, -w * sh])
+        self.x = Ad @ self.x + Bd * zmp[0]
+        self.y = Ad @ self.y + Bd * zmp[1]
+        a = force_z / self.mass - G
+        self.z = np.array([self.z[0] + self.dt * self.z[1] + 0.5 * self.dt**2 * a, self.z[1] + self.dt * a])
+
+    def add_disturb(self, impulse_per_mass):
+        self.x[1] += impulse_per_mass[0]
+        self.y[1] += impulse_per_mass[0]

@@ -1,0 +1,109 @@
+"""CPU tier for CCC::DdpZmp: oracle pinned on the reference's known-answer material
+(tests/src/TestDdpZmp.cpp), and the ZMP instantiation of the CUDA core under the warp emulator."""
+import ctypes as C
+
+import numpy as np
+
+from centroidalcontrolcollection_b200 import problem
+
+import emu_lib
+from footstep_manager import walking_plan
+from parity import assert_ddp_parity
+from sim_models import ComZmpSim3d
+
+G = 9.80665
+
+
+def _eval(oracle, ps, x, u):
+    L = oracle.lib()
+    L.ccc_oracle_zmp_eval.restype = C.c_int32
+    L.ccc_oracle_zmp_eval.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 10
+    bs = ps.as_struct()
+    out = dict(xn=np.zeros(6), rc=C.c_double(), tc=C.c_double(), Fx=np.zeros((6, 6)), Fu=np.zeros((6, 3)), Lx=np.zeros(6),
+               Lu=np.zeros(3), Vx=np.zeros(6))
+    x, u = np.ascontiguousarray(x), np.ascontiguousarray(u)
+    assert L.ccc_oracle_zmp_eval(C.addressof(bs), 0, x.ctypes.data, u.ctypes.data, out["xn"].ctypes.data,
+                                 C.addressof(out["rc"]), C.addressof(out["tc"]), out["Fx"].ctypes.data, out["Fu"].ctypes.data,
+                                 out["Lx"].ctypes.data, out["Lu"].ctypes.data, out["Vx"].ctypes.data) == 0
+    out["rc"], out["tc"] = out["rc"].value, out["tc"].value
+    return out
+
+
+def test_check_derivatives(oracle):
+    """tests/src/TestDdpZmp.cpp:153-248: dt 0.005, ref zmp (0.1,-0.2,0.3), com_z 1.0, x, u literals; tol 1e-6."""
+    ref_zmp = np.tile(np.array([0.1, -0.2, 0.3]), (1, 2, 1))
+    com_z = np.ones((1, 2))
+    x = np.array([1.0, 0.1, -2.1, -0.5, 1.1, 0.5])
+    u = np.array([1.0, -2.0, 1000.0])
+    ps = problem.DdpZmpProblemSet(ref_zmp, com_z, [0], x[None], 100.0, 0.005)
+    eps = 1e-6
+    a = _eval(oracle, ps, x, u)
+    Fx, Fu, Lx, Lu, Vx = np.zeros((6, 6)), np.zeros((6, 3)), np.zeros(6), np.zeros(3), np.zeros(6)
+    for i in range(6):
+        e = np.zeros(6)
+        e[i] = eps
+        p, q = _eval(oracle, ps, x + e, u), _eval(oracle, ps, x - e, u)
+        Fx[:, i], Lx[i], Vx[i] = (p["xn"] - q["xn"]) / (2 * eps), (p["rc"] - q["rc"]) / (2 * eps), (p["tc"] - q["tc"]) / (2 * eps)
+    for i in range(3):
+        e = np.zeros(3)
+        e[i] = eps
+        p, q = _eval(oracle, ps, x, u + e), _eval(oracle, ps, x, u - e)
+        Fu[:, i], Lu[i] = (p["xn"] - q["xn"]) / (2 * eps), (p["rc"] - q["rc"]) / (2 * eps)
+    for k, num in (("Fx", Fx), ("Fu", Fu), ("Lx", Lx), ("Lu", Lu), ("Vx", Vx)):
+        assert np.linalg.norm(a[k] - num) < 1e-6, k
+    # running cost against the reference formula (src/DdpZmp.cpp:20-27)
+    rc = 1e2 * 0.5 * (x[4] - 1.0) ** 2 + 1e-1 * 0.5 * ((u[:2] - [0.1, -0.2]) ** 2).sum() + 1e-4 * 0.5 * (u[2] - 100 * G) ** 2
+    assert np.isclose(a["rc"], rc, rtol=1e-13)
+
+
+def run_ddp_zmp_closed_loop(solve, end_time=10.0):
+    """tests/src/TestDdpZmp.cpp:15-137.  solve(problem_set, cfg) -> DdpResultArrays."""
+    horizon_dt, N, sim_dt, mass, h = 0.02, 100, 0.005, 100.0, 1.0
+    fm = walking_plan()
+    sim = ComZmpSim3d(mass, sim_dt)
+    sim.z[0] = h
+    cfg = problem.ddp_config(max_iter=3)  # :28 (nmpc_ddp defaults otherwise)
+    t, u_prev, ok, planned = 0.0, None, True, None
+    while t < end_time:
+        fm.update(t)
+        ref_zmp = np.zeros((1, N + 1, 3))
+        for k in range(N + 1):
+            ref_zmp[0, k, :2] = fm.ref_zmp(t + k * horizon_dt)
+        com_z = np.full((1, N + 1), h)
+        x0 = np.array([[sim.x[0], sim.x[1], sim.y[0], sim.y[1], sim.z[0], sim.z[1]]])
+        u_init = np.tile(np.array([sim.x[0], sim.y[0], mass * G]), (1, N, 1)) if u_prev is None else u_prev  # :84-93
+        ps = problem.DdpZmpProblemSet(ref_zmp, com_z, [0], x0, mass, horizon_dt, u_init=u_init)
+        res = solve(ps, cfg)
+        u_prev = res.u.copy()
+        planned = res.u[0, 0]
+        rz = fm.ref_zmp(t)
+        ok &= bool(np.linalg.norm(planned[:2] - rz) < 0.1 and abs(sim.z[0] - h) < 0.1)  # :108-109
+        t += sim_dt
+        sim.update(planned[:2], planned[2])
+        for dtm in (4.5, 8.5):
+            if dtm <= t < dtm + sim_dt:
+                sim.add_disturb(np.array([0.05, 0.05]))
+    return ok, planned, sim, fm.ref_zmp(t)
+
+
+def test_closed_loop(oracle):
+    ok, planned, sim, rz = run_ddp_zmp_closed_loop(lambda ps, cfg: oracle.ddp_zmp_solve(ps, cfg))
+    assert ok
+    assert np.linalg.norm(planned[:2] - rz) < 1e-2          # :131
+    assert abs(sim.z[0] - 1.0) < 1e-2                        # :132
+    assert np.linalg.norm(sim.pos[:2] - rz) < 1e-2           # :133
+    assert np.linalg.norm(sim.vel) < 1e-2                    # :134
+
+
+def test_emulated_kernel_matches_oracle(oracle):
+    fm = walking_plan()
+    fm.update(1.9)
+    N = 20
+    ref_zmp = np.zeros((1, N + 1, 3))
+    for k in range(N + 1):
+        ref_zmp[0, k, :2] = fm.ref_zmp(1.9 + k * 0.02)
+    x0 = np.array([[0.01, 0.1, -0.02, -0.05, 1.02, 0.03], [0.0, 0.0, 0.0, 0.0, 1.0, 0.0]])
+    u_init = np.tile(np.array([0.0, 0.0, 100 * G]), (2, N, 1))
+    ps = problem.DdpZmpProblemSet(ref_zmp, np.ones((1, N + 1)), [0, 0], x0, 100.0, 0.02, u_init=u_init)
+    cfg = problem.ddp_config(max_iter=4)
+    assert_ddp_parity(oracle.ddp_zmp_solve(ps, cfg, trace_len=4), emu_lib.ddp_zmp_solve(ps, cfg, trace_len=4, chunk=2))
