@@ -636,6 +636,11 @@ struct DdpWarp
       cur = 0;
       // the BoxQP warm start of the last stage reads its own previous gain: zero it
       gain(N - 1)[lane] = 0.0;
+      if(P.out_clamped)
+      {
+        CCC_NOUNROLL
+        for(int k = lane; k < N; k += 32) P.out_clamped[(size_t)b * N + k] = 0u;
+      }
       CCC_NOUNROLL
       for(int i = lane; i < P.trace_len; i += 32)
       {
