@@ -296,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
                     "steps": e2e_steps, "api": "ccc_ddp_centroidal_solve(CCC_MEM_HOST), pinned host buffers"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "ddp_centroidal_solve_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "ccc_host::ddp_solve_kernel<ccc::CentroidalModel,8,1,true>",
                          "algorithmic_bytes_per_solve": abytes, "kernel_ms_per_launch": kernel_ms,
                          "note": "latency/FP64-issue bound serial recursion: HBM fraction is small by nature, see DESIGN.md §5"},
         }
