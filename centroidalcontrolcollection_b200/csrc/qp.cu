@@ -14,10 +14,13 @@ __global__ void __launch_bounds__(ccc::kQpThreads, 1) qp_setup_kernel(int n, int
   ccc::qp_setup_cta(n, me, mi, Q, A, C, Lg, invd, J0, At, Ct, ok_flag);
 }
 
-__global__ void __launch_bounds__(ccc::kQpThreads, 1) qp_solve_kernel(const __grid_constant__ ccc::QpParams P, int * __restrict__ counter)
+template<int NT, bool kGlobal>
+__global__ void __launch_bounds__(NT, 1) qp_solve_kernel(const __grid_constant__ ccc::QpParams P, int * __restrict__ counter,
+                                                         double * __restrict__ gmat)
 {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_b;
+  double * slab = kGlobal ? gmat + (size_t)blockIdx.x * 2 * P.n * P.ld : nullptr;
   for(;;)
   {
     if(threadIdx.x == 0) s_b = atomicAdd(counter, 1);
@@ -25,9 +28,18 @@ __global__ void __launch_bounds__(ccc::kQpThreads, 1) qp_solve_kernel(const __gr
     const int b = s_b;
     __syncthreads();
     if(b >= P.B) break;
-    ccc::QpCta cta(P, smem, b);
+    ccc::QpCta<NT, kGlobal> cta(P, smem, b, slab);
     cta.solve();
   }
+}
+
+constexpr size_t kSmemLimit = 227 * 1024;
+
+/** 0: 128 threads, J/R in shared memory; 1: 128 threads, J/R in global memory; 2: 256 threads, global. */
+int qp_shape(int n)
+{
+  if(n > 128) return 2;
+  return ccc::QpSm<128, false>::bytes(n, n | 1) <= kSmemLimit ? 0 : 1;
 }
 
 template<class T>
@@ -42,6 +54,8 @@ struct ccc_qp_ws
   int n = 0, me = 0, mi = 0, max_batch = 0, device = 0, launches = 0;
   double *Lg = nullptr, *invd = nullptr, *J0 = nullptr, *At = nullptr, *Ct = nullptr;
   int *ok_flag = nullptr, *counter = nullptr;
+  double * gmat = nullptr; // per-CTA J/R slabs when they do not fit in shared memory
+  int n_sm = 148;
   // staging for CCC_MEM_HOST
   double *d_Q = nullptr, *d_A = nullptr, *d_C = nullptr, *d_c = nullptr, *d_b = nullptr, *d_d = nullptr, *d_x = nullptr;
   int *d_iters = nullptr, *d_status = nullptr, *d_nact = nullptr, *d_active = nullptr;
@@ -52,9 +66,10 @@ extern "C" {
 
 ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max_batch)
 {
-  if(n <= 0 || n > 128 || n_eq < 0 || n_eq > 8 || n_ineq <= 0 || n_ineq > 256 || max_batch <= 0)
+  const int nt_threads = n > 128 ? 256 : 128;
+  if(n <= 0 || n > 256 || n_eq < 0 || n_eq > n || n_ineq <= 0 || n_eq + n_ineq > 4 * nt_threads || max_batch <= 0)
   {
-    ccc_host::set_error("ccc_qp_create: sizes outside the kernel's limits (n <= 128, n_eq <= 8, n_ineq <= 256)");
+    ccc_host::set_error("ccc_qp_create: sizes outside the kernel's limits (n <= 256, n_eq <= n, n_eq + n_ineq <= 4 x threads)");
     return nullptr;
   }
   int ndev = 0;
@@ -78,10 +93,15 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
   ok = ok && dev_alloc(ws->d_iters, B) && dev_alloc(ws->d_status, B) && dev_alloc(ws->d_nact, B) && dev_alloc(ws->d_active, B * N);
   ok = ok && ccc_host::check(cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   const int ld = n | 1;
-  ok = ok
-       && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)ccc::QpSm::bytes(n, ld)),
-                          "cudaFuncSetAttribute(smem)");
+  cudaDeviceGetAttribute(&ws->n_sm, cudaDevAttrMultiProcessorCount, ws->device);
+  const int shape = qp_shape(n);
+  if(shape == 0)
+    ok = ok
+         && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)ccc::QpSm<128, false>::bytes(n, ld)),
+                            "cudaFuncSetAttribute(smem)");
+  else
+    ok = ok && dev_alloc(ws->gmat, (size_t)ws->n_sm * 2 * N * ld);
   if(!ok)
   {
     ccc_qp_destroy(ws);
@@ -93,7 +113,7 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
 void ccc_qp_destroy(ccc_qp_ws_t * ws)
 {
   if(!ws) return;
-  void * ptrs[] = {ws->Lg,  ws->invd, ws->J0,  ws->At,  ws->Ct,     ws->ok_flag, ws->counter, ws->d_Q,    ws->d_A,
+  void * ptrs[] = {ws->gmat, ws->Lg,  ws->invd, ws->J0,  ws->At,  ws->Ct,     ws->ok_flag, ws->counter, ws->d_Q,    ws->d_A,
                    ws->d_C, ws->d_c,  ws->d_b, ws->d_d, ws->d_x,    ws->d_iters, ws->d_status, ws->d_nact, ws->d_active};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -160,10 +180,19 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   P.out_n_active = o_nact;
   P.out_active = o_active;
   if(!check(cudaMemsetAsync(ws->counter, 0, sizeof(int), st), "memset")) return CCC_ERR_CUDA;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ws->device);
-  const int grid = B < n_sm ? B : n_sm;
-  qp_solve_kernel<<<grid, ccc::kQpThreads, ccc::QpSm::bytes(n, P.ld), st>>>(P, ws->counter);
+  const int grid = B < ws->n_sm ? B : ws->n_sm;
+  switch(qp_shape(n))
+  {
+    case 0:
+      qp_solve_kernel<128, false><<<grid, 128, ccc::QpSm<128, false>::bytes(n, P.ld), st>>>(P, ws->counter, nullptr);
+      break;
+    case 1:
+      qp_solve_kernel<128, true><<<grid, 128, ccc::QpSm<128, true>::bytes(n, P.ld), st>>>(P, ws->counter, ws->gmat);
+      break;
+    default:
+      qp_solve_kernel<256, true><<<grid, 256, ccc::QpSm<256, true>::bytes(n, P.ld), st>>>(P, ws->counter, ws->gmat);
+      break;
+  }
   ws->launches++;
   if(!check(cudaGetLastError(), "launch qp_solve_kernel")) return CCC_ERR_CUDA;
   if(mem == CCC_MEM_HOST)

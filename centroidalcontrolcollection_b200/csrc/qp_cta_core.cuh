@@ -1,22 +1,23 @@
-// qp_cta_core.cuh — one CTA (128 threads) solves one strictly convex dense QP with the
+// qp_cta_core.cuh — one CTA (NT = 128 or 256 threads) solves one strictly convex dense QP with the
 // Goldfarb-Idnani dual active-set method; Q, A, C are shared by the batch.
 //
-//   min 0.5 x'Qx + c'x   s.t.  A x = b,  C x <= d        n <= 128, n_ineq <= 256
+//   min 0.5 x'Qx + c'x   s.t.  A x = b,  C x <= d        n <= NT, n_eq + n_ineq <= 4 NT
 //
 // Replaces: QpSolverCollection::QpSolver::solve(QpCoeff &) as called at reference
-// src/LinearMpcZmp.cpp:69 and src/IntrinsicallyStableMpc.cpp:93.  Algorithm and evaluation order:
-// oracle/qp.hpp (bit-exact): thread i owns variable i / row i of J = L^-T Q_givens, thread j column
-// sums, sequential fma chains in the oracle's order; scalar products through a fixed 128-leaf tree;
-// the small triangular solve R r = d runs as a column sweep on warp 0.
+// src/LinearMpcZmp.cpp:69, src/IntrinsicallyStableMpc.cpp:93 and src/LinearMpcXY.cpp:181.  Algorithm and
+// evaluation order: oracle/qp.hpp (bit-exact): thread i owns variable i / row i of J = L^-T Q_givens,
+// thread j column sums, sequential fma chains in the oracle's order; scalar products through a fixed
+// NT-leaf tree; the small triangular solve R r = d runs as a column sweep on warp 0.
 //
-// Shared memory per CTA: J and R (n x ld doubles each, ld odd so that both row- and column-wise
-// accesses are conflict free) + a few vectors: 170 KB at n = 100, one CTA per SM.
+// J and R (n x ld doubles each) live in shared memory when they fit (kGlobal = false; ld odd so that
+// row- and column-wise accesses are conflict free; 176 KB at n = 100, one CTA per SM), else in a
+// per-CTA slab of global memory that stays L2 resident (kGlobal = true; LinearMpcXY, n = 240).
 #pragma once
 #include "warp_ctx.cuh"
 
 namespace ccc
 {
-constexpr int kQpThreads = 128;
+constexpr int kQpThreads = 128; // setup kernel; the solve kernel runs NT = 128 or 256 threads
 
 struct QpParams
 {
@@ -54,16 +55,21 @@ CCC_DEV double givens_hypot(double a, double b)
 }
 
 /** Shared-memory layout of one QP (offsets in doubles). */
+template<int NT, bool kGlobal>
 struct QpSm
 {
   int n, ld;
   CCC_DEV QpSm(int n_, int ld_) : n(n_), ld(ld_) {}
+  CCC_DEV int mats() const { return kGlobal ? 0 : 2 * n * ld; }
   CCC_DEV int J() const { return 0; }
   CCC_DEV int R() const { return n * ld; }
-  CCC_DEV int vec(int k) const { return 2 * n * ld + k * 128; } // x, z, d, np, r, u(+1 in next), tmp
-  CCC_DEV int red() const { return vec(8); }                     // 256 doubles: two trees / argmin values
-  CCC_DEV int ints() const { return vec(8) + 256; }              // int area (as doubles): A[129], is_active[264], ctrl
-  static size_t bytes(int n, int ld) { return (size_t)(2 * n * ld + 8 * 128 + 256 + 512) * sizeof(double); }
+  CCC_DEV int vec(int k) const { return mats() + k * NT; } // x, z, d, np, r, u(+1 in next), tmp
+  CCC_DEV int red() const { return vec(8); }                // 2 NT doubles: two trees / argmin values
+  CCC_DEV int ints() const { return vec(8) + 2 * NT; }      // int area: A[NT+4], red_i[NT], is_active[4 NT bytes], ctrl
+  static size_t bytes(int n, int ld)
+  {
+    return (size_t)((kGlobal ? 0 : 2 * n * ld) + 8 * NT + 2 * NT + 4 * NT) * sizeof(double);
+  }
 };
 
 struct QpCtrl
@@ -73,6 +79,7 @@ struct QpCtrl
   int l, ip, status;
 };
 
+template<int NT, bool kGlobal>
 struct QpCta
 {
   const QpParams & P;
@@ -85,25 +92,26 @@ struct QpCta
   int q;
   double R_norm;
 
-  CCC_DEV QpCta(const QpParams & p, double * smem, int prob)
+  /** `gmat`: this CTA's slab of 2 n ld doubles in global memory (kGlobal only). */
+  CCC_DEV QpCta(const QpParams & p, double * smem, int prob, double * gmat = nullptr)
   : P(p), sm(smem), b(prob), tid(thread_id()), n(p.n), me(p.me), mi(p.mi), ld(p.ld), q(0), R_norm(1.0)
   {
-    QpSm L(n, ld);
-    J = sm + L.J();
-    R = sm + L.R();
+    QpSm<NT, kGlobal> L(n, ld);
+    J = (kGlobal ? gmat : sm) + L.J();
+    R = (kGlobal ? gmat : sm) + L.R();
     x = sm + L.vec(0);
     z = sm + L.vec(1);
     d = sm + L.vec(2);
     np = sm + L.vec(3);
     r = sm + L.vec(4);
-    u = sm + L.vec(5); // 129 entries: spills one double into vec(6)'s first slot
+    u = sm + L.vec(5); // NT + 1 entries: spills one double into vec(6)'s first slot
     tmp = sm + L.vec(7);
     red = sm + L.red();
     int * ib = reinterpret_cast<int *>(sm + L.ints());
-    A = ib;                                                        // 129 ints
-    red_i = ib + 132;                                              // 256 ints
-    is_active = reinterpret_cast<unsigned char *>(ib + 132 + 256); // 264 bytes
-    ctrl = reinterpret_cast<QpCtrl *>(ib + 132 + 256 + 72);
+    A = ib;                                                          // NT + 1 ints
+    red_i = ib + NT + 4;                                             // NT ints
+    is_active = reinterpret_cast<unsigned char *>(ib + 2 * NT + 4); // 4 NT bytes
+    ctrl = reinterpret_cast<QpCtrl *>(ib + 3 * NT + 4);
   }
 
   CCC_DEV double normal(int id, int j) const
@@ -119,18 +127,18 @@ struct QpCta
     return id < me ? acc - ldg(P.b + (size_t)b * me + id) : acc + ldg(P.d + (size_t)b * mi + (id - me));
   }
 
-  /** two 128-leaf pairwise trees at once over (z.z, z.np); results in red[0], red[128] */
+  /** two NT-leaf pairwise trees at once over (z.z, z.np); results in red[0], red[NT] */
   CCC_DEV void dot_trees()
   {
     red[tid] = tid < n ? z[tid] * z[tid] : 0.0;
-    red[128 + tid] = tid < n ? z[tid] * np[tid] : 0.0;
+    red[NT + tid] = tid < n ? z[tid] * np[tid] : 0.0;
     cta_sync();
-    for(int off = 64; off >= 1; off >>= 1)
+    for(int off = NT / 2; off >= 1; off >>= 1)
     {
       if(tid < off)
       {
         red[tid] = red[tid] + red[tid + off];
-        red[128 + tid] = red[128 + tid] + red[128 + tid + off];
+        red[NT + tid] = red[NT + tid] + red[NT + tid + off];
       }
       cta_sync();
     }
@@ -154,23 +162,26 @@ struct QpCta
     }
     if(tid < 32)
     {
-      // column sweep of the back substitution on warp 0: lane owns rows lane, lane+32, lane+64, lane+96
-      double a0 = tid < q ? d[tid] : 0.0, a1 = tid + 32 < q ? d[tid + 32] : 0.0;
-      double a2 = tid + 64 < q ? d[tid + 64] : 0.0, a3 = tid + 96 < q ? d[tid + 96] : 0.0;
+      // column sweep of the back substitution on warp 0: lane owns rows lane, lane + 32, ...
+      constexpr int kSlots = NT / 32;
+      double a[kSlots];
+      CCC_UNROLL
+      for(int s = 0; s < kSlots; s++) a[s] = tid + 32 * s < q ? d[tid + 32 * s] : 0.0;
       for(int i = q - 1; i >= 0; i--)
       {
         if((i & 31) == tid)
         {
           const int slot = i >> 5;
-          const double a = slot == 0 ? a0 : slot == 1 ? a1 : slot == 2 ? a2 : a3;
-          r[i] = a / R[i * ld + i];
+          double ai = a[0];
+          CCC_UNROLL
+          for(int s = 1; s < kSlots; s++) ai = slot == s ? a[s] : ai;
+          r[i] = ai / R[i * ld + i];
         }
         warp_sync();
         const double ri = r[i];
-        if(tid < i) a0 = dfma(-R[tid * ld + i], ri, a0);
-        if(tid + 32 < i) a1 = dfma(-R[(tid + 32) * ld + i], ri, a1);
-        if(tid + 64 < i) a2 = dfma(-R[(tid + 64) * ld + i], ri, a2);
-        if(tid + 96 < i) a3 = dfma(-R[(tid + 96) * ld + i], ri, a3);
+        CCC_UNROLL
+        for(int s = 0; s < kSlots; s++)
+          if(tid + 32 * s < i) a[s] = dfma(-R[(tid + 32 * s) * ld + i], ri, a[s]);
       }
     }
     cta_sync();
@@ -329,9 +340,9 @@ struct QpCta
       return;
     }
     // load the shared factor, reset the bookkeeping
-    for(int e = tid; e < n * n; e += kQpThreads) J[(e / n) * ld + (e % n)] = ldg(P.J0 + e);
-    for(int e = tid; e < me + mi; e += kQpThreads) is_active[e] = 0;
-    for(int e = tid; e <= n; e += kQpThreads)
+    for(int e = tid; e < n * n; e += NT) J[(e / n) * ld + (e % n)] = ldg(P.J0 + e);
+    for(int e = tid; e < me + mi; e += NT) is_active[e] = 0;
+    for(int e = tid; e <= n; e += NT)
     {
       A[e] = -1;
       u[e] = 0.0;
@@ -364,7 +375,7 @@ struct QpCta
       if(tid == 0)
       {
         double t2 = 0.0;
-        if(dabs(red[0]) > eps) t2 = (-slack(e)) / red[128];
+        if(dabs(red[0]) > eps) t2 = (-slack(e)) / red[NT];
         ctrl->t = t2;
       }
       cta_sync();
@@ -391,7 +402,7 @@ struct QpCta
         // most violated inactive inequality, lowest index on ties
         double best = -P.viol_tol;
         int best_i = -1;
-        for(int i = tid; i < mi; i += kQpThreads)
+        for(int i = tid; i < mi; i += NT)
         {
           if(is_active[me + i]) continue;
           const double s = slack(me + i);
@@ -404,7 +415,7 @@ struct QpCta
         red[tid] = best;
         red_i[tid] = best_i;
         cta_sync();
-        for(int off = 64; off >= 1; off >>= 1)
+        for(int off = NT / 2; off >= 1; off >>= 1)
         {
           if(tid < off)
           {
@@ -463,7 +474,7 @@ struct QpCta
             }
           }
         double t2 = inf;
-        if(dabs(red[0]) > eps) t2 = (-s_ip) / red[128];
+        if(dabs(red[0]) > eps) t2 = (-s_ip) / red[NT];
         const double t = t1 < t2 ? t1 : t2;
         ctrl->t = t;
         ctrl->l = l;

@@ -91,3 +91,40 @@ class InvariantSequentialExtension:
                 C_seq[i * p:(i + 1) * p, i * n:(i + 1) * n] = model.C
             A_seq, B_seq, E_seq = C_seq @ A_seq, C_seq @ B_seq, C_seq @ E_seq
         self.A_seq, self.B_seq, self.E_seq, self.seq_len = A_seq, B_seq, E_seq, seq_len
+
+
+class VariantSequentialExtension:
+    """x_seq = A_seq x0 + B_seq u_seq + E_seq for a time-variant model list whose input dimension may
+    change (and be zero) per stage (reference include/CCC/VariantSequentialExtension.h:110-208)."""
+
+    def __init__(self, model_list, extend_for_output=False):
+        n = model_list[0].state_dim
+        L = len(model_list)
+        self.model_list = model_list
+        self.total_state_dim = L * n
+        self.total_input_dim = sum(m.input_dim for m in model_list)
+        self.total_output_dim = sum(m.output_dim for m in model_list)
+        A_seq = np.zeros((L * n, n))
+        B_seq = np.zeros((L * n, self.total_input_dim))
+        E_seq = np.zeros(L * n)
+        acc = 0
+        for i, mi in enumerate(model_list):
+            m = mi.input_dim
+            A_seq[i * n:(i + 1) * n] = mi.Ad if i == 0 else mi.Ad @ A_seq[(i - 1) * n:i * n]
+            for j in range(i, L):
+                if j == i:
+                    B_seq[j * n:(j + 1) * n, acc:acc + m] = mi.Bd
+                else:
+                    B_seq[j * n:(j + 1) * n, acc:acc + m] = model_list[j].Ad @ B_seq[(j - 1) * n:j * n, acc:acc + m]
+            E_seq[i * n:(i + 1) * n] = mi.Ed if i == 0 else mi.Ad @ E_seq[(i - 1) * n:i * n] + mi.Ed
+            acc += m
+        if extend_for_output:
+            C_seq = np.zeros((self.total_output_dim, L * n))
+            acc_o = 0
+            for i, mi in enumerate(model_list):
+                p = mi.output_dim
+                C_seq[acc_o:acc_o + p, i * n:(i + 1) * n] = mi.C
+                acc_o += p
+            # the reference's extension for outputs drops F (and requires D = 0), :188-206
+            A_seq, B_seq, E_seq = C_seq @ A_seq, C_seq @ B_seq, C_seq @ E_seq
+        self.A_seq, self.B_seq, self.E_seq = A_seq, B_seq, E_seq

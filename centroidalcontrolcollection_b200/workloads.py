@@ -227,3 +227,40 @@ def ismpc_config5(n_plans=256, n_perturb=512, t0=1.8, seed=20260104):
                 com_height=h, horizon_duration=N * dt, horizon_dt=dt, control_dt=0.005, capture_point=cp,
                 planned_zmp=np.zeros((B, 2)), ref_zmp=np.array(refs)[plan], lim_min=np.array(los)[plan],
                 lim_max=np.array(his)[plan])
+
+
+def linear_mpc_xy_batch(batch=256, horizon_steps=15, t0=2.8, seed=20260105):
+    """LinearMpcXY problems on the reference test's schedule (tests/src/TestLinearMpcXY.cpp:17-83: mass 100,
+    horizon_dt 0.1, single rectangle contact that changes at t = 3, 4, 5, 6 s) sampled at t0, with `batch`
+    perturbed initial states: pos = ref + U(-0.03, 0.03)^2, vel = U(-0.15, 0.15)^2, L_xy = U(-0.5, 0.5)^2.
+    n = 16 x horizon_steps decision variables (240 at the reference's horizon)."""
+    from . import contact, linear_mpc_xy
+    from .linear_models import G
+
+    mass, horizon_dt = 100.0, 0.1
+
+    def motion_param(t):
+        if t < 3.0:
+            rect = ((0.9, -0.15), (1.1, 0.15))
+        elif t < 4.0:
+            rect = ((0.9, 0.05), (1.1, 0.15))
+        elif t < 5.0:
+            rect = ((1.15, -0.15), (1.35, -0.05))
+        elif t < 6.0:
+            rect = ((1.4, 0.05), (1.6, 0.15))
+        else:
+            rect = ((1.4, -0.15), (1.6, 0.15))
+        vertex, ridge = contact.contact_from_rect(*rect)
+        return linear_mpc_xy.MotionParam(1.0, mass * G, vertex, ridge)
+
+    def ref_data(t):
+        pos = (1.0, 0.0) if t < 3.0 else (1.0, 0.1) if t < 4.0 else (1.25, -0.1) if t < 5.0 else (1.5, 0.1) if t < 6.0 else (1.5, 0.0)
+        return np.array(pos), np.zeros(2), np.zeros(2)
+
+    rng = np.random.default_rng(seed)
+    pos = ref_data(t0)[0][None, :] + rng.uniform(-0.03, 0.03, (batch, 2))
+    vel = rng.uniform(-0.15, 0.15, (batch, 2))
+    am = rng.uniform(-0.5, 0.5, (batch, 2))
+    return {"name": "LinearMpcXY test schedule", "mass": mass, "horizon_dt": horizon_dt, "horizon_steps": horizon_steps,
+            "t0": t0, "motion_param_func": motion_param, "ref_data_func": ref_data,
+            "x0": linear_mpc_xy.to_state(mass, pos, vel, am)}

@@ -218,8 +218,10 @@ int32_t ccc_ddp_zmp_last_launches(const ccc_ddp_zmp_ws_t * ws);
  * Replaces: qp_solver_->solve(qp_coeff_) at reference src/LinearMpcZmp.cpp:69 (Q = I, c = 0, no
  * equality, C = [-B_seq; B_seq]) and src/IntrinsicallyStableMpc.cpp:93 (Q = w_vel I + w_zmp P'P, one
  * equality, C = [-P; P]).  QpCoeff fields: obj_mat_ = Q, obj_vec_ = c, eq_mat_/eq_vec_ = A/b,
- * ineq_mat_/ineq_vec_ = C/d; x_min_/x_max_ are +-1e10 on this path and not represented.
- * Limits of the kernel: n <= 128, n_ineq <= 256, n_eq <= 8. */
+ * ineq_mat_/ineq_vec_ = C/d; x_min_/x_max_ are +-1e10 on those two paths and not represented.
+ * src/LinearMpcXY.cpp:181 (Q = B_seq' W B_seq + w I, one equality per contact stage, finite bounds
+ * x_min_/x_max_): the caller appends the bounds as inequality rows  -e_j x <= -x_min,  e_j x <= x_max.
+ * Limits of the kernel: n <= 256, n_eq <= n, n_eq + n_ineq <= 512 (n <= 128) or 1024 (n > 128). */
 typedef struct
 {
   int32_t n, n_eq, n_ineq, batch;

@@ -369,7 +369,7 @@ int32_t ccc_oracle_zmp_eval(const ccc_ddp_zmp_batch_t * bt, int32_t k, const dou
 /** Same contract as ccc_qp_solve with host pointers; n_threads host threads. */
 int32_t ccc_oracle_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t * r, int32_t n_threads)
 {
-  if(!bt || !r || bt->n <= 0 || bt->n > 128) return CCC_ERR_INVALID;
+  if(!bt || !r || bt->n <= 0 || bt->n > 256) return CCC_ERR_INVALID;
   const int n = bt->n, me = bt->n_eq, mi = bt->n_ineq;
   DenseQpShared S;
   S.n = n;

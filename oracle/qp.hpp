@@ -15,10 +15,12 @@
 //
 // Call sites: src/LinearMpcZmp.cpp:69 (n = N, 0 eq, 2N ineq), src/IntrinsicallyStableMpc.cpp:93
 // (n = N, 1 eq, 2N ineq).  Bounds x_min/x_max = -+1e10 (src/LinearMpcZmp.cpp:26-27) are inactive and
-// not represented.  Q, A, C are shared by a batch; c, b, d are per problem.
+// not represented.  src/LinearMpcXY.cpp:181 (n = sum of ridge counts <= 256, one equality per contact
+// stage, no inequalities, finite bounds x_min <= x <= x_max): the caller appends the bounds as
+// inequality rows (-e_j x <= -x_min, e_j x <= x_max).  Q, A, C are shared by a batch; c, b, d are per problem.
 //
 // Canonical arithmetic (num.hpp): sequential fma chains for matrix-vector products, a fixed
-// 128-leaf pairwise tree for the two scalar products of a step, IEEE / and sqrt.
+// 128-leaf (n <= 128) or 256-leaf pairwise tree for the two scalar products of a step, IEEE / and sqrt.
 #pragma once
 #include "num.hpp"
 
@@ -26,14 +28,26 @@
 
 namespace oracle
 {
-/** Pairwise tree over 128 zero-padded leaves: strides 64, 32, ..., 1. */
-inline double tree_sum128(const double * p, int n)
+/** Number of leaves of the scalar-product tree: 128 up to n = 128, else 256 (= threads of the CTA that
+ *  solves the problem in the engine). */
+inline int qp_tree_leaves(int n)
 {
-  double t[128];
-  for(int i = 0; i < 128; i++) t[i] = i < n ? p[i] : 0.0;
-  for(int off = 64; off >= 1; off >>= 1)
+  return n <= 128 ? 128 : 256;
+}
+
+/** Pairwise tree over `leaves` zero-padded leaves: strides leaves/2, ..., 1. */
+inline double tree_sum_leaves(const double * p, int n, int leaves)
+{
+  double t[256];
+  for(int i = 0; i < leaves; i++) t[i] = i < n ? p[i] : 0.0;
+  for(int off = leaves / 2; off >= 1; off >>= 1)
     for(int i = 0; i < off; i++) t[i] = t[i] + t[i + off];
   return t[0];
+}
+
+inline double tree_sum128(const double * p, int n)
+{
+  return tree_sum_leaves(p, n, 128);
 }
 
 /** sqrt(a^2 + b^2) without overflow, as used for the Givens rotations. */
@@ -260,9 +274,9 @@ struct DenseQpSolver
       }
     };
     auto dot_tree = [&](const std::vector<double> & a, const std::vector<double> & bb) {
-      double p[128];
+      double p[256];
       for(int i = 0; i < n; i++) p[i] = a[i] * bb[i];
-      return tree_sum128(p, n);
+      return tree_sum_leaves(p, n, qp_tree_leaves(n));
     };
 
     // equality constraints: always active, full step each

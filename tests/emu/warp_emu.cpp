@@ -29,15 +29,15 @@ namespace ccc_emu
 {
 namespace
 {
-constexpr int kMaxThreads = 128;
-constexpr size_t kStack = 1 << 20;
+constexpr int kMaxThreads = 256;
+constexpr int kCtaGroup = kMaxThreads / 32; // barrier groups: 0..7 = the warps, 8 = the whole CTA
+constexpr size_t kStack = 1 << 19;
 ucontext_t g_main, g_ctx[kMaxThreads];
 std::vector<char> g_stacks;
 bool g_done[kMaxThreads];
 int g_cur = 0, g_nthreads = 32, g_alive = 0;
-// barrier groups: 0..3 = the four warps, 4 = the whole CTA
-int g_arrived[5] = {0, 0, 0, 0, 0};
-unsigned long g_gen[5] = {0, 0, 0, 0, 0};
+int g_arrived[kCtaGroup + 1] = {};
+unsigned long g_gen[kCtaGroup + 1] = {};
 double g_xd[kMaxThreads];
 int g_xi[kMaxThreads];
 std::function<void()> g_body;
@@ -85,10 +85,10 @@ void trampoline()
   g_body();
   g_done[g_cur] = true;
   g_alive--;
-  if(g_arrived[4] > 0 && g_alive > 0)
+  if(g_arrived[kCtaGroup] > 0 && g_alive > 0)
   {
     // a thread exited while others wait at a CTA barrier: divergence bug in the kernel
-    std::fprintf(stderr, "ccc_emu: thread %d exited while %d threads wait at __syncthreads\n", g_cur, g_arrived[4]);
+    std::fprintf(stderr, "ccc_emu: thread %d exited while %d threads wait at __syncthreads\n", g_cur, g_arrived[kCtaGroup]);
     std::abort();
   }
   for(int c = 0; c < g_nthreads; c++)
@@ -105,7 +105,7 @@ void trampoline()
 int tid() { return g_cur; }
 int lane() { return g_cur & 31; }
 void syncwarp() { barrier(g_cur >> 5, warp_size_of(g_cur >> 5)); }
-void syncthreads() { barrier(4, g_nthreads); }
+void syncthreads() { barrier(kCtaGroup, g_nthreads); }
 double shfl(double v, int src)
 {
   const int w = g_cur >> 5;
@@ -137,14 +137,14 @@ unsigned ballot(bool p)
   return r;
 }
 
-/** Run `body` once on each of `nthreads` (<= 128) threads of one CTA in lock step. */
+/** Run `body` once on each of `nthreads` (<= 256) threads of one CTA in lock step. */
 void run_cta(int nthreads, const std::function<void()> & body)
 {
   if(g_stacks.empty()) g_stacks.resize(kStack * kMaxThreads);
   g_body = body;
   g_nthreads = nthreads;
   g_alive = nthreads;
-  for(int g = 0; g < 5; g++) g_arrived[g] = 0;
+  for(int g = 0; g <= kCtaGroup; g++) g_arrived[g] = 0;
   for(int i = 0; i < nthreads; i++)
   {
     g_done[i] = false;
@@ -340,7 +340,7 @@ extern "C" int32_t ccc_emu_ddp_srb_solve(const ccc_ddp_srb_batch_t * bt, const c
 extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t * r)
 {
   const int n = bt->n, me = bt->n_eq, mi = bt->n_ineq, B = bt->batch, ld = n | 1;
-  if(n > 128 || mi > 256) return CCC_ERR_INVALID;
+  if(n > 256 || me + mi > (n > 128 ? 1024 : 512)) return CCC_ERR_INVALID;
   std::vector<double> Lg((size_t)n * n, 0.0), invd(n), J0((size_t)n * n), At((size_t)n * (me ? me : 1)), Ct((size_t)n * mi);
   int ok_flag = 0;
   ccc_emu::run_cta(ccc::kQpThreads, [&]() {
@@ -367,12 +367,36 @@ extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t *
   P.out_status = r->status;
   P.out_n_active = r->n_active;
   P.out_active = r->active;
-  std::vector<double> smem(ccc::QpSm::bytes(n, ld) / sizeof(double) + 2, 0.0);
-  for(int b = 0; b < B; b++)
-    ccc_emu::run_cta(ccc::kQpThreads, [&]() {
-      ccc::QpCta cta(P, smem.data(), b);
-      cta.solve();
-    });
+  // same shapes as qp.cu: 128 threads with J/R in "shared" memory up to n = 116, 128 threads with the
+  // global slab up to n = 128, 256 threads with the global slab beyond
+  std::vector<double> gmat((size_t)2 * n * ld, 0.0);
+  if(n > 128)
+  {
+    std::vector<double> smem(ccc::QpSm<256, true>::bytes(n, ld) / sizeof(double) + 2, 0.0);
+    for(int b = 0; b < B; b++)
+      ccc_emu::run_cta(256, [&]() {
+        ccc::QpCta<256, true> cta(P, smem.data(), b, gmat.data());
+        cta.solve();
+      });
+  }
+  else if(ccc::QpSm<128, false>::bytes(n, ld) > 227 * 1024)
+  {
+    std::vector<double> smem(ccc::QpSm<128, true>::bytes(n, ld) / sizeof(double) + 2, 0.0);
+    for(int b = 0; b < B; b++)
+      ccc_emu::run_cta(128, [&]() {
+        ccc::QpCta<128, true> cta(P, smem.data(), b, gmat.data());
+        cta.solve();
+      });
+  }
+  else
+  {
+    std::vector<double> smem(ccc::QpSm<128, false>::bytes(n, ld) / sizeof(double) + 2, 0.0);
+    for(int b = 0; b < B; b++)
+      ccc_emu::run_cta(128, [&]() {
+        ccc::QpCta<128, false> cta(P, smem.data(), b);
+        cta.solve();
+      });
+  }
   return CCC_OK;
 }
 

@@ -47,3 +47,31 @@ def test_ismpc_structure(oracle):
                       np.stack([w["lim_min"][:, :N, 1], w["lim_max"][:, :N, 1]], axis=2))
     ref = _same(oracle, ps)
     assert (ref.status == 0).all() and (ref.n_active >= 1).all()
+
+
+def _xy_problem_set(horizon_steps, batch):
+    from centroidalcontrolcollection_b200 import linear_mpc_xy
+
+    w = workloads.linear_mpc_xy_batch(batch=batch, horizon_steps=horizon_steps)
+    mpc = linear_mpc_xy.LinearMpcXY(w["mass"], w["horizon_dt"], horizon_steps)
+    ts = [w["t0"] + i * w["horizon_dt"] for i in range(horizon_steps)]
+    ref = np.concatenate([linear_mpc_xy.to_state(w["mass"], *w["ref_data_func"](t)) for t in ts])
+    return mpc.build_qp([w["motion_param_func"](t) for t in ts], ref, w["x0"])
+
+
+def test_linear_mpc_xy_structure_128_threads_global_slab(oracle):
+    """n = 128 (8 stages x 16 ridges): J and R no longer fit in shared memory, 128-thread CTA."""
+    ps = _xy_problem_set(8, 2)
+    assert ps.n == 128 and ps.n_eq == 8 and ps.n_ineq == 256
+    ref = _same(oracle, ps)
+    assert (ref.status == 0).all()
+
+
+def test_linear_mpc_xy_structure_256_threads(oracle):
+    """The reference's size: n = 240 (15 x 16), 15 equalities, 480 bound rows; 256-thread CTA, 256-leaf trees."""
+    ps = _xy_problem_set(15, 1)
+    assert ps.n == 240 and ps.n_eq == 15 and ps.n_ineq == 480
+    ref = _same(oracle, ps)
+    assert (ref.status == 0).all() and ref.iters[0] > 20
+    viol, dual = zip(*ps.kkt_residuals(ref.x, tol=1e-7))
+    assert max(viol) < 1e-7

@@ -74,6 +74,28 @@ def test_config5_ismpc_sample(oracle, qp_solve):
     assert (got.status == 0).mean() > 0.99
 
 
+def test_linear_mpc_xy_batch(oracle, qp_solve):
+    """LinearMpcXY at the reference's size (n = 240, 15 equalities, 480 bound rows; 256-thread CTAs with J/R in an
+    L2-resident slab) and at n = 128 (128-thread CTAs with the slab): bit-exact incl. active sets."""
+    from test_emu_qp import _xy_problem_set
+
+    for horizon_steps, batch in ((15, 160), (8, 200)):
+        ps = _xy_problem_set(horizon_steps, batch)
+        ref = _parity(oracle, qp_solve, ps)
+        assert (ref.status == 0).all()
+
+
+def test_linear_mpc_xy_closed_loop(qp_solve):
+    """reference tests/src/TestLinearMpcXY.cpp through the engine, with the reference's tolerances."""
+    from test_linear_mpc_xy_cpu import xy_closed_loop
+
+    sim, ok, ref_pos, iters = xy_closed_loop(qp_solve)
+    assert ok
+    assert np.linalg.norm(sim.pos - ref_pos) < 0.1
+    assert np.linalg.norm(sim.vel) < 0.1
+    assert np.linalg.norm(sim.angular_momentum) < 0.1
+
+
 def test_closed_loops(qp_solve):
     """reference tests/src/TestLinearMpcZmp.cpp and TestIntrinsicallyStableMpc.cpp through the engine."""
     for kind in ("lmpc", "ismpc"):
