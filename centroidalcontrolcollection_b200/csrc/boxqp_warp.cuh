@@ -1,5 +1,5 @@
-// boxqp_warp.cuh — one-warp projected-Newton box QP and the per-stage LL^T it shares with the
-// DDP backward pass.  Lane i owns input i (m <= 32): row i of the Hessian lives in 32 FP64
+// boxqp_warp.cuh — one-warp projected-Newton box QP and the per-stage Cholesky (square-root-free,
+// L D L') it shares with the DDP backward pass.  Lane i owns input i (m <= 32): row i of the Hessian lives in 32 FP64
 // registers, the Cholesky factor lives in the warp's shared-memory tile.
 //
 // Replaces: nmpc_ddp::BoxQP<InputDim>::solve as reached from the reference through
@@ -13,7 +13,7 @@
 // matrix-vector product at six sites; the kernel spent 72 % of its issue slots waiting for
 // instruction fetch.  This version keeps every hot loop either rolled or single-site:
 //  * the free block is compacted (rank r <- r-th free input), so the factorisation is the
-//    oracle's dense nf x nf LL^T with no skipped columns;
+//    oracle's dense nf x nf L D L' with no skipped columns;
 //  * the column loop is rolled: after column k every lane shifts its register row by one
 //    (folded into the update fma), so the live column is always register 0;
 //  * BoxQP has one objective-evaluation site, driven by a small phase variable;
@@ -145,14 +145,17 @@ CCC_DEV void load_compact_row(double (&Hc)[32], const double * A, const int * id
 
 constexpr int kCbStride = 68; // one column buffer: 32 values (+1 shift) + zero tail up to index 63
 
-/** Dense LL^T of the compact nf x nf block, rows in registers, column loop rolled.
- *  In: Hc = compact row `lane`.  Out: Hc destroyed; A's strict lower triangle holds the compact
- *  factor (row r > col c at A[r][c]); invd_c = 1 / L[lane][lane] (compact numbering).
- *  cb: 2 * kCbStride doubles of smem.  Column k is published at offset (k & 1) of buffer (k & 1),
- *  so that the trailing-update reads start at an even (16-byte aligned) index and pair up.
- *  rhs_c (compact numbering): in b, out y = L^-1 b — the forward substitution is carried along
- *  column by column in the oracle's order (acc_i = fma(-L[i][k], y_k, acc_i), k ascending).
- *  Returns false (warp-uniform) if a pivot is not > 0. */
+/** Square-root-free Cholesky (L D L', L unit lower) of the compact nf x nf block, rows in
+ *  registers, column loop rolled.  In: Hc = compact row `lane`.  Out: Hc destroyed; A's strict
+ *  lower triangle holds the compact L (row r > col c at A[r][c]); invd_c = 1 / d_lane (compact
+ *  numbering).  cb: 2 * kCbStride doubles of smem.  The *unscaled* column k (entries a_ik = L_ik d_k)
+ *  is published at offset (k & 1) of buffer (k & 1), so that the trailing-update reads start at an
+ *  even (16-byte aligned) index and pair up; publishing the unscaled column keeps the publish and
+ *  the barrier off the pivot -> reciprocal -> scale -> update critical path.
+ *  rhs_c (compact numbering): in b, out y = L^-1 b (not yet scaled by D^-1) — the forward
+ *  substitution is carried along column by column in the oracle's order
+ *  (acc_i = fma(-L[i][k], y_k, acc_i), k ascending).
+ *  Returns false (warp-uniform) if a pivot is not > 0.  Operation order: oracle FreeLlt::compute. */
 CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int nf, double & invd_c, double & rhs_c)
 {
   const int lane = lane_id();
@@ -165,32 +168,32 @@ CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int n
   CCC_NOUNROLL
   for(int k = 0; k < nf; k++)
   {
+    const bool below = lane > k && lane < nf;
+    const double c = below ? Hc[0] : 0.0; // unscaled column entry a_ik
+    const int odd = k & 1;
+    double * cbuf = cb + odd * kCbStride;
+    cbuf[lane + odd] = c;
+    warp_sync(); // the one barrier of a column; nothing below it waits on another lane's store
+    const double * col = cbuf + k + odd; // even index: col[2q], col[2q+1] load as one LDS.128
+    const double c1 = col[1];            // feeds the next pivot: issued before the reciprocal chain
     const double piv = warp_shfl(Hc[0], k);
-    const double rk = warp_shfl(rhs, k);
-    if(!(piv > 0.0))
-    {
-      ok = false;
-      break;
-    }
-    const double inv = drcp(dsqrt(piv));
-    const double yk = rk * inv; // forward substitution rides along: y_k = acc_k / L[k][k]
+    const double yk = warp_shfl(rhs, k); // unit L: y_k is the accumulated right-hand side itself
+    ok = piv > 0.0; // a failed pivot poisons this column's update only; the loop exits below
+    const double inv = drcp(piv);
     if(lane == k)
     {
       invd_c = inv;
       y = yk;
     }
-    const bool below = lane > k && lane < nf;
-    const double l = below ? Hc[0] * inv : 0.0;
-    if(below) rhs = dfma(-l, yk, rhs);
-    const int odd = k & 1;
-    double * cbuf = cb + odd * kCbStride;
-    cbuf[lane + odd] = l;
-    if(below) A[lane * kLda + k] = l;
-    warp_sync();
+    const double l = c * inv;
+    if(below)
+    {
+      rhs = dfma(-l, yk, rhs);
+      A[lane * kLda + k] = l;
+    }
     // trailing update folded with a shift by one register: entry (lane, k+j) moves to slot j-1
     const int rem = nf - k;
-    const double * col = cbuf + k + odd; // even index: col[2q], col[2q+1] load as one LDS.128
-    Hc[0] = dfma(-l, col[1], Hc[1]);
+    Hc[0] = dfma(-l, c1, Hc[1]);
     CCC_UNROLL
     for(int j = 2; j < 32; j += 2)
     {
@@ -199,29 +202,31 @@ CCC_DEV bool llt_factor_compact(double (&Hc)[32], double * A, double * cb, int n
       Hc[j - 1] = dfma(-l, c2.x, Hc[j]);
       if(j + 1 < 32) Hc[j] = dfma(-l, c2.y, Hc[j + 1]);
     }
+    if(!ok) break;
   }
   warp_sync();
   rhs_c = y;
   return ok;
 }
 
-/** Back substitution L' x = y on the compact block (y, x in compact numbering, lane r). */
+/** Back substitution L' x = D^-1 y on the compact block (y, x in compact numbering, lane r). */
 CCC_DEV double llt_back_compact(double y_c, const double * A, int nf, double invd_c)
 {
   const int lane = lane_id();
   const bool in = lane < nf;
-  double acc = in ? y_c : 0.0;
+  double acc = in ? y_c * invd_c : 0.0;
   CCC_UNROLL_N(2)
   for(int j = nf - 1; j >= 0; j--)
   {
-    const double xj = warp_shfl(acc * invd_c, j);
+    const double xj = warp_shfl(acc, j);
     if(in && lane < j) acc = dfma(-A[j * kLda + lane], xj, acc);
   }
-  return in ? acc * invd_c : 0.0;
+  return acc;
 }
 
-/** Forward substitution L y = b on the compact block (used when the factor is reused). */
-CCC_DEV double llt_fwd_compact(double rhs_c, const double * A, int nf, double invd_c)
+/** Forward substitution L y = b on the compact block (used when the factor is reused); y is not
+ *  yet scaled by D^-1, like the one llt_factor_compact carries along. */
+CCC_DEV double llt_fwd_compact(double rhs_c, const double * A, int nf)
 {
   const int lane = lane_id();
   const bool in = lane < nf;
@@ -229,13 +234,13 @@ CCC_DEV double llt_fwd_compact(double rhs_c, const double * A, int nf, double in
   CCC_UNROLL_N(2)
   for(int j = 0; j < nf; j++)
   {
-    const double yj = warp_shfl(acc * invd_c, j);
+    const double yj = warp_shfl(acc, j);
     if(in && lane > j) acc = dfma(-A[lane * kLda + j], yj, acc);
   }
-  return in ? acc * invd_c : 0.0;
+  return acc;
 }
 
-/** Same for NR right-hand sides per lane (compact numbering). */
+/** (L D L') x = r for NR right-hand sides per lane (compact numbering). */
 template<int NR>
 CCC_DEV void llt_solve_compactN(double (&r)[NR], const double * A, int nf, double invd_c)
 {
@@ -251,7 +256,7 @@ CCC_DEV void llt_solve_compactN(double (&r)[NR], const double * A, int nf, doubl
     CCC_UNROLL
     for(int c = 0; c < NR; c++)
     {
-      const double yj = warp_shfl(r[c] * invd_c, j);
+      const double yj = warp_shfl(r[c], j);
       if(upd) r[c] = dfma(-lij, yj, r[c]);
     }
   }
@@ -265,12 +270,10 @@ CCC_DEV void llt_solve_compactN(double (&r)[NR], const double * A, int nf, doubl
     CCC_UNROLL
     for(int c = 0; c < NR; c++)
     {
-      const double xj = warp_shfl(r[c] * invd_c, j);
+      const double xj = warp_shfl(r[c], j);
       if(upd) r[c] = dfma(-lji, xj, r[c]);
     }
   }
-  CCC_UNROLL
-  for(int c = 0; c < NR; c++) r[c] = in ? r[c] * invd_c : 0.0;
 }
 
 struct BoxQpOut
@@ -278,7 +281,7 @@ struct BoxQpOut
   int retval;       // boxQP.m result code
   unsigned clamped; // bit j = input j clamped
   FreeSet fs;       // compact numbering matching the factor left in A (unless all clamped)
-  double invd_c;    // 1 / L[r][r] of that factor, compact numbering
+  double invd_c;    // 1 / d_r of that factor (L D L'), compact numbering
   int iters, nfactor, ls_steps;
 };
 
@@ -399,7 +402,7 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     }
     else
     {
-      y_c = llt_fwd_compact(warp_shfl(gc, out.fs.idx), A, out.fs.nf, out.invd_c);
+      y_c = llt_fwd_compact(warp_shfl(gc, out.fs.idx), A, out.fs.nf);
     }
     old_clamped = clamped;
     const bool free_i = active && !cl;

@@ -166,7 +166,7 @@ struct Variants
   static const V * table(int & n)
   {
     static const V t[] = {
-        {8, 2, {ddp_solve_kernel<M, 8, 2, false>, ddp_solve_kernel<M, 8, 2, true>}}, // 16 warps/SM, 128 registers
+        {12, 1, {ddp_solve_kernel<M, 12, 1, false>, ddp_solve_kernel<M, 12, 1, true>}}, // 12 warps/SM in one CTA, 168 registers
         {4, 3, {ddp_solve_kernel<M, 4, 3, false>, ddp_solve_kernel<M, 4, 3, true>}}, // 12 warps/SM, 168 registers
         {8, 1, {ddp_solve_kernel<M, 8, 1, false>, ddp_solve_kernel<M, 8, 1, true>}}, //  8 warps/SM, 255 registers
     };

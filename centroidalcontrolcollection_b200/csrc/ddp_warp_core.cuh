@@ -93,13 +93,13 @@ struct SmLayout
   static constexpr int QXX = T + NN;
   static constexpr int S2 = QXX + NN;                           // scratch NX x NX
   static constexpr int QX = S2 + NN;
-  static constexpr int TOTAL = QX + NV;
+  static constexpr int QUXR = QX + NV;                          // [32][NXP] Qux rows (parked here across BoxQP: registers)
+  static constexpr int TOTAL = QUXR + 32 * NXP;
   // aliases inside A (+ the start of VB), valid while no factor is alive
   static constexpr int WT = A;                                  // [32][6]  the 6 live rows of Vxx*Fu, transposed
   static constexpr int KB = A;                                  // [32][NXP] K rows
   static constexpr int ZB = A + 32 * NXP;                       // [32][NXP] (Quu K) rows
-  static constexpr int QB = A + 64 * NXP;                       // [32][NXP] Qux rows
-  static constexpr int VB0 = A + 96 * NXP;                      // three 32-vectors: k, Quu k, Qu
+  static constexpr int VB0 = A + 64 * NXP;                      // three 32-vectors: k, Quu k, Qu
   static constexpr int VB1 = VB0 + 32;
   static constexpr int VB2 = VB0 + 64;
   static_assert(VB2 + 32 <= IDX, "cost-to-go scratch must fit in the tile + BoxQP buffers");
@@ -200,6 +200,16 @@ struct DdpWarp
       }
       else
       {
+        // the next stage's gains, nominal (x, u) and stage table do not depend on this stage's
+        // result: pull them into L1 while this stage computes (each stage is otherwise a
+        // load -> feedback -> reduce -> step chain that exposes the full HBM/L2 latency)
+        if(k + 1 < N)
+        {
+          prefetch_span(gain(k + 1), 32 * (1 + NX) * 8);
+          prefetch_span(stage_tab(k + 1), 32 * M::TAB_ROWS * 8);
+          prefetch_span(un + (size_t)(k + 1) * 32, 32 * 8);
+          if(lane < 2) prefetch_l1(xn + (size_t)(k + 1) * NX + lane * (NX - 1));
+        }
         double dx[NX];
         CCC_UNROLL
         for(int c = 0; c < NX; c++) dx[c] = x[c] - xn[(size_t)k * NX + c];
@@ -322,15 +332,16 @@ struct DdpWarp
       CCC_UNROLL
       for(int r = 0; r < 6; r++) WT[lane * 6 + r] = w[r];
     }
-    // Qux row of this lane: Fu' (Vxx Fx)
-    double Qux[NX];
+    // Qux row of this lane: Fu' (Vxx Fx), parked in shared memory until the gain solve and the
+    // cost-to-go update need it (rows of inactive lanes are +0.0)
+    double * QUXR = s + sm::QUXR;
     CCC_UNROLL
     for(int c = 0; c < NX; c++)
     {
       double acc = 0.0;
       CCC_UNROLL
       for(int r = 0; r < 6; r++) acc = dfma(Fu[r], T[(R0 + r) * NX + c], acc);
-      Qux[c] = 0.0 + acc;
+      QUXR[lane * NXP + c] = active ? 0.0 + acc : 0.0;
     }
     warp_sync();
     // Quu row (lower triangle is the definition; mirrored through A's upper triangle)
@@ -389,7 +400,7 @@ struct DdpWarp
       {
         // K[free,:] = -(Quu_F[free,free])^-1 Qux[free,:] with BoxQP's factor (compact numbering)
         CCC_UNROLL
-        for(int c = 0; c < NX; c++) K[c] = warp_shfl(Qux[c], r.fs.idx);
+        for(int c = 0; c < NX; c++) K[c] = QUXR[r.fs.idx * NXP + c];
         llt_solve_compactN<NX>(K, A, r.fs.nf, r.invd_c);
         const bool free_i = active && !((clamped >> lane) & 1u);
         CCC_UNROLL
@@ -417,7 +428,7 @@ struct DdpWarp
       double r1[NX + 1];
       r1[0] = Qu;
       CCC_UNROLL
-      for(int c = 0; c < NX; c++) r1[1 + c] = Qux[c];
+      for(int c = 0; c < NX; c++) r1[1 + c] = QUXR[lane * NXP + c];
       llt_solve_compactN<NX + 1>(r1, A, fs.nf, invd_c);
       kk = active ? -r1[0] : 0.0;
       CCC_UNROLL
@@ -444,10 +455,10 @@ struct DdpWarp
     double * VB0 = s + sm::VB0;
     double * VB1 = s + sm::VB1;
     double * VB2 = s + sm::VB2;
-    warp_sync(); // the factor in A and the BoxQP buffers are dead from here on: KB/ZB/QB/VB0-2 alias them
+    warp_sync(); // the factor in A and the BoxQP buffers are dead from here on: KB/ZB/VB0-2 alias them
     double * KB = s + sm::KB;
     double * ZB = s + sm::ZB;
-    double * QB = s + sm::QB;
+    const double * QB = QUXR;
     VB0[lane] = kk;
     CCC_UNROLL
     for(int c = 0; c < NX; c++) KB[lane * NXP + c] = K[c];
@@ -478,11 +489,7 @@ struct DdpWarp
       dV1 = dfma(0.5, dv[1], dV1);
     }
     CCC_UNROLL
-    for(int c = 0; c < NX; c++)
-    {
-      ZB[lane * NXP + c] = active ? Z[c] : 0.0;
-      QB[lane * NXP + c] = active ? Qux[c] : 0.0;
-    }
+    for(int c = 0; c < NX; c++) ZB[lane * NXP + c] = active ? Z[c] : 0.0;
     VB1[lane] = active ? Quuk : 0.0;
     VB2[lane] = active ? Qu : 0.0;
     warp_sync();

@@ -43,6 +43,7 @@ inline double drint(double a) { return std::nearbyint(a); }
 inline double dabs(double a) { return std::fabs(a); }
 template<class T>
 inline T ldg(const T * p) { return *p; }
+inline void prefetch_l1(const void *) {}
 } // namespace ccc
 #else
 #  include <cuda_runtime.h>
@@ -71,6 +72,8 @@ CCC_DEV double drint(double a) { return rint(a); }
 CCC_DEV double dabs(double a) { return fabs(a); }
 template<class T>
 CCC_DEV T ldg(const T * p) { return __ldg(p); }
+/** Hint: bring the 128-byte line holding p into L1 (no register, no scoreboard wait). */
+CCC_DEV void prefetch_l1(const void * p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 } // namespace ccc
 #endif
 
@@ -147,6 +150,19 @@ CCC_DEV void warp_sum8(double (&v)[8], double * xch)
   warp_sync();
   CCC_UNROLL
   for(int i = 0; i < 8; i++) v[i] = xch[i];
+}
+
+/** Every lane prefetches one 128-byte line of the span [p, p + bytes) (bytes is a compile-time
+ *  constant at the call sites, so the loop is one or two predicated instructions). */
+CCC_DEV void prefetch_span(const void * p, int bytes)
+{
+  const char * c = static_cast<const char *>(p);
+  CCC_UNROLL
+  for(int off = 0; off < bytes; off += 32 * 128)
+  {
+    const int o = off + lane_id() * 128;
+    if(o < bytes) prefetch_l1(c + o);
+  }
 }
 
 CCC_DEV double warp_max(double v)

@@ -26,15 +26,76 @@ struct BoxQpConfig
   double armijo = 0.1;
 };
 
-/** Cholesky factor of the free block H[free,free] (compact storage, row-major nf x nf). */
+/** Square-root-free Cholesky factor H[free,free] = L D L' of the free block (compact storage,
+ *  row-major nf x nf, L unit lower).  Eigen::LLT (what nmpc_ddp::BoxQP calls) and L D L' are the
+ *  same factorisation up to where the pivot's square root is taken: the positive-definiteness
+ *  test (pivot > 0), the solution and the free/clamped logic are unchanged; only the rounding of
+ *  individual entries differs (canonical arithmetic).  It is the form the engine
+ *  runs because it keeps the square root and the column publish off the per-column critical path. */
 struct FreeLlt
 {
   int nf = 0;
   std::vector<int> idx;     // free indices, ascending
+  std::vector<double> L;    // nf*nf, unit lower (strict part stored)
+  std::vector<double> C;    // nf*nf, lower: C[i][k] = L[i][k] * d_k, the unscaled column entries (diagonal: d_k)
+  std::vector<double> invd; // 1 / d_k
+
+  /** Left-looking L D L' in the engine's operation order: entry (i,k) accumulates
+   *  fma(-L[i][j], C[k][j], .) over j ascending; returns false if a pivot is not > 0. */
+  bool compute(const double * H, int ld, const std::vector<int> & free_idx)
+  {
+    idx = free_idx;
+    nf = static_cast<int>(idx.size());
+    L.assign(static_cast<size_t>(nf) * nf, 0.0);
+    C.assign(static_cast<size_t>(nf) * nf, 0.0);
+    invd.assign(nf, 0.0);
+    for(int k = 0; k < nf; k++)
+    {
+      double d = H[idx[k] * ld + idx[k]];
+      for(int j = 0; j < k; j++) d = std::fma(-L[k * nf + j], C[k * nf + j], d);
+      if(!(d > 0.0)) return false;
+      const double inv = 1.0 / d;
+      C[k * nf + k] = d;
+      invd[k] = inv;
+      for(int i = k + 1; i < nf; i++)
+      {
+        double a = H[idx[i] * ld + idx[k]]; // lower triangle of H, like Eigen::LLT<Lower>
+        for(int j = 0; j < k; j++) a = std::fma(-L[i * nf + j], C[k * nf + j], a);
+        C[i * nf + k] = a;
+        L[i * nf + k] = a * inv;
+      }
+    }
+    return true;
+  }
+
+  /** Solve (L D L') y = b in place on a compact vector of length nf (stride sb). */
+  void solve(double * b, int sb) const
+  {
+    for(int i = 0; i < nf; i++)
+    {
+      double acc = b[i * sb];
+      for(int j = 0; j < i; j++) acc = std::fma(-L[i * nf + j], b[j * sb], acc);
+      b[i * sb] = acc;
+    }
+    for(int i = 0; i < nf; i++) b[i * sb] = b[i * sb] * invd[i];
+    for(int i = nf - 1; i >= 0; i--)
+    {
+      double acc = b[i * sb];
+      for(int j = nf - 1; j > i; j--) acc = std::fma(-L[j * nf + i], b[j * sb], acc);
+      b[i * sb] = acc;
+    }
+  }
+};
+
+/** Plain unblocked LL' with the same interface (the 3x3 inertia solves of the single-rigid-body
+ *  model, reference src/DdpSingleRigidBody.cpp:70,146-167 `inertia.llt().solve`). */
+struct DenseLlt
+{
+  int nf = 0;
+  std::vector<int> idx;
   std::vector<double> L;    // nf*nf, lower
   std::vector<double> invd; // 1 / L[k][k]
 
-  /** Unblocked left-looking LL^T; returns false if a pivot is not > 0. */
   bool compute(const double * H, int ld, const std::vector<int> & free_idx)
   {
     idx = free_idx;
@@ -52,7 +113,7 @@ struct FreeLlt
       invd[k] = inv;
       for(int i = k + 1; i < nf; i++)
       {
-        double a = H[idx[i] * ld + idx[k]]; // lower triangle of H, like Eigen::LLT<Lower>
+        double a = H[idx[i] * ld + idx[k]];
         for(int j = 0; j < k; j++) a = std::fma(-L[i * nf + j], L[k * nf + j], a);
         L[i * nf + k] = a * inv;
       }
@@ -60,7 +121,6 @@ struct FreeLlt
     return true;
   }
 
-  /** Solve (L L') y = b in place on a compact vector of length nf (stride sb). */
   void solve(double * b, int sb) const
   {
     for(int i = 0; i < nf; i++)

@@ -6,8 +6,8 @@
 // State x = (c, ZYX Euler angles, v, omega) — 12 states (BASELINE.json says "13-state"; the
 // reference is 12, include/CCC/DdpSingleRigidBody.h:110).  Scalar formulas are written exactly as
 // in the reference and compiled without contraction; sin/cos come from sincos_canon (num.hpp) so
-// that the engine can reproduce them bit for bit; the 3x3 inertia solves use the same LL^T
-// (FreeLlt) as everything else.
+// that the engine can reproduce them bit for bit; the 3x3 inertia solves use a plain
+// LL^T (DenseLlt, boxqp.hpp), as the reference's inertia.llt().solve does.
 #pragma once
 #include "ddp.hpp"
 
@@ -46,9 +46,9 @@ struct SrbProblem : public DdpProblem
     E[8] = 0.0;
   }
 
-  FreeLlt inertiaLlt(int k) const
+  DenseLlt inertiaLlt(int k) const
   {
-    FreeLlt llt;
+    DenseLlt llt;
     llt.compute(inertia + 9 * k, 3, {0, 1, 2});
     return llt;
   }
@@ -126,7 +126,7 @@ struct SrbProblem : public DdpProblem
   {
     const int m = m_tab[k];
     const double * I = inertia + 9 * k;
-    FreeLlt llt = inertiaLlt(k);
+    DenseLlt llt = inertiaLlt(k);
     double f[3], n[3], E[9];
     wrench(k, x, u, f, n);
     for(int i = 0; i < 144; i++) Fx[i] = 0.0;
