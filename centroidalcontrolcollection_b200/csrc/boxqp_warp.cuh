@@ -329,7 +329,7 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     publish(pub, xc, active);
     const double Hxc = matvec32(H, pub, m);
     double sums[2] = {active ? xc * Hxc : 0.0, active ? xc * g : 0.0};
-    warp_sum_n<2>(sums);
+    warp_sum2(sums);
     const double objc = dfma(0.5, sums[0], sums[1]);
     if(phase != 0)
     {

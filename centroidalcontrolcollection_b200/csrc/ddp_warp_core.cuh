@@ -484,7 +484,7 @@ struct DdpWarp
     }
     {
       double dv[2] = {active ? kk * Qu : 0.0, active ? kk * Quuk : 0.0};
-      warp_sum_n<2>(dv);
+      warp_sum2(dv);
       dV0 = dV0 + dv[0];
       dV1 = dfma(0.5, dv[1], dV1);
     }

@@ -108,6 +108,25 @@ CCC_DEV void warp_sum_n(double (&v)[N])
   }
 }
 
+/** Two pairwise-tree sums with 6 shuffles instead of 10: level 16 leaves value 0 in the lower
+ *  half-warp and value 1 in the upper one (each lane adds the partner's copy of the value it
+ *  keeps, exactly the butterfly's pair), levels 8..1 finish both inside their halves, one more
+ *  exchange hands every lane the other total.  Same tree, same bits as two warp_sum calls. */
+CCC_DEV void warp_sum2(double (&v)[2])
+{
+  const bool up = (lane_id() & 16) != 0;
+  const double send = up ? v[0] : v[1];
+  double keep = up ? v[1] : v[0];
+  keep = keep + warp_shfl_xor(send, 16);
+  keep = keep + warp_shfl_xor(keep, 8);
+  keep = keep + warp_shfl_xor(keep, 4);
+  keep = keep + warp_shfl_xor(keep, 2);
+  keep = keep + warp_shfl_xor(keep, 1);
+  const double other = warp_shfl_xor(keep, 16);
+  v[0] = up ? other : keep;
+  v[1] = up ? keep : other;
+}
+
 /** Eight pairwise-tree sums at once by halving the value set at each butterfly level
  *  ("transpose-reduce"): level 16 exchanges 4 of the 8 values, level 8 two, level 4 one, levels
  *  2 and 1 finish the single value a lane is left with — 9 shuffles instead of 40.  Every value

@@ -1,5 +1,14 @@
-"""The C++ drop-in class CCC::DdpCentroidal (centroidalcontrolcollection_b200/include/CCC/) driven by the
-reference's own closed-loop test, restated in tests/cpp/TestDdpCentroidal.cpp."""
+"""The C++ drop-in host classes (centroidalcontrolcollection_b200/include/CCC/*.h) driven by the reference's own
+test scenarios, restated in tests/cpp/*.cpp (GoogleTest and Eigen are absent: plain checks, exit code).
+
+Two tiers, the same test programs in both:
+  * CPU tier — TestHostModels needs no engine at all (discretisation, condensing, preview gains and the whole
+    PreviewControlZmp closed loop, BASELINE config 1).  The other programs are linked against
+    tests/cpp/oracle_engine_shim.cpp, which implements the C-ABI on the CPU oracle, so that the host-side logic
+    (callback sampling, QP coefficient assembly, batching, post-processing) is checked without a GPU; and linked
+    against the real libccc_b200.so they must refuse to run without a device (no CPU fallback in the product).
+  * GPU tier — linked against libccc_b200.so and run on the device.
+"""
 import os
 import subprocess
 
@@ -7,37 +16,64 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "centroidalcontrolcollection_b200")
-EXE = os.path.join(ROOT, "tests", "cpp", "test_ddp_centroidal.bin")
+CPP = os.path.join(ROOT, "tests", "cpp")
+ORACLE = os.path.join(ROOT, "oracle")
+
+ENGINE_TESTS = ["TestDdpCentroidal", "TestDdpSingleRigidBody", "TestDdpZmp", "TestZmpMpc", "TestLinearMpcXY"]
 
 
-def _build():
-    from centroidalcontrolcollection_b200 import build
+def _compile(name, engine):
+    """engine: None (host only), "gpu" (libccc_b200.so) or "oracle" (CPU shim)."""
+    exe = os.path.join(CPP, f"{name}_{engine or 'host'}.bin")
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, os.path.join(CPP, name + ".cpp")]
+    if engine == "gpu":
+        from centroidalcontrolcollection_b200 import build
 
-    build.build()
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "TestDdpCentroidal.cpp"),
-           "-L" + PKG, "-lccc_b200", "-Wl,-rpath," + PKG, "-L/usr/local/cuda/lib64", "-lcudart"]
+        build.build()
+        cmd += ["-L" + PKG, "-lccc_b200", "-Wl,-rpath," + PKG, "-L/usr/local/cuda/lib64", "-lcudart"]
+    elif engine == "oracle":
+        from oracle import binding
+
+        binding.build()
+        cmd += [os.path.join(CPP, "oracle_engine_shim.cpp"), "-L" + ORACLE, "-lccc_oracle", "-Wl,-rpath," + ORACLE, "-pthread"]
     subprocess.check_call(cmd)
+    return exe
 
 
-def test_cpp_dropin_compiles_and_refuses_without_gpu():
-    """CPU tier: the header-only host classes compile against the C-ABI; without a device the
-    program must fail loudly (no CPU fallback)."""
-    _build()
+def _run(exe, timeout=900):
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ALL CHECKS PASSED" in r.stdout
+
+
+def test_host_models_and_preview_control_closed_loop():
+    """StateSpaceModel / sequential extensions (reference TestStateSpaceModel, TestInvariantSequentialExtension,
+    TestVariantSequentialExtension) and BASELINE config 1: TestPreviewControlZmp, single problem on the CPU."""
+    _run(_compile("TestHostModels", None))
+
+
+@pytest.mark.parametrize("name", ENGINE_TESTS)
+def test_cpp_host_logic_with_oracle_engine(name):
+    """The reference scenarios through the C++ classes with the CPU oracle standing in for the engine."""
+    _run(_compile(name, "oracle"))
+
+
+def test_cpp_dropin_refuses_without_gpu():
+    """Linked against the product library, a drop-in program must fail loudly without a device."""
     from centroidalcontrolcollection_b200 import engine
 
+    exe = _compile("TestDdpCentroidal", "gpu")
     if engine.lib().ccc_device_count() > 0:
         pytest.skip("a CUDA device is present")
-    r = subprocess.run([EXE], capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
 
 
 @pytest.mark.gpu
-def test_cpp_plan_once_closed_loop():
-    """reference tests/src/TestDdpCentroidal.cpp:15-163 through CCC::DdpCentroidal::planOnce, plus
-    planBatch == repeated planOnce, on the GPU."""
-    _build()
-    r = subprocess.run([EXE], capture_output=True, text=True, timeout=600)
-    print(r.stdout[-2000:])
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "ALL CHECKS PASSED" in r.stdout
+@pytest.mark.parametrize("name", ENGINE_TESTS)
+def test_cpp_dropin_on_gpu(name):
+    """reference tests/src/Test{DdpCentroidal,DdpSingleRigidBody,DdpZmp,LinearMpcZmp,IntrinsicallyStableMpc,
+    LinearMpcXY}.cpp closed loops through CCC::<Method>::planOnce on the GPU, plus planBatch == repeated planOnce."""
+    _run(_compile(name, "gpu"))
