@@ -334,7 +334,7 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     if(phase != 0)
     {
       const bool ls_fail = (phase == 2 && step < cfg.min_step);
-      if(!ls_fail && ddiv(objc - old_obj, step * sdotg) < cfg.armijo)
+      if(!ls_fail && (objc - old_obj) > cfg.armijo * (step * sdotg)) // Armijo ratio test, cross-multiplied (oracle/boxqp.hpp)
       {
         step = step * cfg.step_factor;
         out.ls_steps++;

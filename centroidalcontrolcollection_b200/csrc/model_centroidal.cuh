@@ -73,11 +73,12 @@ struct CentroidalModel
     r7[7] = 0.0;
     warp_sum8(r7, w.s + W::sm::S2);
     const double mass = w.P.mp.mass, dt = w.P.mp.dt;
+    const double inv_mass = ddiv(1, mass); // loop invariant; the same rounded 1 / m as init_Fx
     double xdot[9];
     CCC_UNROLL
     for(int a = 0; a < 3; a++)
     {
-      xdot[a] = ddiv(x[3 + a], mass);
+      xdot[a] = x[3 + a] * inv_mass;
       xdot[3 + a] = r7[a];
       xdot[6 + a] = r7[3 + a];
     }

@@ -253,7 +253,10 @@ struct BoxQp
       for(int i = 0; i < m; i++) xc[i] = clampd(std::fma(step, search[i], x[i]), lo[i], hi[i]);
       double objc = objective(H, m, g, xc.data(), Hxc.data());
       bool ls_fail = false;
-      while((objc - old_obj) / (step * sdotg) < cfg.armijo)
+      // boxQP.m: while (vc - oldvalue) / (step * sdotg) < Armijo.  step * sdotg < 0 here, so the ratio
+      // test is evaluated cross-multiplied (no division in the backtracking loop); the two forms differ
+      // only if the ratio is within rounding of the threshold
+      while((objc - old_obj) > cfg.armijo * (step * sdotg))
       {
         step = step * cfg.step_factor;
         ls_steps++;

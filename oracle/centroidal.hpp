@@ -56,9 +56,12 @@ struct CentroidalProblem : public DdpProblem
   {
     double f[3], n[3], xdot[9];
     wrench(k, x, u, f, n);
+    // P / m as P * (1 / m): the same rounded 1 / m that calcStateEqDeriv puts into Fx (:100), so that
+    // the rollout and its linearisation agree, and no division sits on the per-stage critical path
+    const double inv_mass = 1 / mass;
     for(int a = 0; a < 3; a++)
     {
-      xdot[a] = x[3 + a] / mass;
+      xdot[a] = x[3 + a] * inv_mass;
       xdot[3 + a] = f[a];
       xdot[6 + a] = n[a];
     }

@@ -19,7 +19,7 @@ PKG = os.path.join(ROOT, "centroidalcontrolcollection_b200")
 CPP = os.path.join(ROOT, "tests", "cpp")
 ORACLE = os.path.join(ROOT, "oracle")
 
-ENGINE_TESTS = ["TestDdpCentroidal", "TestDdpSingleRigidBody", "TestDdpZmp", "TestZmpMpc", "TestLinearMpcXY"]
+ENGINE_TESTS = ["TestDdpCentroidal", "TestDdpSingleRigidBody", "TestDdpZmp", "TestZmpMpc", "TestLinearMpcXY", "TestLinearMpcZ"]
 
 
 def _compile(name, engine):
@@ -75,5 +75,5 @@ def test_cpp_dropin_refuses_without_gpu():
 @pytest.mark.parametrize("name", ENGINE_TESTS)
 def test_cpp_dropin_on_gpu(name):
     """reference tests/src/Test{DdpCentroidal,DdpSingleRigidBody,DdpZmp,LinearMpcZmp,IntrinsicallyStableMpc,
-    LinearMpcXY}.cpp closed loops through CCC::<Method>::planOnce on the GPU, plus planBatch == repeated planOnce."""
+    LinearMpcXY,LinearMpcZ}.cpp closed loops through CCC::<Method>::planOnce on the GPU, plus planBatch == repeated planOnce."""
     _run(_compile(name, "gpu"))
