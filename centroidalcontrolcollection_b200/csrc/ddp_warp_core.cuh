@@ -188,6 +188,23 @@ struct DdpWarp
     CCC_UNROLL
     for(int i = 0; i < NX; i++) x[i] = initial ? ldg(P.x0 + (size_t)b * NX + i) : xn[i];
     double Jc = 0.0;
+    // line-search passes: the gains and the nominal (x, u) of a stage do not depend on the stages before
+    // it, so they are fetched one stage ahead into registers (gq/uq/xq) and the HBM / L2 latency hides
+    // behind the previous stage's feedback -> reduce -> step chain; lanes >= m fetch values they never use
+    double gq[1 + NX], xq[NX], uq = 0.0;
+    CCC_UNROLL
+    for(int c = 0; c <= NX; c++) gq[c] = 0.0;
+    CCC_UNROLL
+    for(int c = 0; c < NX; c++) xq[c] = 0.0;
+    if(!initial)
+    {
+      const double * g = gain(0);
+      CCC_UNROLL
+      for(int c = 0; c <= NX; c++) gq[c] = g[c * 32 + lane];
+      uq = un[lane];
+      CCC_UNROLL
+      for(int c = 0; c < NX; c++) xq[c] = xn[c];
+    }
     CCC_NOUNROLL
     for(int k = 0; k < N; k++)
     {
@@ -200,30 +217,26 @@ struct DdpWarp
       }
       else
       {
-        // the next stage's gains, nominal (x, u) and stage table do not depend on this stage's
-        // result: pull them into L1 while this stage computes (each stage is otherwise a
-        // load -> feedback -> reduce -> step chain that exposes the full HBM/L2 latency)
+        double gk[1 + NX], dx[NX];
+        const double uj = uq;
+        CCC_UNROLL
+        for(int c = 0; c <= NX; c++) gk[c] = gq[c];
+        CCC_UNROLL
+        for(int c = 0; c < NX; c++) dx[c] = x[c] - xq[c];
         if(k + 1 < N)
         {
-          prefetch_span(gain(k + 1), 32 * (1 + NX) * 8);
-          prefetch_span(stage_tab(k + 1), 32 * M::TAB_ROWS * 8);
-          prefetch_span(un + (size_t)(k + 1) * 32, 32 * 8);
-          if(lane < 2) prefetch_l1(xn + (size_t)(k + 1) * NX + lane * (NX - 1));
-        }
-        double dx[NX];
-        CCC_UNROLL
-        for(int c = 0; c < NX; c++) dx[c] = x[c] - xn[(size_t)k * NX + c];
-        const double * g = gain(k);
-        double fb = 0.0;
-        double kj = 0.0, uj = 0.0;
-        if(active)
-        {
-          kj = g[lane];
-          uj = un[(size_t)k * 32 + lane];
+          const double * g = gain(k + 1);
           CCC_UNROLL
-          for(int c = 0; c < NX; c++) fb = dfma(g[(1 + c) * 32 + lane], dx[c], fb);
+          for(int c = 0; c <= NX; c++) gq[c] = g[c * 32 + lane];
+          uq = un[(size_t)(k + 1) * 32 + lane];
+          CCC_UNROLL
+          for(int c = 0; c < NX; c++) xq[c] = xn[(size_t)(k + 1) * NX + c];
+          prefetch_span(stage_tab(k + 1), 32 * M::TAB_ROWS * 8);
         }
-        u = dfma(alpha, kj, uj) + fb;
+        double fb = 0.0;
+        CCC_UNROLL
+        for(int c = 0; c < NX; c++) fb = dfma(gk[1 + c], dx[c], fb);
+        u = dfma(alpha, gk[0], uj) + fb;
         if(kConstrained) u = clampd(u, P.u_lo, P.u_hi);
         if(!active) u = 0.0;
       }
