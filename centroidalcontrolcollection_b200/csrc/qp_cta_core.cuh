@@ -63,12 +63,12 @@ struct QpSm
   CCC_DEV int mats() const { return kGlobal ? 0 : 2 * n * ld; }
   CCC_DEV int J() const { return 0; }
   CCC_DEV int R() const { return n * ld; }
-  CCC_DEV int vec(int k) const { return mats() + k * NT; } // x, z, d, np, r, u(+1 in next), tmp
-  CCC_DEV int red() const { return vec(8); }                // 2 NT doubles: two trees / argmin values
-  CCC_DEV int ints() const { return vec(8) + 2 * NT; }      // int area: A[NT+4], red_i[NT], is_active[4 NT bytes], ctrl
+  CCC_DEV int vec(int k) const { return mats() + k * NT; } // x, z, d, np, r, u(+1 in next), tmp, gs, gx
+  CCC_DEV int red() const { return vec(10); }               // 2 NT doubles: two trees / argmin values / scan ping-pong
+  CCC_DEV int ints() const { return vec(10) + 2 * NT; }     // int area: A[NT+4], red_i[NT], is_active[4 NT bytes], ctrl
   static size_t bytes(int n, int ld)
   {
-    return (size_t)((kGlobal ? 0 : 2 * n * ld) + 8 * NT + 2 * NT + 4 * NT) * sizeof(double);
+    return (size_t)((kGlobal ? 0 : 2 * n * ld) + 10 * NT + 2 * NT + 4 * NT) * sizeof(double);
   }
 };
 
@@ -85,7 +85,7 @@ struct QpCta
   const QpParams & P;
   double * sm;
   int b, tid, n, me, mi, ld;
-  double *J, *R, *x, *z, *d, *np, *r, *u, *tmp, *red;
+  double *J, *R, *x, *z, *d, *np, *r, *u, *tmp, *gs, *gx, *red;
   int *A, *red_i;
   unsigned char * is_active;
   QpCtrl * ctrl;
@@ -106,6 +106,8 @@ struct QpCta
     r = sm + L.vec(4);
     u = sm + L.vec(5); // NT + 1 entries: spills one double into vec(6)'s first slot
     tmp = sm + L.vec(7);
+    gs = sm + L.vec(8);
+    gx = sm + L.vec(9);
     red = sm + L.red();
     int * ib = reinterpret_cast<int *>(sm + L.ints());
     A = ib;                                                          // NT + 1 ints
@@ -122,8 +124,18 @@ struct QpCta
   /** n_id . x + offset (>= 0 when satisfied) */
   CCC_DEV double slack(int id) const
   {
+    // the fma chain is sequential (oracle order); the loads are not: eight in flight per step
     double acc = 0.0;
-    for(int j = 0; j < n; j++) acc = dfma(normal(id, j), x[j], acc);
+    int j = 0;
+    for(; j + 8 <= n; j += 8)
+    {
+      double v[8];
+      CCC_UNROLL
+      for(int e = 0; e < 8; e++) v[e] = normal(id, j + e);
+      CCC_UNROLL
+      for(int e = 0; e < 8; e++) acc = dfma(v[e], x[j + e], acc);
+    }
+    for(; j < n; j++) acc = dfma(normal(id, j), x[j], acc);
     return id < me ? acc - ldg(P.b + (size_t)b * me + id) : acc + ldg(P.d + (size_t)b * mi + (id - me));
   }
 
@@ -187,63 +199,74 @@ struct QpCta
     cta_sync();
   }
 
-  /** Givens sweep that turns d into (d[0..q-1], +-|d[q..]|, 0...) and rotates J; appends the column to R.
+  /** Givens sweep that folds d[q..n-1] into d[q] and rotates J; appends the column to R.  The rotation
+   *  parameters of all n-q-1 steps come from the suffix sums of squares of d (Kogge-Stone scan, then thread j
+   *  evaluates step j: two square roots and three divisions in parallel instead of a chain of n-q-1 dependent
+   *  hypot / division steps), after which every thread rotates its own row of J with two fma per step.
+   *  Operation order: oracle/qp.hpp add_constraint.
    *  Returns false if the new constraint is linearly dependent on the active ones. */
   CCC_DEV bool add_constraint()
   {
     const double eps = 2.220446049250313e-16;
-    double dj = d[n - 1];
+    double * Ta = red;
+    double * Tb = red + NT;
+    Ta[tid] = (tid >= q && tid < n) ? d[tid] * d[tid] : 0.0;
+    cta_sync();
+    for(int off = 1; off < n - q; off <<= 1)
+    {
+      Tb[tid] = Ta[tid] + (tid + off < n ? Ta[tid + off] : 0.0);
+      cta_sync();
+      double * t = Ta;
+      Ta = Tb;
+      Tb = t;
+    }
+    double * gc = tmp;
+    if(tid >= q + 1 && tid <= n - 1)
+    {
+      const int j = tid;
+      const double aa = d[j - 1];
+      const double bmag = j == n - 1 ? dabs(d[n - 1]) : dsqrt(Ta[j]);
+      const bool bneg = d[j] < 0.0;
+      const double h = dsqrt(Ta[j - 1]);
+      double cc = -1.0, ss = 0.0, xny = 0.0; // cc = -1: no rotation at this step
+      if(!(h < eps))
+      {
+        cc = dabs(aa) / h;
+        ss = bmag / h;
+        if((aa < 0.0) != bneg) ss = -ss;
+        xny = ss / (1.0 + cc);
+      }
+      gc[j] = cc;
+      gs[j] = ss;
+      gx[j] = xny;
+    }
+    const double dq = n - 1 == q ? d[q] : (d[q] < 0.0 ? -dsqrt(Ta[q]) : dsqrt(Ta[q]));
+    cta_sync();
     if(tid < n)
     {
       double * row = J + tid * ld;
+      double t2 = row[n - 1];
       for(int j = n - 1; j >= q + 1; j--)
       {
-        double cc = d[j - 1], ss = dj;
-        const double h = givens_hypot(cc, ss);
-        if(dabs(h) < eps)
-        {
-          dj = cc;
-          continue;
-        }
-        ss = ss / h;
-        cc = cc / h;
+        const double cc = gc[j];
+        const double t1 = row[j - 1];
         if(cc < 0.0)
         {
-          cc = -cc;
-          ss = -ss;
-          dj = -h;
-        }
-        else
-          dj = h;
-        const double xny = ss / (1.0 + cc);
-        const double t1 = row[j - 1], t2 = row[j];
-        const double a = dfma(t2, ss, t1 * cc);
-        row[j - 1] = a;
-        row[j] = dfma(xny, t1 + a, -t2);
-      }
-    }
-    else
-    {
-      // threads beyond n only need the final value of the scalar chain
-      for(int j = n - 1; j >= q + 1; j--)
-      {
-        double cc = d[j - 1], ss = dj;
-        const double h = givens_hypot(cc, ss);
-        if(dabs(h) < eps)
-        {
-          dj = cc;
+          t2 = t1;
           continue;
         }
-        cc = cc / h;
-        dj = cc < 0.0 ? -h : h;
+        const double a = dfma(t2, gs[j], t1 * cc);
+        row[j] = dfma(gx[j], t1 + a, -t2);
+        t2 = a; // column j-1 of this row: written when the next step (or the loop end) is done with it
+        row[j - 1] = a;
       }
     }
     cta_sync();
     if(tid < q) R[tid * ld + q] = d[tid];
-    if(tid == 0) R[q * ld + q] = dj;
+    if(tid == 0) R[q * ld + q] = dq;
     q++;
-    const bool ok = !(dabs(dj) <= eps * R_norm);
-    if(ok) R_norm = R_norm < dabs(dj) ? dabs(dj) : R_norm;
+    const bool ok = !(dabs(dq) <= eps * R_norm);
+    if(ok) R_norm = R_norm < dabs(dq) ? dabs(dq) : R_norm;
     cta_sync();
     return ok;
   }

@@ -186,32 +186,47 @@ struct DenseQpSolver
         r[i] = acc / R[i * n + i];
       }
     };
+    // Givens sweep that folds d[q..n-1] into d[q] and rotates the columns of J (Goldfarb-Idnani's
+    // "add constraint").  The textbook sweep runs j = n-1 .. q+1 with h_j = hypot(d[j-1], running value):
+    // a chain of n-q-1 dependent hypot / division steps.  |running value at j| is sqrt(sum_{i>=j} d_i^2), so the
+    // rotation parameters of ALL steps follow from the suffix sums of squares T_j and can be evaluated
+    // independently of each other; that is the form used here (and by the engine, where one thread computes
+    // one step's parameters).  T_j is summed by a Kogge-Stone scan (fixed association, zeros are exact), the
+    // sign of the running value at j is the sign of d[j] (the sweep normalises cc >= 0).
     auto add_constraint = [&]() -> bool {
-      for(int j = n - 1; j >= q + 1; j--)
+      std::vector<double> Ta(n + 1, 0.0), Tb(n + 1, 0.0), gc(n, -1.0), gs(n, 0.0), gx(n, 0.0);
+      for(int j = q; j < n; j++) Ta[j] = d[j] * d[j];
+      for(int off = 1; off < n - q; off <<= 1)
       {
-        double cc = d[j - 1], ss = d[j];
-        const double h = givens_hypot(cc, ss);
-        if(std::fabs(h) < eps) continue;
-        d[j] = 0.0;
-        ss = ss / h;
-        cc = cc / h;
-        if(cc < 0.0)
-        {
-          cc = -cc;
-          ss = -ss;
-          d[j - 1] = -h;
-        }
-        else
-          d[j - 1] = h;
-        const double xny = ss / (1.0 + cc);
-        for(int k = 0; k < n; k++)
-        {
-          const double t1 = J[k * n + j - 1], t2 = J[k * n + j];
-          const double a = std::fma(t2, ss, t1 * cc);
-          J[k * n + j - 1] = a;
-          J[k * n + j] = std::fma(xny, t1 + a, -t2);
-        }
+        for(int j = 0; j < n; j++) Tb[j] = Ta[j] + (j + off < n ? Ta[j + off] : 0.0);
+        Ta.swap(Tb);
       }
+      for(int j = q + 1; j <= n - 1; j++)
+      {
+        const double aa = d[j - 1];
+        const double bmag = j == n - 1 ? std::fabs(d[n - 1]) : std::sqrt(Ta[j]);
+        const bool bneg = d[j] < 0.0;
+        const double h = std::sqrt(Ta[j - 1]);
+        if(h < eps) continue; // gc[j] = -1: no rotation at this step
+        const double cc = std::fabs(aa) / h;
+        double ss = bmag / h;
+        if((aa < 0.0) != bneg) ss = -ss;
+        gc[j] = cc;
+        gs[j] = ss;
+        gx[j] = ss / (1.0 + cc);
+      }
+      const double dq = n - 1 == q ? d[q] : (d[q] < 0.0 ? -std::sqrt(Ta[q]) : std::sqrt(Ta[q]));
+      for(int k = 0; k < n; k++)
+        for(int j = n - 1; j >= q + 1; j--)
+        {
+          const double cc = gc[j];
+          if(cc < 0.0) continue;
+          const double t1 = J[k * n + j - 1], t2 = J[k * n + j];
+          const double a = std::fma(t2, gs[j], t1 * cc);
+          J[k * n + j - 1] = a;
+          J[k * n + j] = std::fma(gx[j], t1 + a, -t2);
+        }
+      d[q] = dq;
       q++;
       for(int i = 0; i < q; i++) R[i * n + q - 1] = d[i];
       if(std::fabs(d[q - 1]) <= eps * R_norm) return false; // linearly dependent
