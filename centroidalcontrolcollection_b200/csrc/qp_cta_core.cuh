@@ -124,16 +124,28 @@ struct QpCta
   /** n_id . x + offset (>= 0 when satisfied) */
   CCC_DEV double slack(int id) const
   {
-    // the fma chain is sequential (oracle order); the loads are not: eight in flight per step
+    // the fma chain is sequential (oracle order); the loads (L2-resident constraint matrix) are not: the next
+    // block of 16 is in flight while the chain consumes the current one
+    constexpr int kBlk = 16;
     double acc = 0.0;
+    double v[kBlk], w[kBlk];
     int j = 0;
-    for(; j + 8 <= n; j += 8)
+    if(n >= kBlk)
     {
-      double v[8];
       CCC_UNROLL
-      for(int e = 0; e < 8; e++) v[e] = normal(id, j + e);
+      for(int e = 0; e < kBlk; e++) v[e] = normal(id, e);
+      for(; j + 2 * kBlk <= n; j += kBlk)
+      {
+        CCC_UNROLL
+        for(int e = 0; e < kBlk; e++) w[e] = normal(id, j + kBlk + e);
+        CCC_UNROLL
+        for(int e = 0; e < kBlk; e++) acc = dfma(v[e], x[j + e], acc);
+        CCC_UNROLL
+        for(int e = 0; e < kBlk; e++) v[e] = w[e];
+      }
       CCC_UNROLL
-      for(int e = 0; e < 8; e++) acc = dfma(v[e], x[j + e], acc);
+      for(int e = 0; e < kBlk; e++) acc = dfma(v[e], x[j + e], acc);
+      j += kBlk;
     }
     for(; j < n; j++) acc = dfma(normal(id, j), x[j], acc);
     return id < me ? acc - ldg(P.b + (size_t)b * me + id) : acc + ldg(P.d + (size_t)b * mi + (id - me));
