@@ -87,7 +87,7 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
   const size_t N = n, ME = n_eq, MI = n_ineq, B = max_batch;
   bool ok = true;
   ok = ok && dev_alloc(ws->Lg, N * N) && dev_alloc(ws->invd, N) && dev_alloc(ws->J0, N * N);
-  ok = ok && dev_alloc(ws->At, N * ME) && dev_alloc(ws->Ct, N * MI) && dev_alloc(ws->ok_flag, 1) && dev_alloc(ws->counter, 1);
+  ok = ok && dev_alloc(ws->At, N * ME) && dev_alloc(ws->Ct, N * MI) && dev_alloc(ws->ok_flag, 2) && dev_alloc(ws->counter, 1);
   ok = ok && dev_alloc(ws->d_Q, N * N) && dev_alloc(ws->d_A, N * ME) && dev_alloc(ws->d_C, N * MI);
   ok = ok && dev_alloc(ws->d_c, B * N) && dev_alloc(ws->d_b, B * ME) && dev_alloc(ws->d_d, B * MI) && dev_alloc(ws->d_x, B * N);
   ok = ok && dev_alloc(ws->d_iters, B) && dev_alloc(ws->d_status, B) && dev_alloc(ws->d_nact, B) && dev_alloc(ws->d_active, B * N);

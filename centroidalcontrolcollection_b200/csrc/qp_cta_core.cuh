@@ -28,7 +28,7 @@ struct QpParams
   const double * c;  // [B][n] or null
   const double * b;  // [B][me]
   const double * d;  // [B][mi]
-  const int * setup_ok;
+  const int * setup_ok; // [0]: Q positive definite; [1]: inequality rows i and i + mi/2 are exact negatives of each other
   int max_iter;
   double viol_tol;
   double * out_x;
@@ -124,6 +124,13 @@ struct QpCta
   /** n_id . x + offset (>= 0 when satisfied) */
   CCC_DEV double slack(int id) const
   {
+    const double acc = slack_dot(id);
+    return id < me ? acc - ldg(P.b + (size_t)b * me + id) : acc + ldg(P.d + (size_t)b * mi + (id - me));
+  }
+
+  /** n_id . x */
+  CCC_DEV double slack_dot(int id) const
+  {
     // the fma chain is sequential (oracle order); the loads (L2-resident constraint matrix) are not: the next
     // block of 16 is in flight while the chain consumes the current one
     constexpr int kBlk = 16;
@@ -148,7 +155,7 @@ struct QpCta
       j += kBlk;
     }
     for(; j < n; j++) acc = dfma(normal(id, j), x[j], acc);
-    return id < me ? acc - ldg(P.b + (size_t)b * me + id) : acc + ldg(P.d + (size_t)b * mi + (id - me));
+    return acc;
   }
 
   /** two NT-leaf pairwise trees at once over (z.z, z.np); results in red[0], red[NT] */
@@ -427,6 +434,7 @@ struct QpCta
       if(!add_constraint()) status = 1;
     }
 
+    const bool paired = ldg(P.setup_ok + 1) != 0;
     bool need_pick = true;
     int ip = -1;
     double s_ip = 0.0;
@@ -437,16 +445,46 @@ struct QpCta
         // most violated inactive inequality, lowest index on ties
         double best = -P.viol_tol;
         int best_i = -1;
-        for(int i = tid; i < mi; i += NT)
+        if(paired)
         {
-          if(is_active[me + i]) continue;
-          const double s = slack(me + i);
-          if(s < best)
+          // rows i and i + h are exact negatives: fma(-a, b, -c) = -fma(a, b, c), so one chain serves both
+          const int h = mi / 2;
+          for(int i = tid; i < h; i += NT)
           {
-            best = s;
-            best_i = i;
+            const bool a0 = is_active[me + i], a1 = is_active[me + i + h];
+            if(a0 && a1) continue;
+            const double acc = slack_dot(me + i);
+            if(!a0)
+            {
+              const double s = acc + ldg(P.d + (size_t)b * mi + i);
+              if(s < best || (s == best && best_i >= 0 && i < best_i))
+              {
+                best = s;
+                best_i = i;
+              }
+            }
+            if(!a1)
+            {
+              const double s = (-acc) + ldg(P.d + (size_t)b * mi + i + h);
+              if(s < best || (s == best && best_i >= 0 && i + h < best_i))
+              {
+                best = s;
+                best_i = i + h;
+              }
+            }
           }
         }
+        else
+          for(int i = tid; i < mi; i += NT)
+          {
+            if(is_active[me + i]) continue;
+            const double s = slack(me + i);
+            if(s < best)
+            {
+              best = s;
+              best_i = i;
+            }
+          }
         red[tid] = best;
         red_i[tid] = best_i;
         cta_sync();
@@ -633,6 +671,22 @@ CCC_DEV void qp_setup_cta(int n, int me, int mi, const double * Q, const double 
   }
   for(int e = tid; e < n * me; e += kQpThreads) At[e] = A[(e % me) * n + e / me];
   for(int e = tid; e < n * mi; e += kQpThreads) Ct[e] = C[(size_t)(e % mi) * n + e / mi];
+  // two-sided constraints lo <= G x <= hi arrive as C = [-G; G] (reference src/LinearMpcZmp.cpp:25,
+  // src/IntrinsicallyStableMpc.cpp:42; the box rows of LinearMpcXY): if row i + mi/2 is the exact negative of
+  // row i for every i, the solve kernel evaluates one product per pair (the other one is its exact negative)
+  if(tid == 0) ok_flag[1] = (mi % 2 == 0) ? 1 : 0;
+  cta_sync();
+  if(mi % 2 == 0)
+  {
+    const int h = mi / 2;
+    bool same = true;
+    for(int e = tid; e < n * h; e += kQpThreads)
+    {
+      const int i = e % h, j = e / h;
+      same = same && (C[(size_t)(i + h) * n + j] == -C[(size_t)i * n + j]);
+    }
+    if(!same) ok_flag[1] = 0;
+  }
   cta_sync();
 }
 } // namespace ccc
