@@ -64,3 +64,18 @@ def test_unconstrained_path(oracle):
     cfg = problem.ddp_centroidal_config(max_iter=3)
     cfg.with_input_constraint = 0
     _run(oracle, ps, cfg)
+
+
+def test_indefinite_quu_takes_the_regularisation_retry_path(oracle):
+    """A negative force weight makes Quu + lambda I indefinite at the initial lambda (Fu' Vxx Fu has rank <= 6 of
+    16 inputs): the factorisation must report the non-positive pivot, the backward pass is retried with a larger
+    lambda until it goes through — same retries, same bits on both sides."""
+    w = workloads.ddp_centroidal_config3(batch=2, horizon_steps=6)
+    ps = problem.DdpCentroidalProblemSet.from_workload(w)
+    ps.w_run = ps.w_run.copy()
+    ps.w_run[9] = -1e-4
+    for constrained in (1, 0):
+        cfg = problem.ddp_centroidal_config(max_iter=3)
+        cfg.with_input_constraint = constrained
+        ref = _run(oracle, ps, cfg)
+        assert (ref.lambda_trace[:, 0] > 1e-4).all(), "lambda was not raised: the retry path did not run"
