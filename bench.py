@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 from centroidalcontrolcollection_b200 import _abi, problem, workloads  # noqa: E402
 
+_REAL_STDOUT = 1
 METRIC = "MPC solves/sec (DdpCentroidal horizon=50)"
 UNIT = "solves/s"
 
@@ -149,7 +150,13 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+def _emit(line):
+    """The JSON line goes to the real stdout; everything else a library may print there (NCCL's version banner
+    under torchrun) was redirected to stderr at start-up, so that stdout carries exactly one line."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def run_ours(args, rank, world, local_rank):
@@ -309,7 +316,7 @@ def run_ours(args, rank, world, local_rank):
             v, k, dt = cpu_oracle_rate(ps, cfg, n_sample, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {k} of {B} problems of the same seeded batch, {dt:.1f} s wall"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -331,6 +338,10 @@ def main():
     ap.add_argument("--cpu-baseline-problems-per-thread", type=int, default=96,
                     help="cpu_baseline leg: bounded sample, problems per host thread (~10-20 s in total)")
     args = ap.parse_args()
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # stray library output on stdout -> stderr
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -152,7 +152,7 @@ class DdpCentroidalEngine(_DdpEngineBase):
 
     @staticmethod
     def set_variant(v):
-        """Tuning hook: launch shape of the solve kernel (0: 16 warps/SM, 1: 12, 2: 8)."""
+        """Tuning hook: launch shape of the solve kernel (0: 12 warps/SM in one CTA, 1: 12 in three CTAs, 2: 8 = default)."""
         return int(lib().ccc_ddp_centroidal_set_variant(int(v)))
 
     @staticmethod
