@@ -63,12 +63,12 @@ struct QpSm
   CCC_DEV int mats() const { return kGlobal ? 0 : 2 * n * ld; }
   CCC_DEV int J() const { return 0; }
   CCC_DEV int R() const { return n * ld; }
-  CCC_DEV int vec(int k) const { return mats() + k * NT; } // x, z, d, np, r, u(+1 in next), tmp, gs, gx
-  CCC_DEV int red() const { return vec(10); }               // 2 NT doubles: two trees / argmin values / scan ping-pong
-  CCC_DEV int ints() const { return vec(10) + 2 * NT; }     // int area: A[NT+4], red_i[NT], is_active[4 NT bytes], ctrl
+  CCC_DEV int vec(int k) const { return mats() + k * NT; } // x, z, d, np, r, u(+1 in next), tmp, gs, gx, rinv
+  CCC_DEV int red() const { return vec(11); }               // 2 NT doubles: two trees / argmin values / scan ping-pong
+  CCC_DEV int ints() const { return vec(11) + 2 * NT; }     // int area: A[NT+4], red_i[NT], is_active[4 NT bytes], ctrl
   static size_t bytes(int n, int ld)
   {
-    return (size_t)((kGlobal ? 0 : 2 * n * ld) + 10 * NT + 2 * NT + 4 * NT) * sizeof(double);
+    return (size_t)((kGlobal ? 0 : 2 * n * ld) + 11 * NT + 2 * NT + 4 * NT) * sizeof(double);
   }
 };
 
@@ -85,7 +85,7 @@ struct QpCta
   const QpParams & P;
   double * sm;
   int b, tid, n, me, mi, ld;
-  double *J, *R, *x, *z, *d, *np, *r, *u, *tmp, *gs, *gx, *red;
+  double *J, *R, *x, *z, *d, *np, *r, *u, *tmp, *gs, *gx, *rinv, *red;
   int *A, *red_i;
   unsigned char * is_active;
   QpCtrl * ctrl;
@@ -108,6 +108,7 @@ struct QpCta
     tmp = sm + L.vec(7);
     gs = sm + L.vec(8);
     gx = sm + L.vec(9);
+    rinv = sm + L.vec(10); // 1 / R[i][i], kept up to date by add_constraint / delete_constraint
     red = sm + L.red();
     int * ib = reinterpret_cast<int *>(sm + L.ints());
     A = ib;                                                          // NT + 1 ints
@@ -158,13 +159,15 @@ struct QpCta
     return acc;
   }
 
-  /** two NT-leaf pairwise trees at once over (z.z, z.np); results in red[0], red[NT] */
+  /** two NT-leaf pairwise trees at once over (z.z, z.np); results in red[0], red[NT].  Same tree as
+   *  oracle/qp.hpp tree_sum_leaves (strides NT/2 .. 1); the strides that cross warps go through shared memory,
+   *  the last five run as shuffles on warp 0 (lane i < off adds the value of lane i + off: the same pair). */
   CCC_DEV void dot_trees()
   {
     red[tid] = tid < n ? z[tid] * z[tid] : 0.0;
     red[NT + tid] = tid < n ? z[tid] * np[tid] : 0.0;
     cta_sync();
-    for(int off = NT / 2; off >= 1; off >>= 1)
+    for(int off = NT / 2; off >= 32; off >>= 1)
     {
       if(tid < off)
       {
@@ -173,6 +176,58 @@ struct QpCta
       }
       cta_sync();
     }
+    if(tid < 32)
+    {
+      double a = red[tid], c = red[NT + tid];
+      CCC_UNROLL
+      for(int off = 16; off >= 1; off >>= 1)
+      {
+        const double ao = warp_shfl(a, (tid + off) & 31), co = warp_shfl(c, (tid + off) & 31);
+        a = a + ao;
+        c = c + co;
+      }
+      if(tid == 0)
+      {
+        red[0] = a;
+        red[NT] = c;
+      }
+    }
+    cta_sync();
+  }
+
+  /** CTA-wide argmin of (v, idx) with the lowest index winning ties; idx < 0 = no candidate.  Comparisons only,
+   *  so the order of the reduction does not matter: shuffles inside the warps, the NT/32 partial results through
+   *  shared memory.  Every thread returns with the result. */
+  CCC_DEV void cta_argmin(double & v, int & idx)
+  {
+    const int lane = tid & 31;
+    CCC_UNROLL
+    for(int off = 16; off >= 1; off >>= 1)
+    {
+      const double vo = warp_shfl_xor(v, off);
+      const int io = warp_shfl_i(idx, lane ^ off);
+      const bool take = io >= 0 && (idx < 0 || vo < v || (vo == v && io < idx));
+      v = take ? vo : v;
+      idx = take ? io : idx;
+    }
+    if(lane == 0)
+    {
+      red[tid >> 5] = v;
+      red_i[tid >> 5] = idx;
+    }
+    cta_sync();
+    v = red[0];
+    idx = red_i[0];
+    CCC_UNROLL
+    for(int w = 1; w < NT / 32; w++)
+    {
+      const double vo = red[w];
+      const int io = red_i[w];
+      const bool take = io >= 0 && (idx < 0 || vo < v || (vo == v && io < idx));
+      v = take ? vo : v;
+      idx = take ? io : idx;
+    }
+    cta_sync(); // red / red_i are free again
   }
 
   /** d = J' np, z = J[:, q:] d[q:], r = R^-1 d[:q] */
@@ -206,7 +261,7 @@ struct QpCta
           double ai = a[0];
           CCC_UNROLL
           for(int s = 1; s < kSlots; s++) ai = slot == s ? a[s] : ai;
-          r[i] = ai / R[i * ld + i];
+          r[i] = ai * rinv[i]; // no division on the sweep's dependency chain
         }
         warp_sync();
         const double ri = r[i];
@@ -282,7 +337,11 @@ struct QpCta
     }
     cta_sync();
     if(tid < q) R[tid * ld + q] = d[tid];
-    if(tid == 0) R[q * ld + q] = dq;
+    if(tid == 0)
+    {
+      R[q * ld + q] = dq;
+      rinv[q] = 1.0 / dq;
+    }
     q++;
     const bool ok = !(dabs(dq) <= eps * R_norm);
     if(ok) R_norm = R_norm < dabs(dq) ? dabs(dq) : R_norm;
@@ -362,6 +421,8 @@ struct QpCta
       }
       cta_sync();
     }
+    if(tid >= qq && tid < q) rinv[tid] = 1.0 / R[tid * ld + tid];
+    cta_sync();
   }
 
   CCC_DEV void solve()
@@ -485,29 +546,9 @@ struct QpCta
               best_i = i;
             }
           }
-        red[tid] = best;
-        red_i[tid] = best_i;
-        cta_sync();
-        for(int off = NT / 2; off >= 1; off >>= 1)
-        {
-          if(tid < off)
-          {
-            const double so = red[tid + off];
-            const int io = red_i[tid + off];
-            const double sa = red[tid];
-            const int ia = red_i[tid];
-            const bool take = io >= 0 && (ia < 0 || so < sa || (so == sa && io < ia));
-            if(take)
-            {
-              red[tid] = so;
-              red_i[tid] = io;
-            }
-          }
-          cta_sync();
-        }
-        const int pick = red_i[0];
-        const double worst = red[0];
-        cta_sync();
+        cta_argmin(best, best_i);
+        const int pick = best_i;
+        const double worst = best;
         if(pick < 0) break; // optimal
         if(q >= n)
         {
@@ -532,37 +573,32 @@ struct QpCta
       }
       compute_dzr();
       dot_trees();
-      if(tid == 0)
+      // step length: t1 = min over the active inequalities with r_k > 0 of u_k / r_k (first minimum in active-set
+      // order, one division per thread instead of a serial loop on one thread), t2 = -s_ip / (z . np)
+      const double zz = red[0], znp = red[NT];
+      cta_sync(); // everyone has read the two sums before cta_argmin reuses the buffer
+      double t1 = inf;
+      int kmin = -1;
+      if(tid >= me && tid < q && r[tid] > 0.0)
       {
-        int l = -1;
-        double t1 = inf;
-        for(int k = me; k < q; k++)
-          if(r[k] > 0.0)
-          {
-            const double ratio = u[k] / r[k];
-            if(ratio < t1)
-            {
-              t1 = ratio;
-              l = A[k];
-            }
-          }
-        double t2 = inf;
-        if(dabs(red[0]) > eps) t2 = (-s_ip) / red[NT];
-        const double t = t1 < t2 ? t1 : t2;
-        ctrl->t = t;
-        ctrl->l = l;
-        if(!(t < inf))
-          ctrl->action = 0; // infeasible
-        else if(!(t2 < inf))
-          ctrl->action = 1;
-        else if(t == t2)
-          ctrl->action = 2;
-        else
-          ctrl->action = 3;
+        t1 = u[tid] / r[tid];
+        kmin = tid;
       }
-      cta_sync();
-      const double t = ctrl->t;
-      const int action = ctrl->action, l = ctrl->l;
+      cta_argmin(t1, kmin);
+      const int l = kmin >= 0 ? A[kmin] : -1;
+      if(kmin < 0) t1 = inf;
+      double t2 = inf;
+      if(dabs(zz) > eps) t2 = (-s_ip) / znp;
+      const double t = t1 < t2 ? t1 : t2;
+      int action; // 0: infeasible, 1: dual step only, 2: full step, 3: partial step
+      if(!(t < inf))
+        action = 0;
+      else if(!(t2 < inf))
+        action = 1;
+      else if(t == t2)
+        action = 2;
+      else
+        action = 3;
       if(action == 0)
       {
         status = 1;

@@ -144,6 +144,7 @@ struct DenseQpSolver
     std::vector<char> is_active(me + mi, 0);
     int q = 0;
     double R_norm = 1.0;
+    std::vector<double> Rinv(n, 0.0);
 
     // unconstrained minimiser x = -Q^-1 c = -J (J' c)
     for(int j = 0; j < n; j++)
@@ -183,7 +184,7 @@ struct DenseQpSolver
       {
         double acc = d[i];
         for(int j = q - 1; j > i; j--) acc = std::fma(-R[i * n + j], r[j], acc);
-        r[i] = acc / R[i * n + i];
+        r[i] = acc * Rinv[i]; // reciprocal of the diagonal kept by add / delete: no division in the sweep
       }
     };
     // Givens sweep that folds d[q..n-1] into d[q] and rotates the columns of J (Goldfarb-Idnani's
@@ -229,6 +230,7 @@ struct DenseQpSolver
       d[q] = dq;
       q++;
       for(int i = 0; i < q; i++) R[i * n + q - 1] = d[i];
+      Rinv[q - 1] = 1.0 / d[q - 1];
       if(std::fabs(d[q - 1]) <= eps * R_norm) return false; // linearly dependent
       R_norm = std::max(R_norm, std::fabs(d[q - 1]));
       return true;
@@ -287,6 +289,7 @@ struct DenseQpSolver
           J[k * n + j + 1] = std::fma(xny, t1 + a, -t2);
         }
       }
+      for(int j = qq; j < q; j++) Rinv[j] = 1.0 / R[j * n + j];
     };
     auto dot_tree = [&](const std::vector<double> & a, const std::vector<double> & bb) {
       double p[256];
