@@ -318,21 +318,44 @@ struct QpCta
     cta_sync();
     if(tid < n)
     {
+      // the chain runs through `a` only (two fma per step); parameters and the row entry of the next step are
+      // loaded one step ahead so that no shared-memory latency sits on it
       double * row = J + tid * ld;
       double t2 = row[n - 1];
-      for(int j = n - 1; j >= q + 1; j--)
+      int j = n - 1;
+      double cc = 0.0, ss = 0.0, xny = 0.0, t1 = 0.0;
+      if(j >= q + 1)
       {
-        const double cc = gc[j];
-        const double t1 = row[j - 1];
+        cc = gc[j];
+        ss = gs[j];
+        xny = gx[j];
+        t1 = row[j - 1];
+      }
+      for(; j >= q + 1; j--)
+      {
+        double ccn = 0.0, ssn = 0.0, xnyn = 0.0, t1n = 0.0;
+        if(j - 1 >= q + 1)
+        {
+          ccn = gc[j - 1];
+          ssn = gs[j - 1];
+          xnyn = gx[j - 1];
+          t1n = row[j - 2];
+        }
         if(cc < 0.0)
         {
-          t2 = t1;
-          continue;
+          t2 = t1; // no rotation at this step
         }
-        const double a = dfma(t2, gs[j], t1 * cc);
-        row[j] = dfma(gx[j], t1 + a, -t2);
-        t2 = a; // column j-1 of this row: written when the next step (or the loop end) is done with it
-        row[j - 1] = a;
+        else
+        {
+          const double a = dfma(t2, ss, t1 * cc);
+          row[j] = dfma(xny, t1 + a, -t2);
+          row[j - 1] = a;
+          t2 = a;
+        }
+        cc = ccn;
+        ss = ssn;
+        xny = xnyn;
+        t1 = t1n;
       }
     }
     cta_sync();
