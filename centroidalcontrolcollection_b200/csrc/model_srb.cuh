@@ -28,7 +28,7 @@ struct Inertia3
     i2 = ldg(row + 14);
   }
 
-  /** LL^T factor in the order of oracle FreeLlt::compute (nf = 3). */
+  /** LL^T factor in the order of oracle DenseLlt::compute (nf = 3; the 3x3 inertia keeps the plain LL^T). */
   CCC_DEV void factor()
   {
     i0 = drcp(dsqrt(I[0]));

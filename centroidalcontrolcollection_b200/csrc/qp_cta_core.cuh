@@ -233,18 +233,41 @@ struct QpCta
   /** d = J' np, z = J[:, q:] d[q:], r = R^-1 d[:q] */
   CCC_DEV void compute_dzr()
   {
+    // both products as four interleaved fma chains (oracle num.hpp dot4: slot = position % 4 inside the summed
+    // range, combined as (s0 + s1) + (s2 + s3))
     if(tid < n)
     {
-      double acc = 0.0;
-      for(int i = 0; i < n; i++) acc = dfma(J[i * ld + tid], np[i], acc);
-      d[tid] = acc;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int i = 0;
+      for(; i + 4 <= n; i += 4)
+      {
+        s0 = dfma(J[i * ld + tid], np[i], s0);
+        s1 = dfma(J[(i + 1) * ld + tid], np[i + 1], s1);
+        s2 = dfma(J[(i + 2) * ld + tid], np[i + 2], s2);
+        s3 = dfma(J[(i + 3) * ld + tid], np[i + 3], s3);
+      }
+      if(i < n) s0 = dfma(J[i * ld + tid], np[i], s0);
+      if(i + 1 < n) s1 = dfma(J[(i + 1) * ld + tid], np[i + 1], s1);
+      if(i + 2 < n) s2 = dfma(J[(i + 2) * ld + tid], np[i + 2], s2);
+      d[tid] = (s0 + s1) + (s2 + s3);
     }
     cta_sync();
     if(tid < n)
     {
-      double acc = 0.0;
-      for(int j = q; j < n; j++) acc = dfma(J[tid * ld + j], d[j], acc);
-      z[tid] = acc;
+      const double * row = J + tid * ld;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int j = q;
+      for(; j + 4 <= n; j += 4)
+      {
+        s0 = dfma(row[j], d[j], s0);
+        s1 = dfma(row[j + 1], d[j + 1], s1);
+        s2 = dfma(row[j + 2], d[j + 2], s2);
+        s3 = dfma(row[j + 3], d[j + 3], s3);
+      }
+      if(j < n) s0 = dfma(row[j], d[j], s0);
+      if(j + 1 < n) s1 = dfma(row[j + 1], d[j + 1], s1);
+      if(j + 2 < n) s2 = dfma(row[j + 2], d[j + 2], s2);
+      z[tid] = (s0 + s1) + (s2 + s3);
     }
     if(tid < 32)
     {

@@ -167,6 +167,7 @@ public:
     u_init_.assign(warm ? static_cast<size_t>(B) * N * M : 0, 0.0);
     for(int b = 0; b < B; b++)
     {
+      if(items[b].schedule < 0 || items[b].schedule >= S) throw std::runtime_error("planBatch: schedule index out of range");
       sched_id_[b] = items[b].schedule;
       const auto st = items[b].initial_param.toState(mass_);
       for(int i = 0; i < 9; i++) x0_[static_cast<size_t>(b) * 9 + i] = st[i];

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <functional>
 #include <memory>
+#include <stdexcept>
 #include <vector>
 
 #include "CommonModels.h"
@@ -166,6 +167,9 @@ public:
                                   double control_dt = -1)
   {
     const int N = mpc_1d_->horizon_steps_, S = static_cast<int>(ref_data_funcs.size()), B = static_cast<int>(items.size());
+    if(S == 0 || B == 0) throw std::runtime_error("planBatch: empty schedule list or batch");
+    for(const auto & item : items)
+      if(item.schedule < 0 || item.schedule >= S) throw std::runtime_error("planBatch: schedule index out of range");
     std::vector<std::vector<LinearMpcZmp1d::RefData>> seqs(2 * S, std::vector<LinearMpcZmp1d::RefData>(N));
     for(int s = 0; s < S; s++)
       for(int i = 0; i < N; i++)

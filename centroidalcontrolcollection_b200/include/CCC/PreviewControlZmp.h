@@ -137,6 +137,9 @@ public:
                                   double control_dt = -1) const
   {
     const int N = preview_control_1d_->horizon_steps_, S = static_cast<int>(ref_zmp_funcs.size()), B = static_cast<int>(items.size());
+    if(S == 0 || B == 0) throw std::runtime_error("planBatch: empty schedule list or batch");
+    for(const auto & item : items)
+      if(item.schedule < 0 || item.schedule >= S) throw std::runtime_error("planBatch: schedule index out of range");
     std::vector<double> sched(static_cast<size_t>(2) * S * N);
     for(int s = 0; s < S; s++)
       for(int i = 0; i < N; i++)

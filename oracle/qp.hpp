@@ -168,18 +168,10 @@ struct DenseQpSolver
       return id < me ? acc - b[id] : acc + dvec[id - me];
     };
     auto compute_dzr = [&]() {
-      for(int j = 0; j < n; j++)
-      {
-        double acc = 0.0;
-        for(int i = 0; i < n; i++) acc = std::fma(J[i * n + j], np[i], acc);
-        d[j] = acc;
-      }
-      for(int i = 0; i < n; i++)
-      {
-        double acc = 0.0;
-        for(int j = q; j < n; j++) acc = std::fma(J[i * n + j], d[j], acc);
-        z[i] = acc;
-      }
+      // four interleaved fma chains per product (dot4, num.hpp): the engine's threads run one product each and
+      // a single chain of n dependent fma would be pure latency
+      for(int j = 0; j < n; j++) d[j] = dot4(J.data() + j, n, np.data(), 1, n);
+      for(int i = 0; i < n; i++) z[i] = dot4(J.data() + i * n + q, 1, d.data() + q, 1, n - q);
       for(int i = q - 1; i >= 0; i--)
       {
         double acc = d[i];
