@@ -9,9 +9,9 @@ namespace
 {
 __global__ void __launch_bounds__(ccc::kQpThreads, 1) qp_setup_kernel(int n, int me, int mi, const double * Q, const double * A,
                                                                        const double * C, double * Lg, double * invd, double * J0,
-                                                                       double * At, double * Ct, int * ok_flag)
+                                                                       double * At, double * Ct, int * ok_flag, double * J0s)
 {
-  ccc::qp_setup_cta(n, me, mi, Q, A, C, Lg, invd, J0, At, Ct, ok_flag);
+  ccc::qp_setup_cta(n, me, mi, Q, A, C, Lg, invd, J0, At, Ct, ok_flag, J0s);
 }
 
 template<int NT, bool kGlobal>
@@ -20,7 +20,11 @@ __global__ void __launch_bounds__(NT, 1) qp_solve_kernel(const __grid_constant__
 {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_b;
+  __shared__ __align__(8) unsigned long long s_mbar; // completion barrier of the per-problem TMA load of J
   double * slab = kGlobal ? gmat + (size_t)blockIdx.x * 2 * P.n * P.ld : nullptr;
+  if(!kGlobal && threadIdx.x == 0) ccc::mbar_init(&s_mbar, 1);
+  __syncthreads();
+  unsigned mbar_phase = 0;
   for(;;)
   {
     if(threadIdx.x == 0) s_b = atomicAdd(counter, 1);
@@ -29,7 +33,10 @@ __global__ void __launch_bounds__(NT, 1) qp_solve_kernel(const __grid_constant__
     __syncthreads();
     if(b >= P.B) break;
     ccc::QpCta<NT, kGlobal> cta(P, smem, b, slab);
+    cta.mbar = kGlobal ? nullptr : &s_mbar;
+    cta.mbar_phase = mbar_phase;
     cta.solve();
+    mbar_phase = cta.mbar_phase;
   }
 }
 
@@ -52,7 +59,7 @@ bool dev_alloc(T *& p, size_t n)
 struct ccc_qp_ws
 {
   int n = 0, me = 0, mi = 0, max_batch = 0, device = 0, launches = 0;
-  double *Lg = nullptr, *invd = nullptr, *J0 = nullptr, *At = nullptr, *Ct = nullptr;
+  double *Lg = nullptr, *invd = nullptr, *J0 = nullptr, *J0s = nullptr, *At = nullptr, *Ct = nullptr;
   int *ok_flag = nullptr, *counter = nullptr;
   double * gmat = nullptr; // per-CTA J/R slabs when they do not fit in shared memory
   int n_sm = 148;
@@ -86,7 +93,7 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
   cudaGetDevice(&ws->device);
   const size_t N = n, ME = n_eq, MI = n_ineq, B = max_batch;
   bool ok = true;
-  ok = ok && dev_alloc(ws->Lg, N * N) && dev_alloc(ws->invd, N) && dev_alloc(ws->J0, N * N);
+  ok = ok && dev_alloc(ws->Lg, N * N) && dev_alloc(ws->invd, N) && dev_alloc(ws->J0, N * N) && dev_alloc(ws->J0s, N * (N | 1));
   ok = ok && dev_alloc(ws->At, N * ME) && dev_alloc(ws->Ct, N * MI) && dev_alloc(ws->ok_flag, 2) && dev_alloc(ws->counter, 1);
   ok = ok && dev_alloc(ws->d_Q, N * N) && dev_alloc(ws->d_A, N * ME) && dev_alloc(ws->d_C, N * MI);
   ok = ok && dev_alloc(ws->d_c, B * N) && dev_alloc(ws->d_b, B * ME) && dev_alloc(ws->d_d, B * MI) && dev_alloc(ws->d_x, B * N);
@@ -113,7 +120,7 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
 void ccc_qp_destroy(ccc_qp_ws_t * ws)
 {
   if(!ws) return;
-  void * ptrs[] = {ws->gmat, ws->Lg,  ws->invd, ws->J0,  ws->At,  ws->Ct,     ws->ok_flag, ws->counter, ws->d_Q,    ws->d_A,
+  void * ptrs[] = {ws->J0s, ws->gmat, ws->Lg,  ws->invd, ws->J0,  ws->At,  ws->Ct,     ws->ok_flag, ws->counter, ws->d_Q,    ws->d_A,
                    ws->d_C, ws->d_c,  ws->d_b, ws->d_d, ws->d_x,    ws->d_iters, ws->d_status, ws->d_nact, ws->d_active};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -157,7 +164,7 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
     o_nact = res->n_active ? ws->d_nact : nullptr;
     o_active = res->active ? ws->d_active : nullptr;
   }
-  qp_setup_kernel<<<1, ccc::kQpThreads, 0, st>>>(n, me, mi, Q, A, C, ws->Lg, ws->invd, ws->J0, ws->At, ws->Ct, ws->ok_flag);
+  qp_setup_kernel<<<1, ccc::kQpThreads, 0, st>>>(n, me, mi, Q, A, C, ws->Lg, ws->invd, ws->J0, ws->At, ws->Ct, ws->ok_flag, ws->J0s);
   ws->launches++;
   ccc::QpParams P;
   P.n = n;
@@ -166,6 +173,7 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   P.B = B;
   P.ld = n | 1;
   P.J0 = ws->J0;
+  P.J0s = ws->J0s;
   P.At = ws->At;
   P.Ct = ws->Ct;
   P.c = c;

@@ -23,6 +23,7 @@ struct QpParams
 {
   int n, me, mi, B, ld;
   const double * J0; // [n][n]  L^-T of Q (setup kernel)
+  const double * J0s; // [n][ld] the same with the solve kernel's row stride: one TMA bulk copy per problem (or null)
   const double * At; // [n][me] transposed equality matrix
   const double * Ct; // [n][mi] transposed inequality matrix
   const double * c;  // [B][n] or null
@@ -91,6 +92,8 @@ struct QpCta
   QpCtrl * ctrl;
   int q;
   double R_norm;
+  unsigned long long * mbar = nullptr; // mbarrier of the TMA load of J (kernel-owned, initialised once per CTA)
+  unsigned mbar_phase = 0;
 
   /** `gmat`: this CTA's slab of 2 n ld doubles in global memory (kGlobal only). */
   CCC_DEV QpCta(const QpParams & p, double * smem, int prob, double * gmat = nullptr)
@@ -489,13 +492,35 @@ struct QpCta
       return;
     }
     // load the shared factor, reset the bookkeeping
-    for(int e = tid; e < n * n; e += NT) J[(e / n) * ld + (e % n)] = ldg(P.J0 + e);
+    bool by_tma = false;
+#if CCC_HAS_TMA
+    // one TMA bulk copy brings the pre-strided factor (n x ld doubles, 80.8 KB at n = 100) into shared memory
+    // while the threads reset the bookkeeping; the previous problem's generic accesses to J are ordered before
+    // the async-proxy write by the fence (every thread passed the barrier that ends solve())
+    by_tma = !kGlobal && mbar != nullptr && P.J0s != nullptr && ((n * ld) & 1) == 0;
+    if(by_tma && tid == 0)
+    {
+      fence_proxy_async_smem();
+      const unsigned bytes = static_cast<unsigned>(n * ld * sizeof(double));
+      mbar_arrive_expect_tx(mbar, bytes);
+      tma_bulk_g2s(J, P.J0s, bytes, mbar);
+    }
+#endif
+    if(!by_tma)
+      for(int e = tid; e < n * n; e += NT) J[(e / n) * ld + (e % n)] = ldg(P.J0 + e);
     for(int e = tid; e < me + mi; e += NT) is_active[e] = 0;
     for(int e = tid; e <= n; e += NT)
     {
       A[e] = -1;
       u[e] = 0.0;
     }
+#if CCC_HAS_TMA
+    if(by_tma)
+    {
+      mbar_wait(mbar, mbar_phase);
+      mbar_phase ^= 1u;
+    }
+#endif
     cta_sync();
     // unconstrained minimiser x = -J (J' c)
     if(tid < n)
@@ -711,7 +736,7 @@ namespace ccc
 /** Batch-invariant setup, one CTA: L = chol(Q) (scratch Lg), J0 = L^-T, transposed A and C.
  *  Evaluation order: oracle/qp.hpp DenseQpShared::setup. */
 CCC_DEV void qp_setup_cta(int n, int me, int mi, const double * Q, const double * A, const double * C, double * Lg,
-                          double * invd, double * J0, double * At, double * Ct, int * ok_flag)
+                          double * invd, double * J0, double * At, double * Ct, int * ok_flag, double * J0s = nullptr)
 {
   const int tid = thread_id();
   if(tid == 0) *ok_flag = 1;
@@ -750,6 +775,12 @@ CCC_DEV void qp_setup_cta(int n, int me, int mi, const double * Q, const double 
       for(int j = 0; j < r; j++) acc = dfma(-Lg[r * n + j], zrow[j], acc);
       zrow[r] = acc * invd[r];
     }
+  }
+  cta_sync();
+  if(J0s)
+  {
+    const int ld = n | 1;
+    for(int e = tid; e < n * ld; e += kQpThreads) J0s[e] = (e % ld) < n ? J0[(e / ld) * n + (e % ld)] : 0.0;
   }
   for(int e = tid; e < n * me; e += kQpThreads) At[e] = A[(e % me) * n + e / me];
   for(int e = tid; e < n * mi; e += kQpThreads) Ct[e] = C[(size_t)(e % mi) * n + e / mi];

@@ -45,6 +45,7 @@ template<class T>
 inline T ldg(const T * p) { return *p; }
 inline void prefetch_l1(const void *) {}
 } // namespace ccc
+#  define CCC_HAS_TMA 0
 #else
 #  include <cuda_runtime.h>
 #  include <stdint.h>
@@ -74,7 +75,39 @@ template<class T>
 CCC_DEV T ldg(const T * p) { return __ldg(p); }
 /** Hint: bring the 128-byte line holding p into L1 (no register, no scoreboard wait). */
 CCC_DEV void prefetch_l1(const void * p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// ---- TMA bulk copy global -> shared memory, completion on an mbarrier (sm_90+; SASS: UBLKCP / SYNCS) ----
+CCC_DEV unsigned smem_u32(const void * p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+CCC_DEV void mbar_init(unsigned long long * bar, int arrivals)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+/** One arrival + the number of bytes the bulk copies of this phase will deliver. */
+CCC_DEV void mbar_arrive_expect_tx(unsigned long long * bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+/** dst (shared, 16-byte aligned) <- src (global, 16-byte aligned), bytes a multiple of 16. */
+CCC_DEV void tma_bulk_g2s(void * dst, const void * src, unsigned bytes, unsigned long long * bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+CCC_DEV void mbar_wait(unsigned long long * bar, unsigned parity)
+{
+  unsigned done = 0;
+  while(!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+}
+/** Orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes. */
+CCC_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 } // namespace ccc
+#  define CCC_HAS_TMA 1
 #endif
 
 namespace ccc
