@@ -59,6 +59,7 @@ bool dev_alloc(T *& p, size_t n)
 struct ccc_qp_ws
 {
   int n = 0, me = 0, mi = 0, max_batch = 0, device = 0, launches = 0;
+  bool have_setup = false; // the matrices of an earlier call are factorised and resident (reused when Q == NULL)
   double *Lg = nullptr, *invd = nullptr, *J0 = nullptr, *J0s = nullptr, *At = nullptr, *Ct = nullptr;
   int *ok_flag = nullptr, *counter = nullptr;
   double * gmat = nullptr; // per-CTA J/R slabs when they do not fit in shared memory
@@ -135,7 +136,9 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   const int n = bt->n, me = bt->n_eq, mi = bt->n_ineq, B = bt->batch;
   if(n != ws->n || me != ws->me || mi != ws->mi) return ccc_host::fail(CCC_ERR_INVALID, "sizes differ from the workspace's");
   if(B <= 0 || B > ws->max_batch) return ccc_host::fail(CCC_ERR_ALLOC, "batch exceeds workspace");
-  if(!bt->Q || !bt->C || !bt->d || (me && (!bt->A || !bt->b))) return ccc_host::fail(CCC_ERR_INVALID, "null input");
+  const bool reuse = bt->Q == nullptr; // Q == NULL: keep the matrices (and their factorisation) of the previous call
+  if(reuse && !ws->have_setup) return ccc_host::fail(CCC_ERR_INVALID, "Q is NULL but this workspace holds no matrices yet");
+  if(!bt->d || (me && !bt->b) || (!reuse && (!bt->C || (me && !bt->A)))) return ccc_host::fail(CCC_ERR_INVALID, "null input");
   cudaStream_t st = mem == CCC_MEM_HOST ? ws->own_stream : reinterpret_cast<cudaStream_t>(stream_v);
   ws->launches = 0;
   const double *Q = bt->Q, *A = bt->A, *C = bt->C, *c = bt->c, *b = bt->b, *d = bt->d;
@@ -145,9 +148,12 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   {
 #define CCC_H2D(dst, src, nbytes) \
   if(!check(cudaMemcpyAsync(dst, src, (nbytes), cudaMemcpyHostToDevice, st), "H2D")) return CCC_ERR_CUDA
-    CCC_H2D(ws->d_Q, Q, sizeof(double) * n * n);
-    if(me) CCC_H2D(ws->d_A, A, sizeof(double) * me * n);
-    CCC_H2D(ws->d_C, C, sizeof(double) * mi * n);
+    if(!reuse)
+    {
+      CCC_H2D(ws->d_Q, Q, sizeof(double) * n * n);
+      if(me) CCC_H2D(ws->d_A, A, sizeof(double) * me * n);
+      CCC_H2D(ws->d_C, C, sizeof(double) * mi * n);
+    }
     if(c) CCC_H2D(ws->d_c, c, sizeof(double) * B * n);
     if(me) CCC_H2D(ws->d_b, b, sizeof(double) * B * me);
     CCC_H2D(ws->d_d, d, sizeof(double) * B * mi);
@@ -164,8 +170,12 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
     o_nact = res->n_active ? ws->d_nact : nullptr;
     o_active = res->active ? ws->d_active : nullptr;
   }
-  qp_setup_kernel<<<1, ccc::kQpThreads, 0, st>>>(n, me, mi, Q, A, C, ws->Lg, ws->invd, ws->J0, ws->At, ws->Ct, ws->ok_flag, ws->J0s);
-  ws->launches++;
+  if(!reuse)
+  {
+    qp_setup_kernel<<<1, ccc::kQpThreads, 0, st>>>(n, me, mi, Q, A, C, ws->Lg, ws->invd, ws->J0, ws->At, ws->Ct, ws->ok_flag, ws->J0s);
+    ws->launches++;
+    ws->have_setup = true;
+  }
   ccc::QpParams P;
   P.n = n;
   P.me = me;

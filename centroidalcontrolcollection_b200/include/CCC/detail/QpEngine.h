@@ -54,6 +54,7 @@ public:
     if(ws_) ccc_qp_destroy(ws_);
     ws_ = nullptr;
     ws_batch_ = 0;
+    matrices_resident_ = false;
   }
 
   int dimVar() const { return n_; }
@@ -83,6 +84,7 @@ public:
       ws_ = ccc_qp_create(n_, n_eq_, n_ineq_, batch_);
       if(!ws_) throw std::runtime_error(std::string("ccc_qp_create: ") + ccc_last_error());
       ws_batch_ = batch_;
+      matrices_resident_ = false;
     }
     x_.assign(static_cast<size_t>(batch_) * n_, 0.0);
     iters_.assign(batch_, 0);
@@ -94,9 +96,10 @@ public:
     bt.n_eq = n_eq_;
     bt.n_ineq = n_ineq_;
     bt.batch = batch_;
-    bt.Q = Q_.data();
-    bt.A = n_eq_ ? A_.data() : nullptr;
-    bt.C = C_.data();
+    // the matrices are uploaded and factorised by the first solve after setup(); later solves reuse them
+    bt.Q = matrices_resident_ ? nullptr : Q_.data();
+    bt.A = (matrices_resident_ || !n_eq_) ? nullptr : A_.data();
+    bt.C = matrices_resident_ ? nullptr : C_.data();
     bt.c = with_c_ ? c_.data() : nullptr;
     bt.b = n_eq_ ? b_.data() : nullptr;
     bt.d = d_.data();
@@ -108,6 +111,7 @@ public:
     rs.active = active_.data();
     const int rc = ccc_qp_solve(ws_, &bt, &rs, CCC_MEM_HOST, nullptr);
     if(rc != CCC_OK) throw std::runtime_error(std::string("ccc_qp_solve: ") + ccc_last_error());
+    matrices_resident_ = true;
     return x_;
   }
 
@@ -118,7 +122,7 @@ public:
 
 private:
   int n_ = 0, n_eq_ = 0, n_ineq_ = 0, batch_ = 0, ws_batch_ = 0;
-  bool with_c_ = false;
+  bool with_c_ = false, matrices_resident_ = false;
   Matrix Q_, A_, C_;
   std::vector<double> c_, b_, d_, x_;
   std::vector<int32_t> iters_, status_, n_active_, active_;

@@ -225,7 +225,8 @@ int32_t ccc_ddp_zmp_last_launches(const ccc_ddp_zmp_ws_t * ws);
 typedef struct
 {
   int32_t n, n_eq, n_ineq, batch;
-  const double * Q; /* [n][n]       shared */
+  const double * Q; /* [n][n]       shared; NULL = reuse Q, A, C (and their factorisation) of the previous call on
+                       this workspace: what a controller does that keeps one QpCoeff structure over its ticks */
   const double * A; /* [n_eq][n]    shared (NULL if n_eq = 0) */
   const double * C; /* [n_ineq][n]  shared */
   const double * c; /* [B][n]       or NULL = 0 */

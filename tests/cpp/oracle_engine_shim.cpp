@@ -6,6 +6,8 @@
  * libccc_b200.so on the GPU.  It is linked INSTEAD of libccc_b200.so by tests/test_cpp_dropin.py only; the
  * product library has no CPU path and nothing in the package refers to this file.
  */
+#include <vector>
+
 #include "../../include/ccc_b200.h"
 
 extern "C" {
@@ -20,7 +22,10 @@ int32_t ccc_oracle_hardware_threads(void);
 struct ccc_ddp_centroidal_ws { int dummy; };
 struct ccc_ddp_srb_ws { int dummy; };
 struct ccc_ddp_zmp_ws { int dummy; };
-struct ccc_qp_ws { int dummy; };
+struct ccc_qp_ws
+{
+  std::vector<double> Q, A, C; // matrices of the last call that carried them (Q == NULL reuses them)
+};
 
 void ccc_ddp_config_default(ccc_ddp_config_t * c) { ccc_oracle_ddp_config_default(c); }
 ccc_ddp_centroidal_ws_t * ccc_ddp_centroidal_create(int32_t, int32_t, int32_t) { return new ccc_ddp_centroidal_ws; }
@@ -43,9 +48,22 @@ int32_t ccc_ddp_zmp_solve(ccc_ddp_zmp_ws_t *, const ccc_ddp_zmp_batch_t * b, con
 }
 ccc_qp_ws_t * ccc_qp_create(int32_t, int32_t, int32_t, int32_t) { return new ccc_qp_ws; }
 void ccc_qp_destroy(ccc_qp_ws_t * w) { delete w; }
-int32_t ccc_qp_solve(ccc_qp_ws_t *, const ccc_qp_batch_t * b, ccc_qp_result_t * r, int32_t, void *)
+int32_t ccc_qp_solve(ccc_qp_ws_t * w, const ccc_qp_batch_t * b, ccc_qp_result_t * r, int32_t, void *)
 {
-  return ccc_oracle_qp_solve(b, r, ccc_oracle_hardware_threads());
+  ccc_qp_batch_t bt = *b;
+  const size_t n = b->n;
+  if(b->Q)
+  {
+    w->Q.assign(b->Q, b->Q + n * n);
+    w->A.assign(b->A ? b->A : b->Q, b->A ? b->A + static_cast<size_t>(b->n_eq) * n : b->Q);
+    w->C.assign(b->C, b->C + static_cast<size_t>(b->n_ineq) * n);
+  }
+  else if(w->Q.empty())
+    return CCC_ERR_INVALID;
+  bt.Q = w->Q.data();
+  bt.A = b->n_eq ? w->A.data() : nullptr;
+  bt.C = w->C.data();
+  return ccc_oracle_qp_solve(&bt, r, ccc_oracle_hardware_threads());
 }
 int32_t ccc_preview_input(int32_t batch, int32_t n, const double * K, const double * F, const double * x, const double * ref, double * u, int32_t, void *)
 {

@@ -103,3 +103,33 @@ def test_closed_loops(qp_solve):
         assert ok
         assert (planned - zl[0] >= 0).all() and (zl[1] - planned >= 0).all()
         assert (pos - zl[0] >= 0).all() and (zl[1] - pos >= 0).all()
+
+
+def test_matrix_reuse_and_unpaired_rows(oracle):
+    """Q == NULL reuses the matrices and the factorisation of the previous call on the workspace (what a
+    controller's per-tick calls do); a constraint matrix that is not of the [-G; G] form takes the unpaired search."""
+    import ctypes as C
+
+    from centroidalcontrolcollection_b200 import _abi, engine
+
+    rng = np.random.default_rng(7)
+    n, mi, B = 24, 37, 96  # odd row count: cannot be paired
+    M = rng.standard_normal((n, n))
+    ps = QpProblemSet(M @ M.T + np.eye(n), rng.standard_normal((mi, n)), rng.uniform(0.05, 0.6, (B, mi)), None, None,
+                      2 * rng.standard_normal((B, n)))
+    eng = engine.QpEngine(n, 0, mi, B)
+    first = eng.solve(ps.subset(np.arange(0, 48)))
+    second_ps = ps.subset(np.arange(48, 96))
+    res = second_ps.new_result()
+    bs, rs = second_ps.as_struct(), res.as_struct()
+    bs.Q = bs.A = bs.C = None
+    rc = engine.lib().ccc_qp_solve(eng._h, C.addressof(bs), C.addressof(rs), _abi.CCC_MEM_HOST, None)
+    assert rc == 0
+    ref = oracle.qp_solve(ps, n_threads=max(1, oracle.hardware_threads()))
+    for f in FIELDS:
+        assert np.array_equal(getattr(ref, f)[:48], getattr(first, f)), f
+        assert np.array_equal(getattr(ref, f)[48:], getattr(res, f)), f
+    # a fresh workspace has nothing to reuse
+    eng2 = engine.QpEngine(n, 0, mi, B)
+    rc = engine.lib().ccc_qp_solve(eng2._h, C.addressof(bs), C.addressof(rs), _abi.CCC_MEM_HOST, None)
+    assert rc != 0
