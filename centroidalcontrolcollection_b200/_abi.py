@@ -116,6 +116,23 @@ class DdpZmpBatch(C.Structure):
                 ("com_z", C.c_void_p), ("w", C.c_double * 6), ("x0", C.c_void_p), ("u_init", C.c_void_p)]
 
 
+class DdpCentroidalLoop(C.Structure):
+    """ccc_ddp_centroidal_loop_t"""
+
+    _fields_ = [("horizon_steps", C.c_int32), ("batch", C.c_int32), ("n_sched", C.c_int32), ("m_max", C.c_int32),
+                ("dt", C.c_double), ("mass", C.c_double), ("sim_dt", C.c_double),
+                ("ticks", C.c_int32), ("stride", C.c_int32), ("grid_len", C.c_int32), ("max_iter_later", C.c_int32),
+                ("sched_id", C.c_void_p), ("m", C.c_void_p), ("ridge", C.c_void_p), ("vertex", C.c_void_p), ("ref_pos", C.c_void_p),
+                ("w_run", C.c_double * 10), ("w_term", C.c_double * 9), ("u_lo", C.c_double), ("u_hi", C.c_double),
+                ("plant0", C.c_void_p), ("disturb_tick", C.c_int32), ("reserved0", C.c_int32), ("disturb_vel", C.c_double * 3)]
+
+
+class DdpCentroidalLoopResult(C.Structure):
+    """ccc_ddp_centroidal_loop_result_t"""
+
+    _fields_ = [("plant", C.c_void_p), ("u0", C.c_void_p), ("iters", C.c_void_p)]
+
+
 class QpBatch(C.Structure):
     """ccc_qp_batch_t"""
 

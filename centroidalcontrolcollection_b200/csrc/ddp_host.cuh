@@ -281,6 +281,89 @@ struct DdpEngine
     if(own_stream) cudaStreamDestroy(own_stream);
   }
 
+  /** Everything of the kernel parameters that does not depend on where inputs / outputs live (device pointers
+   *  in `in`); the caller sets u_init and the out_* pointers. */
+  ccc::DdpParams<M> make_params(const DdpInputs<M> & in, const ccc_ddp_config_t * cfg) const
+  {
+    ccc::DdpParams<M> P;
+    P.N = N;
+    P.B = in.B;
+    P.S = in.S;
+    P.tab_len = N;
+    P.ref_len = N + 1;
+    P.tab_off = 0;
+    P.tab_stride = 1;
+    P.sched_id = in.sched_id;
+    P.m = in.m;
+    P.tab = tab;
+    P.ref = in.ref;
+    for(int i = 0; i <= NX; i++) P.w_run[i] = in.w_run[i];
+    for(int i = 0; i < NX; i++) P.w_term[i] = in.w_term[i];
+    P.mp = in.mp;
+    P.u_lo = in.u_lo;
+    P.u_hi = in.u_hi;
+    P.x0 = in.x0;
+    P.u_init = nullptr;
+    P.cfg = to_cfg(cfg);
+    P.chunk_iters = 0;
+    P.xbuf = xbuf;
+    P.ubuf = ubuf;
+    P.gains = gains;
+    P.resume = resume;
+    P.out_x = nullptr;
+    P.out_u = nullptr;
+    P.out_cost = nullptr;
+    P.out_iters = nullptr;
+    P.out_status = nullptr;
+    P.trace_len = 0;
+    P.out_alpha_idx = nullptr;
+    P.out_lambda = nullptr;
+    P.out_clamped = nullptr;
+    return P;
+  }
+
+  /** Work queue + persistent solve kernel for the problems described by P (all pointers on the device). */
+  int launch_solve(ccc::DdpParams<M> & P, const ccc_ddp_config_t * cfg, cudaStream_t st)
+  {
+    const int B = P.B;
+    // work queue: every problem once, plus room for re-queued (suspended) solves
+    int nv = 0;
+    const auto * vt = Variants<M>::table(nv);
+    const auto & var = vt[g_variant() < nv ? g_variant() : 0];
+    auto kernel = var.kernel[cfg->with_input_constraint ? 1 : 0];
+    const size_t smem_bytes = (size_t)var.warps * ccc::SmLayout<M::NX, M::NXP>::TOTAL * sizeof(double);
+    SolveQueue q;
+    q.slot = qslot;
+    q.head = qctl;
+    q.tail = qctl + 1;
+    q.done = qctl + 2;
+    P.chunk_iters = g_chunk();
+    if(P.chunk_iters > 0)
+    {
+      // a solve is re-queued at most ceil(max_iter / chunk) - 1 times; fall back to
+      // run-to-completion if that does not fit the queue allocated with the workspace
+      const long long visits = ((long long)cfg->max_iter + P.chunk_iters - 1) / P.chunk_iters + 1;
+      if(visits * B > qcap) P.chunk_iters = 0;
+    }
+    q.capacity = P.chunk_iters > 0 ? qcap : B;
+    init_queue_kernel<<<(q.capacity + 255) / 256, 256, 0, st>>>(q, B);
+    launches++;
+    // persistent grid: exactly the CTAs that are co-resident (warps spin on the queue, so every
+    // launched CTA must be running)
+    int n_sm = 148, per_sm = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    if(!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, var.warps * 32, smem_bytes), "occupancy"))
+      return CCC_ERR_CUDA;
+    if(per_sm < 1) return fail(CCC_ERR_CUDA, "solve kernel does not fit on an SM");
+    if(per_sm > var.ctas) per_sm = var.ctas;
+    int grid = (B + var.warps - 1) / var.warps;
+    if(grid > n_sm * per_sm) grid = n_sm * per_sm;
+    kernel<<<grid, var.warps * 32, smem_bytes, st>>>(P, q);
+    launches++;
+    if(!check(cudaGetLastError(), "launch ddp_solve_kernel")) return CCC_ERR_CUDA;
+    return CCC_OK;
+  }
+
   /** Validate, stage (host mode), pack, launch, collect.  `extra_pack(stream, in_dev)` is called
    *  after the common table rows are packed, with device pointers, to fill model-specific rows. */
   template<class ExtraPack>
@@ -362,26 +445,8 @@ struct DdpEngine
     }
     double * solver_out_u = (o_u && mm != 32) ? uo32 : o_u;
 
-    ccc::DdpParams<M> P;
-    P.N = N;
-    P.B = B;
-    P.S = S;
-    P.sched_id = in.sched_id;
-    P.m = in.m;
-    P.tab = tab;
-    P.ref = in.ref;
-    for(int i = 0; i <= NX; i++) P.w_run[i] = in.w_run[i];
-    for(int i = 0; i < NX; i++) P.w_term[i] = in.w_term[i];
-    P.mp = in.mp;
-    P.u_lo = in.u_lo;
-    P.u_hi = in.u_hi;
-    P.x0 = in.x0;
+    ccc::DdpParams<M> P = make_params(in, cfg);
     P.u_init = u_init32;
-    P.cfg = to_cfg(cfg);
-    P.xbuf = xbuf;
-    P.ubuf = ubuf;
-    P.gains = gains;
-    P.resume = resume;
     P.out_x = o_x;
     P.out_u = solver_out_u;
     P.out_cost = o_cost;
@@ -391,42 +456,8 @@ struct DdpEngine
     P.out_alpha_idx = o_alpha;
     P.out_lambda = o_lambda;
     P.out_clamped = o_clamped;
-
-    // work queue: every problem once, plus room for re-queued (suspended) solves
-    int nv = 0;
-    const auto * vt = Variants<M>::table(nv);
-    const auto & var = vt[g_variant() < nv ? g_variant() : 0];
-    auto kernel = var.kernel[cfg->with_input_constraint ? 1 : 0];
-    const size_t smem_bytes = (size_t)var.warps * ccc::SmLayout<M::NX, M::NXP>::TOTAL * sizeof(double);
-    SolveQueue q;
-    q.slot = qslot;
-    q.head = qctl;
-    q.tail = qctl + 1;
-    q.done = qctl + 2;
-    P.chunk_iters = g_chunk();
-    if(P.chunk_iters > 0)
-    {
-      // a solve is re-queued at most ceil(max_iter / chunk) - 1 times; fall back to
-      // run-to-completion if that does not fit the queue allocated with the workspace
-      const long long visits = ((long long)cfg->max_iter + P.chunk_iters - 1) / P.chunk_iters + 1;
-      if(visits * B > qcap) P.chunk_iters = 0;
-    }
-    q.capacity = P.chunk_iters > 0 ? qcap : B;
-    init_queue_kernel<<<(q.capacity + 255) / 256, 256, 0, st>>>(q, B);
-    launches++;
-    // persistent grid: exactly the CTAs that are co-resident (warps spin on the queue, so every
-    // launched CTA must be running)
-    int n_sm = 148, per_sm = 0;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-    if(!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, var.warps * 32, smem_bytes), "occupancy"))
-      return CCC_ERR_CUDA;
-    if(per_sm < 1) return fail(CCC_ERR_CUDA, "solve kernel does not fit on an SM");
-    if(per_sm > var.ctas) per_sm = var.ctas;
-    int grid = (B + var.warps - 1) / var.warps;
-    if(grid > n_sm * per_sm) grid = n_sm * per_sm;
-    kernel<<<grid, var.warps * 32, smem_bytes, st>>>(P, q);
-    launches++;
-    if(!check(cudaGetLastError(), "launch ddp_solve_kernel")) return CCC_ERR_CUDA;
+    const int rc = launch_solve(P, cfg, st);
+    if(rc != CCC_OK) return rc;
 
     if(o_u && solver_out_u != o_u)
     {

@@ -48,10 +48,14 @@ template<class M>
 struct DdpParams
 {
   int N, B, S;
+  // Stage k of a problem reads entry tab_off + k * tab_stride of its schedule's tables.  A plain solve has one
+  // entry per stage (tab_len = N, ref_len = N + 1, offset 0, stride 1); the closed loop keeps the tables on the
+  // plant's time grid and slides the horizon over them (offset = control cycle, stride = horizon_dt / sim_dt).
+  int tab_len = 0, ref_len = 0, tab_off = 0, tab_stride = 1;
   const int * sched_id;   // [B]
-  const int * m;          // [S][N]
-  const double * tab;     // [S][N][M::TAB_ROWS][32] packed stage tables (lane-contiguous rows)
-  const double * ref;     // [S][N+1][M::NREF] reference of the first NREF states
+  const int * m;          // [S][tab_len]
+  const double * tab;     // [S][tab_len][M::TAB_ROWS][32] packed stage tables (lane-contiguous rows)
+  const double * ref;     // [S][ref_len][M::NREF] reference of the first NREF states
   double w_run[M::NX + 1]; // diagonal running weights of the states, then the force weight
   double w_term[M::NX];    // diagonal terminal weights
   typename M::Params mp;   // model constants (dt, mass, ...)
@@ -127,9 +131,10 @@ struct DdpWarp
   CCC_DEV double * xtraj(int which) const { return P.xbuf + ((size_t)which * P.B + b) * (size_t)(P.N + 1) * NX; }
   CCC_DEV double * utraj(int which) const { return P.ubuf + ((size_t)which * P.B + b) * (size_t)P.N * 32; }
   CCC_DEV double * gain(int k) const { return P.gains + ((size_t)b * P.N + k) * (32 * (1 + NX)); }
-  CCC_DEV int stage_m(int k) const { return ldg(P.m + (size_t)sched * P.N + k); }
-  CCC_DEV const double * stage_tab(int k) const { return P.tab + ((size_t)sched * P.N + k) * (32 * M::TAB_ROWS); }
-  CCC_DEV const double * ref(int k) const { return P.ref + ((size_t)sched * (P.N + 1) + k) * NREF; }
+  CCC_DEV int entry(int k) const { return P.tab_off + k * P.tab_stride; }
+  CCC_DEV int stage_m(int k) const { return ldg(P.m + (size_t)sched * P.tab_len + entry(k)); }
+  CCC_DEV const double * stage_tab(int k) const { return P.tab + ((size_t)sched * P.tab_len + entry(k)) * (32 * M::TAB_ROWS); }
+  CCC_DEV const double * ref(int k) const { return P.ref + ((size_t)sched * P.ref_len + entry(k)) * NREF; }
 
   /** lanes 0..NX-1 store the (warp-uniform) state vector: select chain, one predicated store. */
   CCC_DEV void storeX(double * dst, const double (&x)[NX]) const

@@ -54,6 +54,8 @@ def lib():
         L.ccc_ddp_centroidal_set_variant.argtypes = [C.c_int32]
         L.ccc_ddp_centroidal_set_chunk.restype = None
         L.ccc_ddp_centroidal_set_chunk.argtypes = [C.c_int32]
+        L.ccc_ddp_centroidal_closed_loop.restype = C.c_int32
+        L.ccc_ddp_centroidal_closed_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_ddp_srb_create.restype = C.c_void_p
         L.ccc_ddp_srb_create.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         L.ccc_ddp_srb_destroy.argtypes = [C.c_void_p]
@@ -149,6 +151,15 @@ class DdpCentroidalEngine(_DdpEngineBase):
     include/CCC/DdpCentroidal.h:342-365): owns the device workspace, solves batches."""
 
     _prefix = "ccc_ddp_centroidal"
+
+    def closed_loop(self, loop, cfg):
+        """Device-resident receding-horizon loop (ccc_ddp_centroidal_closed_loop, host buffers in / out) for a
+        closed_loop.CentroidalLoop; returns its LoopResultArrays."""
+        res = loop.new_result()
+        ls, rs = loop.as_struct(), res.as_struct()
+        rc = lib().ccc_ddp_centroidal_closed_loop(self._h, C.addressof(ls), C.addressof(cfg), C.addressof(rs), _abi.CCC_MEM_HOST, None)
+        _check(rc, "ccc_ddp_centroidal_closed_loop")
+        return res
 
     @staticmethod
     def set_variant(v):

@@ -135,6 +135,58 @@ int32_t ccc_ddp_centroidal_solve(ccc_ddp_centroidal_ws_t * ws,
 /* Number of kernels the last solve on this workspace launched (bench.py's gpu_launches). */
 int32_t ccc_ddp_centroidal_last_launches(const ccc_ddp_centroidal_ws_t * ws);
 
+/* ---- closed loop (receding horizon) around CCC::DdpCentroidal, resident on the device -------------------
+ * The control loop of the reference's own test (tests/src/TestDdpCentroidal.cpp:94-150) for a batch of plants:
+ * every control cycle plans with the plant's current state (warm start = the previous plan, zeroed where a
+ * stage's input dimension changed, :102-114; max_iter = max_iter_later after the first cycle, :116), applies
+ * the first stage's wrench to the plant (CentroidalSim, tests/src/SimModels.h:233-332: exact zero-order hold
+ * of a point mass + angular momentum) and moves on by sim_dt.  No host round trip between cycles.
+ * The contact / reference schedule is given on the plant's time grid: stage k of cycle t reads grid entry
+ * t + k * stride, stride = horizon_dt / sim_dt (an integer), i.e. the callbacks sampled at
+ * time = current_time0 + entry * sim_dt. */
+typedef struct
+{
+  int32_t horizon_steps; /* N */
+  int32_t batch;         /* B */
+  int32_t n_sched;       /* S */
+  int32_t m_max;         /* row stride of ridge/vertex, <= CCC_DDP_M_MAX */
+  double dt;             /* horizon_dt [s] */
+  double mass;           /* [kg] */
+  double sim_dt;         /* control / plant period [s] */
+  int32_t ticks;         /* control cycles */
+  int32_t stride;        /* horizon_dt / sim_dt */
+  int32_t grid_len;      /* time-grid entries per schedule, >= ticks - 1 + horizon_steps * stride + 1 */
+  int32_t max_iter_later; /* DDP iterations per cycle after the first one (the first uses cfg->max_iter) */
+  const int32_t * sched_id; /* [B] */
+  const int32_t * m;        /* [S][grid_len] */
+  const double * ridge;     /* [S][grid_len][m_max][3] */
+  const double * vertex;    /* [S][grid_len][m_max][3] */
+  const double * ref_pos;   /* [S][grid_len][3] */
+  double w_run[10];
+  double w_term[9];
+  double u_lo, u_hi;
+  const double * plant0;    /* [B][9] initial plant state: position, velocity, angular momentum */
+  int32_t disturb_tick;     /* -1: none; else the velocity impulse is added after the plant step of this cycle */
+  int32_t reserved0;
+  double disturb_vel[3];    /* [m/s] */
+} ccc_ddp_centroidal_loop_t;
+
+typedef struct
+{
+  double * plant;  /* [B][ticks+1][9] plant state at the start of every cycle and after the last one */
+  double * u0;     /* [B][ticks][m_max] force scales applied in every cycle, or NULL */
+  int32_t * iters; /* [B][ticks] DDP iterations of every cycle, or NULL */
+} ccc_ddp_centroidal_loop_result_t;
+
+/* Runs on the workspace of ccc_ddp_centroidal_create(horizon_steps, >= batch, >= n_sched).  Host pointers
+ * (CCC_MEM_HOST, synchronous) or device pointers (CCC_MEM_DEVICE, enqueued on `stream`). */
+int32_t ccc_ddp_centroidal_closed_loop(ccc_ddp_centroidal_ws_t * ws,
+                                       const ccc_ddp_centroidal_loop_t * loop,
+                                       const ccc_ddp_config_t * cfg,
+                                       ccc_ddp_centroidal_loop_result_t * result,
+                                       int32_t mem,
+                                       void * stream);
+
 /* ---- CCC::DdpSingleRigidBody -----------------------------------------------------------------
  * Flat form of what DdpSingleRigidBody::planOnce (reference src/DdpSingleRigidBody.cpp:283-307) reads
  * through its callbacks at t_k = current_time + k*dt: MotionParam.{contact_list, inertia_mat}

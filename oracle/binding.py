@@ -86,3 +86,16 @@ def ddp_zmp_solve(problem_set, cfg, trace_len=0, n_threads=1):
     if rc != 0:
         raise RuntimeError(f"oracle returned {rc}")
     return res
+
+
+def ddp_centroidal_closed_loop(loop, cfg, n_threads=1):
+    """Run the oracle's closed loop on a centroidalcontrolcollection_b200.closed_loop.CentroidalLoop."""
+    L = lib()
+    L.ccc_oracle_ddp_centroidal_closed_loop.restype = C.c_int32
+    L.ccc_oracle_ddp_centroidal_closed_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    res = loop.new_result()
+    ls, rs = loop.as_struct(), res.as_struct()
+    rc = L.ccc_oracle_ddp_centroidal_closed_loop(C.addressof(ls), C.addressof(cfg), C.addressof(rs), int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return res

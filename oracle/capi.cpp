@@ -168,6 +168,123 @@ int32_t ccc_oracle_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t * bt,
   return CCC_OK;
 }
 
+/** Same contract as ccc_ddp_centroidal_closed_loop with host pointers: the control loop of the reference's test
+ *  (tests/src/TestDdpCentroidal.cpp:94-150) with the plant of tests/src/SimModels.h:233-332, one problem per task.
+ *  Plant arithmetic in the engine's operation order (sequential fma over the ridges, exact ZOH polynomial). */
+int32_t ccc_oracle_ddp_centroidal_closed_loop(const ccc_ddp_centroidal_loop_t * lp,
+                                              const ccc_ddp_config_t * c,
+                                              ccc_ddp_centroidal_loop_result_t * r,
+                                              int32_t n_threads)
+{
+  if(!lp || !c || !r || !r->plant || lp->m_max > 32 || lp->m_max <= 0 || lp->stride <= 0) return CCC_ERR_INVALID;
+  const int N = lp->horizon_steps, mm = lp->m_max, T = lp->ticks, G = lp->grid_len, stride = lp->stride;
+  if(static_cast<long long>(G) < static_cast<long long>(T) - 1 + static_cast<long long>(N) * stride + 1) return CCC_ERR_INVALID;
+  parallelFor(lp->batch, n_threads, [&](int b) {
+    const size_t sched = static_cast<size_t>(lp->sched_id[b]);
+    const int32_t * mg = lp->m + sched * G;
+    const double * rg = lp->ridge + sched * G * mm * 3;
+    const double * vg = lp->vertex + sched * G * mm * 3;
+    const double * fg = lp->ref_pos + sched * G * 3;
+    double pos[3], vel[3], L[3];
+    for(int a = 0; a < 3; a++)
+    {
+      pos[a] = lp->plant0[static_cast<size_t>(b) * 9 + a];
+      vel[a] = lp->plant0[static_cast<size_t>(b) * 9 + 3 + a];
+      L[a] = lp->plant0[static_cast<size_t>(b) * 9 + 6 + a];
+    }
+    double * log = r->plant + static_cast<size_t>(b) * (T + 1) * 9;
+    for(int a = 0; a < 3; a++)
+    {
+      log[a] = pos[a];
+      log[3 + a] = vel[a];
+      log[6 + a] = L[a];
+    }
+    std::vector<int32_t> m_t(N);
+    std::vector<double> ridge_t(static_cast<size_t>(N) * mm * 3), vertex_t(static_cast<size_t>(N) * mm * 3), ref_t(static_cast<size_t>(N + 1) * 3);
+    std::vector<std::vector<double>> u_prev;
+    DdpConfig cfg = toConfig(c);
+    for(int tick = 0; tick < T; tick++)
+    {
+      // the horizon of this cycle: stage k <- grid entry tick + k * stride
+      for(int k = 0; k <= N; k++)
+      {
+        const size_t e = static_cast<size_t>(tick) + static_cast<size_t>(k) * stride;
+        for(int a = 0; a < 3; a++) ref_t[static_cast<size_t>(k) * 3 + a] = fg[e * 3 + a];
+        if(k == N) break;
+        m_t[k] = mg[e];
+        std::copy(rg + e * mm * 3, rg + (e + 1) * mm * 3, ridge_t.begin() + static_cast<size_t>(k) * mm * 3);
+        std::copy(vg + e * mm * 3, vg + (e + 1) * mm * 3, vertex_t.begin() + static_cast<size_t>(k) * mm * 3);
+      }
+      CentroidalProblem p;
+      p.N = N;
+      p.dt = lp->dt;
+      p.mass = lp->mass;
+      p.m_max = mm;
+      p.m_tab = m_t.data();
+      p.ridge = ridge_t.data();
+      p.vertex = vertex_t.data();
+      p.ref_pos = ref_t.data();
+      for(int i = 0; i < 10; i++) p.w_run[i] = lp->w_run[i];
+      for(int i = 0; i < 9; i++) p.w_term[i] = lp->w_term[i];
+      p.u_lo = lp->u_lo;
+      p.u_hi = lp->u_hi;
+      DdpSolver s(p);
+      if(tick == 1) cfg.max_iter = lp->max_iter_later;
+      s.cfg = cfg;
+      // warm start: the previous plan stage by stage, zeroed where the input dimension changed
+      std::vector<std::vector<double>> u0(N);
+      for(int k = 0; k < N; k++)
+      {
+        const int m = m_t[k];
+        u0[k].assign(m, 0.0);
+        if(tick > 0 && mg[static_cast<size_t>(tick) - 1 + static_cast<size_t>(k) * stride] == m) u0[k] = u_prev[k];
+      }
+      const double x0[9] = {pos[0], pos[1], pos[2], lp->mass * vel[0], lp->mass * vel[1], lp->mass * vel[2], L[0], L[1], L[2]};
+      s.solve(x0, u0);
+      u_prev = s.u;
+      // plant: total wrench of the first stage about the CoM, then one exact ZOH step
+      const int mk = m_t[0];
+      double f[3] = {0.0, 0.0, 0.0}, n[3] = {0.0, 0.0, 0.0};
+      for(int j = 0; j < mk; j++)
+      {
+        const double uj = s.u[0][j];
+        double rho[3], d[3], cr[3];
+        for(int a = 0; a < 3; a++)
+        {
+          rho[a] = ridge_t[static_cast<size_t>(j) * 3 + a];
+          d[a] = vertex_t[static_cast<size_t>(j) * 3 + a] - pos[a];
+        }
+        cross3(d, rho, cr);
+        for(int a = 0; a < 3; a++)
+        {
+          f[a] = std::fma(uj, rho[a], f[a]);
+          n[a] = std::fma(uj, cr[a], n[a]);
+        }
+      }
+      const double sim_dt = lp->sim_dt, half_dt2 = 0.5 * (sim_dt * sim_dt);
+      for(int a = 0; a < 3; a++)
+      {
+        const double acc = f[a] / lp->mass + (a == 2 ? -9.80665 : 0.0);
+        pos[a] = std::fma(half_dt2, acc, std::fma(sim_dt, vel[a], pos[a]));
+        vel[a] = std::fma(sim_dt, acc, vel[a]);
+        L[a] = std::fma(sim_dt, n[a], L[a]);
+        if(tick == lp->disturb_tick) vel[a] = vel[a] + lp->disturb_vel[a];
+      }
+      double * lg = log + static_cast<size_t>(tick + 1) * 9;
+      for(int a = 0; a < 3; a++)
+      {
+        lg[a] = pos[a];
+        lg[3 + a] = vel[a];
+        lg[6 + a] = L[a];
+      }
+      if(r->u0)
+        for(int j = 0; j < mm; j++) r->u0[(static_cast<size_t>(b) * T + tick) * mm + j] = j < mk ? s.u[0][j] : 0.0;
+      if(r->iters) r->iters[static_cast<size_t>(b) * T + tick] = s.trace.back().iter;
+    }
+  });
+  return CCC_OK;
+}
+
 /** Evaluate the DdpCentroidal problem functions of stage k of schedule 0 at (x, u): for the
  *  derivative known-answer tests (reference tests/src/TestDdpCentroidal.cpp:176-284).
  *  Fx 9x9, Fu 9xm (row-major), Lx 9, Lu m; any output may be NULL. */

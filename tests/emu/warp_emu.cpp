@@ -239,6 +239,10 @@ int32_t emuSolve(int N, int B, int S, int mm, const int32_t * sched_id, const in
   P.N = N;
   P.B = B;
   P.S = S;
+  P.tab_len = N;
+  P.ref_len = N + 1;
+  P.tab_off = 0;
+  P.tab_stride = 1;
   P.sched_id = sched_id;
   P.m = m;
   P.tab = tab.data();
