@@ -32,6 +32,9 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_abi.DdpConfig) == 4 * 4 + 9 * 8 + 16 * 8 + 2 * 4 + 5 * 8
     assert C.sizeof(_abi.DdpResult) == 5 * 8 + 2 * 4 + 3 * 8
     assert C.sizeof(_abi.DdpCentroidalBatch) == 4 * 4 + 2 * 8 + 5 * 8 + 19 * 8 + 2 * 8 + 2 * 8
+    # ccc_ddp_centroidal_loop_t: 4 int32, 3 double, 4 int32, 5 pointers, 10 + 9 + 2 double, pointer, 2 int32, 3 double
+    assert C.sizeof(_abi.DdpCentroidalLoop) == 4 * 4 + 3 * 8 + 4 * 4 + 5 * 8 + 21 * 8 + 8 + 2 * 4 + 3 * 8
+    assert C.sizeof(_abi.DdpCentroidalLoopResult) == 3 * 8
 
 
 def test_default_config_matches_host_mirror():
