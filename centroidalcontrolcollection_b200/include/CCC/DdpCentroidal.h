@@ -11,6 +11,7 @@
  * Header-only; link with libccc_b200.so.  No CPU fallback: throws std::runtime_error without a GPU.
  */
 #pragma once
+#include <cmath>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -226,6 +227,124 @@ public:
     std::vector<VectorXd> first(B);
     for(int b = 0; b < B; b++) first[b] = u_list(b)[0];
     return first;
+  }
+
+  /** Result of runClosedLoopBatch: plant state (position, velocity, angular momentum) of every problem at the
+   *  start of every control cycle and after the last one, and the DDP iterations of every cycle. */
+  struct ClosedLoopResult
+  {
+    int batch = 0, ticks = 0;
+    std::vector<double> plant; // [batch][ticks + 1][9]
+    std::vector<int32_t> iters; // [batch][ticks]
+    const double * state(int b, int tick) const { return &plant[(static_cast<size_t>(b) * (ticks + 1) + tick) * 9]; }
+    int iter(int b, int tick) const { return iters[static_cast<size_t>(b) * ticks + tick]; }
+  };
+
+  /** The receding-horizon loop of the reference's own test (tests/src/TestDdpCentroidal.cpp:94-150) for a batch of
+   *  plants, resident on the device (ccc_ddp_centroidal_closed_loop): every cycle plans from the plant's state with
+   *  the previous plan as warm start (config().max_iter iterations in the first cycle, max_iter_later afterwards),
+   *  applies the first stage's wrench to the plant (point mass + angular momentum, exact zero-order hold over
+   *  sim_dt) and moves on.  The callbacks are sampled at start_time + entry * sim_dt; horizon_dt must be an integer
+   *  multiple of sim_dt.  items[b].initial_param gives the initial plant state (u_list is ignored). */
+  ClosedLoopResult runClosedLoopBatch(const std::vector<std::function<MotionParam(double)>> & motion_param_funcs,
+                                      const std::vector<std::function<RefData(double)>> & ref_data_funcs,
+                                      const std::vector<BatchItem> & items,
+                                      double start_time,
+                                      double sim_dt,
+                                      int ticks,
+                                      int max_iter_later = 1,
+                                      int disturb_tick = -1,
+                                      const Vector3d & disturb_vel = {0.0, 0.0, 0.0})
+  {
+    const int N = horizon_steps_, S = static_cast<int>(motion_param_funcs.size()), B = static_cast<int>(items.size());
+    if(S == 0 || ref_data_funcs.size() != motion_param_funcs.size() || B == 0 || ticks <= 0)
+      throw std::runtime_error("runClosedLoopBatch: schedule lists / batch / ticks");
+    const int stride = static_cast<int>(dt_ / sim_dt + 0.5);
+    if(stride < 1 || std::fabs(stride * sim_dt - dt_) > 1e-12 * dt_)
+      throw std::runtime_error("runClosedLoopBatch: horizon_dt must be an integer multiple of sim_dt");
+    const int M = CCC_DDP_M_MAX, G = ticks - 1 + N * stride + 1;
+    std::vector<int32_t> m(static_cast<size_t>(S) * G, 0), sched_id(B);
+    std::vector<double> ridge(static_cast<size_t>(S) * G * M * 3, 0.0), vertex(ridge.size(), 0.0), ref(static_cast<size_t>(S) * G * 3, 0.0);
+    for(int s = 0; s < S; s++)
+      for(int e = 0; e < G; e++)
+      {
+        const double t = start_time + e * sim_dt;
+        const RefData rd = ref_data_funcs[s](t);
+        for(int a = 0; a < 3; a++) ref[(static_cast<size_t>(s) * G + e) * 3 + a] = rd.pos[a];
+        const MotionParam mp = motion_param_funcs[s](t);
+        int j = 0;
+        for(const auto & contact : mp.contact_list)
+          for(const auto & vr : contact->vertexWithRidgeList_)
+            for(const auto & r : vr.ridgeList)
+            {
+              if(j >= M) throw std::runtime_error("runClosedLoopBatch: more than CCC_DDP_M_MAX inputs in a stage");
+              const size_t o = ((static_cast<size_t>(s) * G + e) * M + j) * 3;
+              for(int a = 0; a < 3; a++)
+              {
+                ridge[o + a] = r[a];
+                vertex[o + a] = vr.vertex[a];
+              }
+              j++;
+            }
+        m[static_cast<size_t>(s) * G + e] = j;
+      }
+    std::vector<double> plant0(static_cast<size_t>(B) * 9);
+    for(int b = 0; b < B; b++)
+    {
+      if(items[b].schedule < 0 || items[b].schedule >= S) throw std::runtime_error("runClosedLoopBatch: schedule index out of range");
+      sched_id[b] = items[b].schedule;
+      const InitialParam & ip = items[b].initial_param;
+      for(int a = 0; a < 3; a++)
+      {
+        plant0[static_cast<size_t>(b) * 9 + a] = ip.pos[a];
+        plant0[static_cast<size_t>(b) * 9 + 3 + a] = ip.vel[a];
+        plant0[static_cast<size_t>(b) * 9 + 6 + a] = ip.angular_momentum[a];
+      }
+    }
+    ensureWorkspace(B, S);
+    ClosedLoopResult out;
+    out.batch = B;
+    out.ticks = ticks;
+    out.plant.assign(static_cast<size_t>(B) * (ticks + 1) * 9, 0.0);
+    out.iters.assign(static_cast<size_t>(B) * ticks, 0);
+    ccc_ddp_centroidal_loop_t lp{};
+    lp.horizon_steps = N;
+    lp.batch = B;
+    lp.n_sched = S;
+    lp.m_max = M;
+    lp.dt = dt_;
+    lp.mass = mass_;
+    lp.sim_dt = sim_dt;
+    lp.ticks = ticks;
+    lp.stride = stride;
+    lp.grid_len = G;
+    lp.max_iter_later = max_iter_later;
+    lp.sched_id = sched_id.data();
+    lp.m = m.data();
+    lp.ridge = ridge.data();
+    lp.vertex = vertex.data();
+    lp.ref_pos = ref.data();
+    for(int a = 0; a < 3; a++)
+    {
+      lp.w_run[a] = weight_param_.running_pos[a];
+      lp.w_run[3 + a] = weight_param_.running_linear_momentum[a];
+      lp.w_run[6 + a] = weight_param_.running_angular_momentum[a];
+      lp.w_term[a] = weight_param_.terminal_pos[a];
+      lp.w_term[3 + a] = weight_param_.terminal_linear_momentum[a];
+      lp.w_term[6 + a] = weight_param_.terminal_angular_momentum[a];
+      lp.disturb_vel[a] = disturb_vel[a];
+    }
+    lp.w_run[9] = weight_param_.running_force;
+    lp.u_lo = force_scale_limits_[0];
+    lp.u_hi = force_scale_limits_[1];
+    lp.plant0 = plant0.data();
+    lp.disturb_tick = disturb_tick;
+    ccc_ddp_centroidal_loop_result_t rs{};
+    rs.plant = out.plant.data();
+    rs.iters = out.iters.data();
+    const int rc = ccc_ddp_centroidal_closed_loop(ws_, &lp, &config_, &rs, CCC_MEM_HOST, nullptr);
+    if(rc != CCC_OK) throw std::runtime_error(std::string("ccc_ddp_centroidal_closed_loop: ") + ccc_last_error());
+    return out;
   }
 
   /** ddp_solver_->config() of the reference (max_iter, lambdas, ...). */

@@ -125,8 +125,10 @@ int main()
   std::vector<double> durations;
   double t = 0;
   int first_iter = 0;
+  Vector3d sim_pos_at_600 = {0, 0, 0};
   while(t < 3.0)
   {
+    if(durations.size() == 600) sim_pos_at_600 = sim.pos;
     auto start = std::chrono::steady_clock::now();
     CCC::DdpCentroidal::InitialParam ip;
     ip.pos = sim.pos;
@@ -200,6 +202,36 @@ int main()
     }
     EXPECT_LT(worst, 1e-300); // identical bits
     std::printf("planBatch(64) vs planOnce: max |du0| = %g\n", worst);
+  }
+
+  // ---- runClosedLoopBatch: the same loop for 8 plants on the device in one call; plant 0 starts like the loop above ----
+  {
+    CCC::DdpCentroidal loop(mass, horizon_dt, horizon_steps, weight_param);
+    std::vector<CCC::DdpCentroidal::BatchItem> items(8);
+    for(int i = 0; i < 8; i++)
+    {
+      items[i].initial_param.pos = ref_data_func(0.0).pos;
+      items[i].initial_param.pos[0] += 0.002 * i;
+      items[i].initial_param.vel = {0.0, 0.005 * i, 0.0};
+    }
+    const int ticks = 600;
+    auto start = std::chrono::steady_clock::now();
+    const auto res = loop.runClosedLoopBatch({motion_param_func}, {ref_data_func}, items, 0.0, sim_dt, ticks, 1, 199, {0.05, 0.05, 0.0});
+    const double ms = 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    for(int b = 0; b < 8; b++)
+    {
+      const double * end = res.state(b, ticks);
+      const auto rd_end = ref_data_func(ticks * sim_dt);
+      EXPECT_LT(norm(sub({end[0], end[1], end[2]}, rd_end.pos)), 0.1);
+      EXPECT_LT(norm({end[3], end[4], end[5]}), 0.1);
+      EXPECT_LT(norm({end[6], end[7], end[8]}), 0.01);
+    }
+    // plant 0 against the host-driven loop above (different plant arithmetic order: compare to 1e-6)
+    EXPECT_LT(std::fabs(res.state(0, ticks)[0] - sim_pos_at_600[0]) + std::fabs(res.state(0, ticks)[1] - sim_pos_at_600[1])
+                  + std::fabs(res.state(0, ticks)[2] - sim_pos_at_600[2]),
+              1e-6);
+    std::printf("runClosedLoopBatch: 8 plants x %d cycles in %.1f ms (%.3f ms per control cycle of the batch), first cycle %d iterations\n",
+                ticks, ms, ms / ticks, res.iter(0, 0));
   }
 
   if(g_failures)
