@@ -79,18 +79,19 @@ CCC_DEV void publish(double * vb, double v, bool active)
   warp_sync();
 }
 
-/** Reload row `lane` of the symmetric matrix stored in the upper triangle (+diag) of A.  No
- *  guards: entries outside the m x m block are whatever finite values the tile holds (it is
+/** Reload row `lane` of the symmetric matrix from the full tile S (both triangles stored, row stride kLda:
+ *  16 LDS.128).  No guards: entries outside the m x m block are whatever finite values the tile holds (it is
  *  zero-filled once per solve and only ever receives finite data); they meet +0.0 in matvec32. */
-CCC_DEV void load_sym_row(double (&H)[32], const double * A, int m)
+CCC_DEV void load_sym_row(double (&H)[32], const double * S, int m)
 {
-  const int lane = lane_id();
+  const double * row = S + lane_id() * kLda;
   CCC_UNROLL
-  for(int j = 0; j < 32; j++)
+  for(int q = 0; q < 16; q++)
   {
-    if(j == 16 && m <= 16) break;
-    const int r = j < lane ? j : lane, c = j < lane ? lane : j;
-    H[j] = A[r * kLda + c];
+    if(q == 8 && m <= 16) break;
+    const d2 v = ld2(row + 2 * q);
+    H[2 * q] = v.x;
+    H[2 * q + 1] = v.y;
   }
 }
 
@@ -129,17 +130,16 @@ CCC_DEV FreeSet make_free_set(unsigned clamped, int m, int * idxbuf)
   return fs;
 }
 
-/** Gather compact row `lane` of H[free,free] from the symmetric tile (unguarded: lanes and
- *  columns >= nf pick up finite tile entries that the factorisation never lets through). */
-CCC_DEV void load_compact_row(double (&Hc)[32], const double * A, const int * idxbuf, const FreeSet & fs)
+/** Gather compact row `lane` of H[free,free] from the full symmetric tile S: row idx(lane), columns idx(c)
+ *  (unguarded: lanes and columns >= nf pick up finite tile entries that the factorisation never lets through). */
+CCC_DEV void load_compact_row(double (&Hc)[32], const double * S, const int * idxbuf, const FreeSet & fs)
 {
+  const double * row = S + fs.idx * kLda;
   CCC_UNROLL
   for(int c = 0; c < 32; c++)
   {
     if((c & 7) == 0 && c >= fs.nf && c > 0) break;
-    const int ic = idxbuf[c];
-    const int r = ic < fs.idx ? ic : fs.idx, cc = ic < fs.idx ? fs.idx : ic;
-    Hc[c] = A[r * kLda + cc];
+    Hc[c] = row[idxbuf[c]];
   }
 }
 
@@ -286,11 +286,12 @@ struct BoxQpOut
 };
 
 /** One-warp BoxQP.  H: row `lane` of the symmetric Hessian, also stored in the upper triangle
- *  (+diagonal) of the smem tile A; on return H is intact again and A's strict lower triangle
+ *  in full in the smem tile S (both triangles); on return H is intact again and A's strict lower triangle
  *  holds the compact factor of the final free block.  x (in: start point, out: solution), g,
  *  lo, hi: one value per lane.  vb: 2 * kCbStride + 32 doubles of smem (column buffers + publish
  *  vector); idxbuf: 32 ints. */
 CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
+                            const double * S,
                             double * A,
                             double * vb,
                             int * idxbuf,
@@ -389,10 +390,10 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     {
       out.clamped = clamped;
       out.fs = make_free_set(clamped, m, idxbuf);
-      load_compact_row(H, A, idxbuf, out.fs);
+      load_compact_row(H, S, idxbuf, out.fs);
       y_c = warp_shfl(gc, out.fs.idx);
       const bool ok = llt_factor_compact(H, A, vb, out.fs.nf, out.invd_c, y_c);
-      load_sym_row(H, A, m);
+      load_sym_row(H, S, m);
       if(!ok)
       {
         out.retval = -1;

@@ -166,9 +166,11 @@ struct Variants
   static const V * table(int & n)
   {
     static const V t[] = {
-        {12, 1, {ddp_solve_kernel<M, 12, 1, false>, ddp_solve_kernel<M, 12, 1, true>}}, // 12 warps/SM in one CTA, 168 registers
-        {4, 3, {ddp_solve_kernel<M, 4, 3, false>, ddp_solve_kernel<M, 4, 3, true>}}, // 12 warps/SM, 168 registers
-        {8, 1, {ddp_solve_kernel<M, 8, 1, false>, ddp_solve_kernel<M, 8, 1, true>}}, //  8 warps/SM, 255 registers
+        // 12 warps/SM (168 registers) was measured 20 % slower (spills, instruction fetch) and no longer fits the
+        // shared memory since the solver keeps a full symmetric Quu tile per warp (profiles/r01_summary.md)
+        {6, 1, {ddp_solve_kernel<M, 6, 1, false>, ddp_solve_kernel<M, 6, 1, true>}}, //  6 warps/SM in one CTA
+        {4, 2, {ddp_solve_kernel<M, 4, 2, false>, ddp_solve_kernel<M, 4, 2, true>}}, //  8 warps/SM in two CTAs
+        {8, 1, {ddp_solve_kernel<M, 8, 1, false>, ddp_solve_kernel<M, 8, 1, true>}}, //  8 warps/SM, 255 registers (default)
     };
     n = 3;
     return t;

@@ -87,7 +87,7 @@ struct SmLayout
 {
   static constexpr int NN = NX * NX + ((NX * NX) & 1);         // NX x NX matrix, even-padded
   static constexpr int NV = NX + (NX & 1);                      // NX vector, even-padded
-  static constexpr int A = 0;                                   // 32 x kLda tile: upper+diag = Quu_F, strict lower = compact L
+  static constexpr int A = 0;                                   // 32 x kLda tile: strict lower = compact L (L D L' of the free block)
   static constexpr int VB = A + 32 * kLda;                      // BoxQP column buffers (2 * kCbStride) + publish vector (32)
   static constexpr int IDX = VB + 2 * kCbStride + 32;           // 32 ints: free list of the compact factor
   static constexpr int VXX = IDX + 16;
@@ -98,7 +98,9 @@ struct SmLayout
   static constexpr int S2 = QXX + NN;                           // scratch NX x NX
   static constexpr int QX = S2 + NN;
   static constexpr int QUXR = QX + NV;                          // [32][NXP] Qux rows (parked here across BoxQP: registers)
-  static constexpr int TOTAL = QUXR + 32 * NXP;
+  static constexpr int SYM = QUXR + 32 * NXP;                   // 32 x kLda tile: Quu_F in full (both triangles), rows 16-byte aligned
+  static constexpr int TOTAL = SYM + 32 * kLda;
+  static_assert(SYM % 2 == 0 && TOTAL % 2 == 0, "16-byte alignment of the tile rows and of the next warp's slice");
   // aliases inside A (+ the start of VB), valid while no factor is alive
   static constexpr int WT = A;                                  // [32][6]  the 6 live rows of Vxx*Fu, transposed
   static constexpr int KB = A;                                  // [32][NXP] K rows
@@ -386,14 +388,23 @@ struct DdpWarp
     for(int j = 0; j < 32; j++) quu_diag = (j == lane) ? H[j] : quu_diag;
     warp_sync(); // everyone is done reading WT (aliases A)
     double * A = s + sm::A;
+    double * S = s + sm::SYM;
+    // the lower triangle is the definition (oracle); it is written in row form and mirrored in column form, so that
+    // every later reload of a row (after each factorisation, which borrows the registers) is 16 aligned LDS.128 and
+    // the compact gather a plain indexed read of one row
     CCC_UNROLL
     for(int j = 0; j < 32; j++)
     {
       if(j == 16 && m <= 16) break;
-      if(active && j <= lane) A[j * kLda + lane] = (j == lane) ? quu_diag + lambda : H[j];
+      if(active && j <= lane)
+      {
+        const double v = (j == lane) ? quu_diag + lambda : H[j];
+        S[lane * kLda + j] = v;
+        S[j * kLda + lane] = v;
+      }
     }
     warp_sync();
-    load_sym_row(H, A, m);
+    load_sym_row(H, S, m);
 
     // gains
     double kk = 0.0;
@@ -409,7 +420,7 @@ struct DdpWarp
         x0 = active ? gain(k)[lane] : 0.0;
       else
         x0 = (m_next == m) ? k_next : 0.0;
-      BoxQpOut r = boxqp_warp(H, A, s + sm::VB, idxbuf, Qu, lo, hi, x0, m, P.cfg.boxqp);
+      BoxQpOut r = boxqp_warp(H, S, A, s + sm::VB, idxbuf, Qu, lo, hi, x0, m, P.cfg.boxqp);
       if(r.retval < 1) return false;
       kk = active ? x0 : 0.0;
       clamped = r.clamped;
@@ -438,10 +449,10 @@ struct DdpWarp
     {
       FreeSet fs = make_free_set(0u, m, idxbuf);
       double invd_c = 1.0;
-      load_compact_row(H, A, idxbuf, fs);
+      load_compact_row(H, S, idxbuf, fs);
       double dummy = 0.0;
       const bool ok = llt_factor_compact(H, A, s + sm::VB, fs.nf, invd_c, dummy);
-      load_sym_row(H, A, m);
+      load_sym_row(H, S, m);
       if(!ok) return false;
       double r1[NX + 1];
       r1[0] = Qu;
@@ -652,6 +663,8 @@ struct DdpWarp
     M::init_Fx(*this);
     CCC_NOUNROLL
     for(int e = lane; e < sm::IDX - sm::A; e += 32) s[sm::A + e] = 0.0;
+    CCC_NOUNROLL
+    for(int e = lane; e < 32 * kLda; e += 32) s[sm::SYM + e] = 0.0;
     int rv = 0, iter = 0, a = -1;
     bool need_rollout = true;
     if(!resume)

@@ -163,7 +163,7 @@ class DdpCentroidalEngine(_DdpEngineBase):
 
     @staticmethod
     def set_variant(v):
-        """Tuning hook: launch shape of the solve kernel (0: 12 warps/SM in one CTA, 1: 12 in three CTAs, 2: 8 = default)."""
+        """Tuning hook: launch shape of the solve kernel (0: 6 warps/SM, 1: 8 warps/SM as two CTAs, 2: 8 warps/SM in one CTA = default)."""
         return int(lib().ccc_ddp_centroidal_set_variant(int(v)))
 
     @staticmethod
