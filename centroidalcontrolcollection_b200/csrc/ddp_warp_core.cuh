@@ -339,6 +339,7 @@ struct DdpWarp
     }
     // W = Vxx Fu, rows R0..R0+5, published transposed: WT[lane][0..5]
     double * WT = s + sm::WT;
+    double quu_diag; // Quu(lane, lane) = luu + Fu' (Vxx Fu) of this lane: from the registers, no 32-way select
     {
       double w[6];
       CCC_UNROLL
@@ -351,6 +352,10 @@ struct DdpWarp
       }
       CCC_UNROLL
       for(int r = 0; r < 6; r++) WT[lane * 6 + r] = w[r];
+      double acc = 0.0;
+      CCC_UNROLL
+      for(int r = 0; r < 6; r++) acc = dfma(Fu[r], w[r], acc);
+      quu_diag = M::luu(*this) + acc;
     }
     // Qux row of this lane: Fu' (Vxx Fx), parked in shared memory until the gain solve and the
     // cost-to-go update need it (rows of inactive lanes are +0.0)
@@ -365,7 +370,6 @@ struct DdpWarp
     }
     warp_sync();
     // Quu row (lower triangle is the definition; mirrored through A's upper triangle)
-    const double luu = M::luu(*this);
     double H[32];
     CCC_UNROLL
     for(int j = 0; j < 32; j++) H[j] = 0.0;
@@ -381,11 +385,8 @@ struct DdpWarp
         acc = dfma(Fu[2 * r], w.x, acc);
         acc = dfma(Fu[2 * r + 1], w.y, acc);
       }
-      H[j] = (j == lane ? luu : 0.0) + acc;
+      H[j] = 0.0 + acc; // off-diagonal entries (the diagonal is quu_diag above)
     }
-    double quu_diag = 0.0;
-    CCC_UNROLL
-    for(int j = 0; j < 32; j++) quu_diag = (j == lane) ? H[j] : quu_diag;
     warp_sync(); // everyone is done reading WT (aliases A)
     double * A = s + sm::A;
     double * S = s + sm::SYM;
@@ -393,16 +394,16 @@ struct DdpWarp
     // every later reload of a row (after each factorisation, which borrows the registers) is 16 aligned LDS.128 and
     // the compact gather a plain indexed read of one row
     CCC_UNROLL
-    for(int j = 0; j < 32; j++)
+    for(int j = 0; j < 31; j++)
     {
       if(j == 16 && m <= 16) break;
-      if(active && j <= lane)
+      if(active && j < lane)
       {
-        const double v = (j == lane) ? quu_diag + lambda : H[j];
-        S[lane * kLda + j] = v;
-        S[j * kLda + lane] = v;
+        S[lane * kLda + j] = H[j];
+        S[j * kLda + lane] = H[j];
       }
     }
+    if(active) S[lane * kLda + lane] = quu_diag + lambda;
     warp_sync();
     load_sym_row(H, S, m);
 
@@ -479,8 +480,11 @@ struct DdpWarp
     }
 
     // ---- cost-to-go update with the unregularised Quu ------------------------------------
-    CCC_UNROLL
-    for(int j = 0; j < 32; j++) H[j] = (j == lane) ? quu_diag : H[j]; // selects, not a branch tree
+    // the unregularised diagonal goes into the tile and the row is reloaded (17 instructions instead of a 32-way select)
+    warp_sync();
+    if(active) S[lane * kLda + lane] = quu_diag;
+    warp_sync();
+    load_sym_row(H, S, m);
     double * VB0 = s + sm::VB0;
     double * VB1 = s + sm::VB1;
     double * VB2 = s + sm::VB2;
