@@ -138,13 +138,14 @@ struct DdpWarp
   CCC_DEV const double * stage_tab(int k) const { return P.tab + ((size_t)sched * P.tab_len + entry(k)) * (32 * M::TAB_ROWS); }
   CCC_DEV const double * ref(int k) const { return P.ref + ((size_t)sched * P.ref_len + entry(k)) * NREF; }
 
-  /** lanes 0..NX-1 store the (warp-uniform) state vector: select chain, one predicated store. */
+  /** Lane 0 stores the (warp-uniform) state vector: NX independent stores instead of an NX-deep select chain. */
   CCC_DEV void storeX(double * dst, const double (&x)[NX]) const
   {
-    double v = x[0];
-    CCC_UNROLL
-    for(int i = 1; i < NX; i++) v = (lane == i) ? x[i] : v;
-    if(lane < NX) dst[lane] = v;
+    if(lane == 0)
+    {
+      CCC_UNROLL
+      for(int i = 0; i < NX; i++) dst[i] = x[i];
+    }
   }
 
   /** sum_a w[a] (x[a] - r[a])^2 over the referenced states, then sum_a w[a] x[a]^2 over the rest
@@ -529,43 +530,48 @@ struct DdpWarp
     double * Vxw = s + sm::VX;
     double * Vxxw = s + sm::VXX;
     double * S2 = s + sm::S2;
-    if(lane < NX)
-    {
-      double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      CCC_NOUNROLL
-      for(int j = 0; j < m; j++)
-      {
-        const double kj = KB[j * NXP + lane];
-        a1 = dfma(kj, VB1[j], a1);
-        a2 = dfma(kj, VB2[j], a2);
-        a3 = dfma(QB[j * NXP + lane], VB0[j], a3);
-      }
-      Vxw[lane] = ((Qx[lane] + a1) + a2) + a3;
-    }
+    // One pass over the inputs j feeds all the sums of this lane at once: K'(Quu k), K'Qu, Qux'k for Vx (lanes < NX)
+    // and the (K'QuuK, K'Qux) pair of each of its NQ entries of Vxx — 3 + 2 NQ independent fma chains instead of
+    // four loops with two or three chains each (same sums, same order within each chain).
     constexpr int NQ = (NX * NX + 31) / 32;
     double s1v[NQ], s2v[NQ];
+    int ka[NQ], kc[NQ];
     CCC_UNROLL
     for(int q = 0; q < NQ; q++)
     {
       const int e = lane + 32 * q;
+      const int ee = e < NX * NX ? e : 0; // lanes past the last entry repeat entry 0 and drop the result
+      ka[q] = ee / NX;
+      kc[q] = ee - NX * ka[q];
       s1v[q] = 0.0;
       s2v[q] = 0.0;
-      if(e < NX * NX)
-      {
-        const int a = e / NX, c = e - NX * a;
-        double s1 = 0.0, s2 = 0.0;
-        CCC_NOUNROLL
-        for(int j = 0; j < m; j++)
-        {
-          const double kj = KB[j * NXP + a];
-          s1 = dfma(kj, ZB[j * NXP + c], s1);
-          s2 = dfma(kj, QB[j * NXP + c], s2);
-        }
-        s1v[q] = s1;
-        s2v[q] = s2;
-        S2[e] = s2;
-      }
     }
+    {
+      const int lv = lane < NX ? lane : 0;
+      double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      CCC_NOUNROLL
+      for(int j = 0; j < m; j++)
+      {
+        const double * kr = KB + j * NXP;
+        const double * zr = ZB + j * NXP;
+        const double * qr = QB + j * NXP;
+        const double kj = kr[lv];
+        a1 = dfma(kj, VB1[j], a1);
+        a2 = dfma(kj, VB2[j], a2);
+        a3 = dfma(qr[lv], VB0[j], a3);
+        CCC_UNROLL
+        for(int q = 0; q < NQ; q++)
+        {
+          const double kq = kr[ka[q]];
+          s1v[q] = dfma(kq, zr[kc[q]], s1v[q]);
+          s2v[q] = dfma(kq, qr[kc[q]], s2v[q]);
+        }
+      }
+      if(lane < NX) Vxw[lane] = ((Qx[lane] + a1) + a2) + a3;
+    }
+    CCC_UNROLL
+    for(int q = 0; q < NQ; q++)
+      if(lane + 32 * q < NX * NX) S2[lane + 32 * q] = s2v[q];
     warp_sync();
     // Vn = ((Qxx + K'QuuK) + K'Qux) + Qux'K   (Qux'K = (K'Qux)' bit for bit), staged in T
     CCC_UNROLL
