@@ -278,15 +278,30 @@ struct DdpWarp
     double * T = s + sm::T;
     double * Qxx = s + sm::QXX;
     double * Qx = s + sm::QX;
-    // T = Vxx Fx
-    CCC_NOUNROLL
-    for(int e = lane; e < NX * NX; e += 32)
+    // T = Vxx Fx: the NQE entries of a lane advance together (NQE independent fma chains, not one after the other)
+    constexpr int NQE = (NX * NX + 31) / 32;
+    int ei[NQE], ej[NQE];
+    CCC_UNROLL
+    for(int q = 0; q < NQE; q++)
     {
-      const int i = e / NX, j = e - NX * i;
-      double acc = 0.0;
+      const int e = lane + 32 * q;
+      const int ee = e < NX * NX ? e : 0;
+      ei[q] = ee / NX;
+      ej[q] = ee - NX * ei[q];
+    }
+    {
+      double acc[NQE];
       CCC_UNROLL
-      for(int c = 0; c < NX; c++) acc = dfma(Vxx[i * NX + c], Fx[c * NX + j], acc);
-      T[e] = acc;
+      for(int q = 0; q < NQE; q++) acc[q] = 0.0;
+      CCC_UNROLL
+      for(int c = 0; c < NX; c++)
+      {
+        CCC_UNROLL
+        for(int q = 0; q < NQE; q++) acc[q] = dfma(Vxx[ei[q] * NX + c], Fx[c * NX + ej[q]], acc[q]);
+      }
+      CCC_UNROLL
+      for(int q = 0; q < NQE; q++)
+        if(lane + 32 * q < NX * NX) T[lane + 32 * q] = acc[q];
     }
     if(lane < NX)
     {
@@ -300,14 +315,19 @@ struct DdpWarp
     }
     warp_sync();
     // Qxx = Lxx + Fx' T
-    CCC_NOUNROLL
-    for(int e = lane; e < NX * NX; e += 32)
     {
-      const int i = e / NX, j = e - NX * i;
-      double acc = 0.0;
+      double acc[NQE];
       CCC_UNROLL
-      for(int c = 0; c < NX; c++) acc = dfma(Fx[c * NX + i], T[c * NX + j], acc);
-      Qxx[e] = (i == j ? P.w_run[i] : 0.0) + acc;
+      for(int q = 0; q < NQE; q++) acc[q] = 0.0;
+      CCC_UNROLL
+      for(int c = 0; c < NX; c++)
+      {
+        CCC_UNROLL
+        for(int q = 0; q < NQE; q++) acc[q] = dfma(Fx[c * NX + ei[q]], T[c * NX + ej[q]], acc[q]);
+      }
+      CCC_UNROLL
+      for(int q = 0; q < NQE; q++)
+        if(lane + 32 * q < NX * NX) Qxx[lane + 32 * q] = (ei[q] == ej[q] ? P.w_run[ei[q]] : 0.0) + acc[q];
     }
 
     if(m == 0)
