@@ -329,9 +329,7 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     // ---- the single objective-evaluation site:  0.5 xc'H xc + g'xc  ----
     publish(pub, xc, active);
     const double Hxc = matvec32(H, pub, m);
-    double sums[2] = {active ? xc * Hxc : 0.0, active ? xc * g : 0.0};
-    warp_sum2(sums);
-    const double objc = dfma(0.5, sums[0], sums[1]);
+    const double objc = warp_sum(active ? xc * dfma(0.5, Hxc, g) : 0.0); // one tree sum (oracle/boxqp.hpp objective)
     if(phase != 0)
     {
       const bool ls_fail = (phase == 2 && step < cfg.min_step);
@@ -407,8 +405,8 @@ CCC_DEV BoxQpOut boxqp_warp(double (&H)[32],
     }
     old_clamped = clamped;
     const bool free_i = active && !cl;
-    const double gnorm = dsqrt(warp_sum(free_i ? grad * grad : 0.0));
-    if(gnorm < cfg.grad_thre)
+    const double gnorm2 = warp_sum(free_i ? grad * grad : 0.0);
+    if(gnorm2 < cfg.grad_thre * cfg.grad_thre) // squared form of boxQP.m's norm(grad(free)) < minGrad
     {
       out.retval = 5;
       break;

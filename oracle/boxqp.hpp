@@ -151,14 +151,15 @@ struct BoxQp
 
   static double objective(const double * H, int m, const double * g, const double * x, double * Hx)
   {
-    double xHx[32], xg[32];
+    // 0.5 x'Hx + g'x as ONE tree sum of x_i (0.5 (Hx)_i + g_i): the engine's evaluation is a chain of dependent
+    // shuffle levels, and one reduction is a level shorter than two interleaved ones
+    double t[32];
     for(int i = 0; i < m; i++)
     {
       Hx[i] = dot4(H + i * m, 1, x, 1, m);
-      xHx[i] = x[i] * Hx[i];
-      xg[i] = x[i] * g[i];
+      t[i] = x[i] * std::fma(0.5, Hx[i], g[i]);
     }
-    return std::fma(0.5, tree_sum32(xHx, m), tree_sum32(xg, m));
+    return tree_sum32(t, m);
   }
 
   /** H: m x m row-major.  Returns retval. */
@@ -220,8 +221,9 @@ struct BoxQp
 
       // gradient norm over the free dimensions
       for(int i = 0; i < m; i++) tmp[i] = clamped[i] ? 0.0 : grad[i] * grad[i];
-      double gnorm = std::sqrt(tree_sum32(tmp.data(), m));
-      if(gnorm < cfg.grad_thre)
+      // boxQP.m: norm(grad(free)) < minGrad, tested on the squares (no square root on the iteration's chain)
+      double gnorm2 = tree_sum32(tmp.data(), m);
+      if(gnorm2 < cfg.grad_thre * cfg.grad_thre)
       {
         retval = 5;
         break;
