@@ -39,6 +39,16 @@ CCC_DEV d2 ld2(const double * p)
 #endif
 }
 
+CCC_DEV void st2(double * p, double x, double y)
+{
+#ifdef CCC_WARP_EMU
+  p[0] = x;
+  p[1] = y;
+#else
+  *reinterpret_cast<double2 *>(p) = make_double2(x, y);
+#endif
+}
+
 /** IEEE division (inline: an out-of-line routine far from its callers costs instruction-cache
  *  locality in the hot loops). */
 CCC_DEV double ddiv(double a, double b)
@@ -240,24 +250,39 @@ CCC_DEV double llt_fwd_compact(double rhs_c, const double * A, int nf)
   return acc;
 }
 
-/** (L D L') x = r for NR right-hand sides per lane (compact numbering). */
+/** (L D L') x = r for NR right-hand sides per lane (compact numbering).  The row that becomes final in a step is
+ *  handed to the other lanes through shared memory (NR/2 STS.128 by its owner, one warp barrier, NR/2 broadcast
+ *  LDS.128) instead of 2 NR shuffles; `xb`: 2 * (NR + NR % 2) doubles, two buffers used alternately so that one
+ *  barrier per step is enough.  Same values, same order of operations as the shuffle form. */
 template<int NR>
-CCC_DEV void llt_solve_compactN(double (&r)[NR], const double * A, int nf, double invd_c)
+CCC_DEV void llt_solve_compactN(double (&r)[NR], const double * A, double * xb, int nf, double invd_c)
 {
+  constexpr int NRP = NR + (NR & 1);
   const int lane = lane_id();
   const bool in = lane < nf;
   CCC_UNROLL
   for(int c = 0; c < NR; c++) r[c] = in ? r[c] : 0.0;
+  int flip = 0;
+  warp_sync(); // earlier users of xb are done
   CCC_NOUNROLL
   for(int j = 0; j < nf; j++)
   {
+    double * buf = xb + flip * NRP;
+    flip ^= 1;
+    if(lane == j)
+    {
+      CCC_UNROLL
+      for(int c = 0; c < NR; c += 2) st2(buf + c, r[c], c + 1 < NR ? r[c + 1] : 0.0);
+    }
+    warp_sync();
     const bool upd = in && lane > j;
     const double lij = upd ? A[lane * kLda + j] : 0.0;
     CCC_UNROLL
-    for(int c = 0; c < NR; c++)
+    for(int c = 0; c < NR; c += 2)
     {
-      const double yj = warp_shfl(r[c], j);
-      if(upd) r[c] = dfma(-lij, yj, r[c]);
+      const d2 y = ld2(buf + c);
+      if(upd) r[c] = dfma(-lij, y.x, r[c]);
+      if(c + 1 < NR && upd) r[c + 1] = dfma(-lij, y.y, r[c + 1]);
     }
   }
   CCC_UNROLL
@@ -265,15 +290,25 @@ CCC_DEV void llt_solve_compactN(double (&r)[NR], const double * A, int nf, doubl
   CCC_NOUNROLL
   for(int j = nf - 1; j >= 0; j--)
   {
+    double * buf = xb + flip * NRP;
+    flip ^= 1;
+    if(lane == j)
+    {
+      CCC_UNROLL
+      for(int c = 0; c < NR; c += 2) st2(buf + c, r[c], c + 1 < NR ? r[c + 1] : 0.0);
+    }
+    warp_sync();
     const bool upd = in && lane < j;
     const double lji = upd ? A[j * kLda + lane] : 0.0;
     CCC_UNROLL
-    for(int c = 0; c < NR; c++)
+    for(int c = 0; c < NR; c += 2)
     {
-      const double xj = warp_shfl(r[c], j);
-      if(upd) r[c] = dfma(-lji, xj, r[c]);
+      const d2 x = ld2(buf + c);
+      if(upd) r[c] = dfma(-lji, x.x, r[c]);
+      if(c + 1 < NR && upd) r[c + 1] = dfma(-lji, x.y, r[c + 1]);
     }
   }
+  warp_sync();
 }
 
 struct BoxQpOut

@@ -452,7 +452,7 @@ struct DdpWarp
         // K[free,:] = -(Quu_F[free,free])^-1 Qux[free,:] with BoxQP's factor (compact numbering)
         CCC_UNROLL
         for(int c = 0; c < NX; c++) K[c] = QUXR[r.fs.idx * NXP + c];
-        llt_solve_compactN<NX>(K, A, r.fs.nf, r.invd_c);
+        llt_solve_compactN<NX>(K, A, s + sm::VB, r.fs.nf, r.invd_c); // the BoxQP column buffers are free now
         const bool free_i = active && !((clamped >> lane) & 1u);
         CCC_UNROLL
         for(int c = 0; c < NX; c++)
@@ -480,7 +480,7 @@ struct DdpWarp
       r1[0] = Qu;
       CCC_UNROLL
       for(int c = 0; c < NX; c++) r1[1 + c] = QUXR[lane * NXP + c];
-      llt_solve_compactN<NX + 1>(r1, A, fs.nf, invd_c);
+      llt_solve_compactN<NX + 1>(r1, A, s + sm::VB, fs.nf, invd_c);
       kk = active ? -r1[0] : 0.0;
       CCC_UNROLL
       for(int c = 0; c < NX; c++) K[c] = active ? -r1[1 + c] : 0.0;
