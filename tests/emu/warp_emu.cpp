@@ -234,8 +234,7 @@ int32_t emuSolve(int N, int B, int S, int mm, const int32_t * sched_id, const in
   }
   std::vector<double> xbuf((size_t)2 * B * (N + 1) * NX, 0.0), ubuf((size_t)2 * B * N * 32, 0.0),
       gains((size_t)B * N * 32 * (1 + NX), 0.0), out_u((size_t)B * N * 32, 0.0);
-  ccc::DdpParams<M> P;
-  std::memset(&P, 0, sizeof(P));
+  ccc::DdpParams<M> P{};
   P.N = N;
   P.B = B;
   P.S = S;
@@ -347,7 +346,6 @@ extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t *
   if(n > 256 || me + mi > (n > 128 ? 1024 : 512)) return CCC_ERR_INVALID;
   std::vector<double> Lg((size_t)n * n, 0.0), invd(n), J0((size_t)n * n), At((size_t)n * (me ? me : 1)), Ct((size_t)n * mi);
   int ok_flag_buf[2] = {0, 0};
-  int & ok_flag = ok_flag_buf[0];
   ccc_emu::run_cta(ccc::kQpThreads, [&]() {
     ccc::qp_setup_cta(n, me, mi, bt->Q, bt->A, bt->C, Lg.data(), invd.data(), J0.data(), At.data(), Ct.data(), ok_flag_buf);
   });
