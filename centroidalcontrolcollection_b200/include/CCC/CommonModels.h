@@ -1,7 +1,7 @@
 /* CCC/CommonModels.h — reference include/CCC/CommonModels.h, src/CommonModels.cpp:8-17.
  * ComZmpModelJerkInput: state (CoM position, velocity, acceleration), input CoM jerk, output ZMP. */
 #pragma once
-#include "Constants.h"
+#include "Gravity.h"
 #include "StateSpaceModel.h"
 
 namespace CCC

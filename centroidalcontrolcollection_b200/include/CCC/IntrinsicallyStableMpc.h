@@ -16,7 +16,7 @@
 #include <stdexcept>
 #include <vector>
 
-#include "Constants.h"
+#include "Gravity.h"
 #include "detail/QpEngine.h"
 
 namespace CCC

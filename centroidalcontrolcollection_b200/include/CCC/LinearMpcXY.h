@@ -20,7 +20,7 @@
 #include <utility>
 #include <vector>
 
-#include "Constants.h"
+#include "Gravity.h"
 #include "Contact.h"
 #include "VariantSequentialExtension.h"
 #include "detail/QpEngine.h"

@@ -17,7 +17,7 @@
 #include <utility>
 #include <vector>
 
-#include "Constants.h"
+#include "Gravity.h"
 #include "VariantSequentialExtension.h"
 #include "detail/QpEngine.h"
 
