@@ -286,10 +286,14 @@ def run_ours(args, rank, world, local_rank):
         abytes = algorithmic_bytes_per_solve(ps)
         kernel_ms = total_ms / args.steps
         achieved = abytes * B / (kernel_ms / 1e3) / 1e9
-        traffic = None
+        traffic, util = None, None
         tp = os.path.join(ROOT, "profiles", "ddp_centroidal_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            prof = json.load(open(tp))
+            traffic = prof.get("dram_bytes_per_launch")
+            # what actually binds this kernel: issue slots and the FP64 pipe, from the ncu pass on this launch
+            util = {"issue_slots_pct": prof.get("issue_active_pct"), "fp64_pipe_pct": prof.get("fp64_pipe_active_pct"),
+                    "l2_hit_rate_pct": prof.get("l2_hit_rate_pct"), "source": "profiles/ddp_centroidal_traffic.json (ncu, same launch)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -304,7 +308,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "ccc_host::ddp_solve_kernel<ccc::CentroidalModel,8,1,true>",
-                         "algorithmic_bytes_per_solve": abytes, "kernel_ms_per_launch": kernel_ms,
+                         "algorithmic_bytes_per_solve": abytes, "kernel_ms_per_launch": kernel_ms, "measured_utilisation": util,
                          "note": "latency/FP64-issue bound serial recursion: HBM fraction is small by nature, see DESIGN.md §5"},
         }
         if not args.no_cpu_baseline and world == 1:
