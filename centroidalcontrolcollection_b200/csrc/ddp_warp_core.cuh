@@ -453,18 +453,34 @@ struct DdpWarp
         CCC_UNROLL
         for(int c = 0; c < NX; c++) K[c] = QUXR[r.fs.idx * NXP + c];
         llt_solve_compactN<NX>(K, A, s + sm::VB, r.fs.nf, r.invd_c); // the BoxQP column buffers are free now
-        const bool free_i = active && !((clamped >> lane) & 1u);
-        CCC_UNROLL
-        for(int c = 0; c < NX; c++)
-        {
-          const double v = warp_shfl(K[c], r.fs.rank);
-          K[c] = free_i ? -v : 0.0;
-        }
       }
-      else
+      // Back to the original numbering through the K staging rows of the cost-to-go update (KB aliases the factor
+      // tile, which is dead from here on): compact lane r writes -K into row idx(r), a lane that is not free zeroes
+      // its own row, then every lane reads its row back — instead of one 64-bit shuffle per column of K.
       {
+        double * KBw = s + sm::KB;
+        const bool free_i = active && !((clamped >> lane) & 1u);
+        const bool owner = clamped != active_mask && lane < r.fs.nf;
+        warp_sync();
+        if(!free_i)
+        {
+          CCC_UNROLL
+          for(int c = 0; c < NXP; c += 2) st2(KBw + lane * NXP + c, 0.0, 0.0);
+        }
+        if(owner)
+        {
+          double * row = KBw + r.fs.idx * NXP;
+          CCC_UNROLL
+          for(int c = 0; c < NXP; c += 2) st2(row + c, c < NX ? -K[c] : 0.0, c + 1 < NX ? -K[c + 1] : 0.0);
+        }
+        warp_sync();
         CCC_UNROLL
-        for(int c = 0; c < NX; c++) K[c] = 0.0;
+        for(int c = 0; c < NX; c += 2)
+        {
+          const d2 v = ld2(KBw + lane * NXP + c);
+          K[c] = v.x;
+          if(c + 1 < NX) K[c + 1] = v.y;
+        }
       }
     }
     else
@@ -484,6 +500,10 @@ struct DdpWarp
       kk = active ? -r1[0] : 0.0;
       CCC_UNROLL
       for(int c = 0; c < NX; c++) K[c] = active ? -r1[1 + c] : 0.0;
+      double * KBw = s + sm::KB; // the factor tile is dead: stage K for the cost-to-go update
+      CCC_UNROLL
+      for(int c = 0; c < NX; c++) KBw[lane * NXP + c] = K[c];
+      if(NXP > NX) KBw[lane * NXP + NX] = 0.0;
     }
     if(P.out_clamped && lane == 0) P.out_clamped[(size_t)b * N + k] = clamped;
 
@@ -513,10 +533,7 @@ struct DdpWarp
     double * KB = s + sm::KB;
     double * ZB = s + sm::ZB;
     const double * QB = QUXR;
-    VB0[lane] = kk;
-    CCC_UNROLL
-    for(int c = 0; c < NX; c++) KB[lane * NXP + c] = K[c];
-    if(NXP > NX) KB[lane * NXP + NX] = 0.0;
+    VB0[lane] = kk; // (KB was filled when the gains were formed)
     warp_sync();
     const double Quuk = matvec32(H, VB0, m);
     double Z[NX];
