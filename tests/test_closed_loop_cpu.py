@@ -2,6 +2,7 @@
 reference tolerances, and agreement with the tick-by-tick Python driver of tests/closed_loop.py (which samples the
 callbacks per cycle and steps a numpy plant) — two independent formulations of the same loop."""
 import numpy as np
+import pytest
 
 from centroidalcontrolcollection_b200 import problem
 
@@ -33,3 +34,24 @@ def test_oracle_closed_loop_batch_is_independent(oracle):
         one.set_plants([0], one.plant0[b:b + 1, 0:3], one.plant0[b:b + 1, 3:6], one.plant0[b:b + 1, 6:9])
         r1 = oracle.ddp_centroidal_closed_loop(one, cfg, n_threads=1)
         assert np.array_equal(r1.plant[0], res.plant[b]) and np.array_equal(r1.iters[0], res.iters[b])
+
+
+def test_loop_description_is_validated():
+    """horizon_dt must be an integer multiple of sim_dt; the time grid covers the last cycle's terminal stage."""
+    import pytest
+
+    from centroidalcontrolcollection_b200 import closed_loop, workloads
+
+    w_run, w_term = workloads.centroidal_weights_test()
+    with pytest.raises(ValueError):
+        closed_loop.CentroidalLoop(10, 0.03, 0.007, 5, 100.0, w_run, w_term)
+    lp = closed_loop.CentroidalLoop(10, 0.03, 0.005, 5, 100.0, w_run, w_term)
+    assert lp.stride == 6 and lp.grid_len == 5 - 1 + 10 * 6 + 1
+    assert lp.sched.m.shape == (1, lp.grid_len)
+
+
+def test_oracle_rejects_a_short_time_grid(oracle):
+    lp, _ = reference_scenario(ticks=10, batch=1, horizon_steps=20)
+    lp.grid_len -= 1  # one entry short of the last horizon's terminal stage
+    with pytest.raises(RuntimeError):
+        oracle.ddp_centroidal_closed_loop(lp, problem.ddp_centroidal_config(), n_threads=1)
