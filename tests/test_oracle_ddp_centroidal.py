@@ -116,6 +116,60 @@ def test_cold_start_converges_config3_sample(oracle):
     assert np.isfinite(res.x).all() and np.isfinite(res.cost).all()
 
 
+def test_solution_is_a_kkt_point_of_the_reference_problem(oracle):
+    """Solver-independent pin: the oracle's answer is a stationary point of the reference's box-constrained problem.
+
+    Dynamics and costs of reference src/DdpCentroidal.cpp:32-64 / :100-135 are written out in plain numpy; the
+    returned u is rolled out (must reproduce the returned x and cost), the gradient of the total cost w.r.t. every
+    input comes from a numpy adjoint sweep, and its projection on the box [u_lo, u_hi] must vanish.  Nothing here
+    shares code with oracle/."""
+    B = 8
+    ps = problem.DdpCentroidalProblemSet.from_workload(workloads.ddp_centroidal_config3(batch=B))
+    res = oracle.ddp_centroidal_solve(ps, problem.ddp_centroidal_config(), trace_len=0, n_threads=4)
+    N, dt, mass, sc = ps.N, ps.dt, ps.mass, ps.sched
+    grav = np.array([0.0, 0.0, mass * 9.80665])
+    for b in range(B):
+        s, u = ps.sched_id[b], res.u[b]
+        x = np.zeros((N + 1, 9))
+        x[0] = ps.x0[b]
+        cost = 0.0
+        for k in range(N):
+            m = sc.m[s, k]
+            r, arm = sc.ridge[s, k, :m], sc.vertex[s, k, :m] - x[k, None, 0:3]
+            force = (u[k, :m, None] * r).sum(0)
+            moment = (u[k, :m, None] * np.cross(arm, r)).sum(0)
+            e = x[k].copy()
+            e[0:3] -= sc.ref_pos[s, k]
+            cost += 0.5 * (ps.w_run[:9] * e * e).sum() + 0.5 * ps.w_run[9] * (u[k, :m] ** 2).sum()
+            x[k + 1] = x[k] + dt * np.concatenate([x[k, 3:6] / mass, force - grav, moment])
+        e = x[N].copy()
+        e[0:3] -= sc.ref_pos[s, N]
+        cost += 0.5 * (ps.w_term * e * e).sum()
+        assert np.abs(x - res.x[b]).max() < 1e-11
+        assert abs(cost - res.cost[b]) < 1e-12 * abs(cost)
+
+        costate = ps.w_term * e
+        grad = np.zeros_like(u)
+        for k in range(N - 1, -1, -1):
+            m = sc.m[s, k]
+            r, arm = sc.ridge[s, k, :m], sc.vertex[s, k, :m] - x[k, None, 0:3]
+            Fu = np.zeros((9, m))
+            Fu[3:6], Fu[6:9] = dt * r.T, dt * np.cross(arm, r).T
+            grad[k, :m] = ps.w_run[9] * u[k, :m] + Fu.T @ costate
+            f = (u[k, :m, None] * r).sum(0)
+            Fx = np.eye(9)
+            Fx[0:3, 3:6] = dt / mass * np.eye(3)
+            Fx[6:9, 0:3] = dt * np.array([[0, -f[2], f[1]], [f[2], 0, -f[0]], [-f[1], f[0], 0]])  # d(-p x f)/dp
+            e = x[k].copy()
+            e[0:3] -= sc.ref_pos[s, k]
+            costate = ps.w_run[:9] * e + Fx.T @ costate
+        proj = grad.copy()
+        proj[(u <= ps.u_lo) & (grad > 0)] = 0
+        proj[(u >= ps.u_hi) & (grad < 0)] = 0
+        assert np.abs(grad).max() > 1e-4  # the bounds are what holds the solution: the raw gradient is not small
+        assert np.abs(proj).max() < 1e-5 and np.abs(proj).max() < 1e-2 * np.abs(grad).max()
+
+
 def test_oracle_matches_golden_fixture(oracle):
     """tests/golden/ddp_centroidal_config3_b16.npz (tests/golden/make_golden.py): drift pin."""
     import os
