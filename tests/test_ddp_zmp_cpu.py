@@ -95,6 +95,49 @@ def test_closed_loop(oracle):
     assert np.linalg.norm(sim.vel) < 1e-2                    # :134
 
 
+def test_solution_is_a_stationary_point_of_the_reference_problem(oracle):
+    """Solver-independent pin: total cost of reference src/DdpZmp.cpp:8-45 written out in plain numpy, rolled out
+    from the returned inputs (must give the returned cost); its central-difference gradient w.r.t. every input is
+    two orders of magnitude or more below the gradient at the initial guess (DdpZmp has no input limits)."""
+    fm = walking_plan()
+    fm.update(1.9)
+    N, mass, dt = 20, 100.0, 0.02
+    ref_zmp = np.zeros((1, N + 1, 3))
+    for k in range(N + 1):
+        ref_zmp[0, k, :2] = fm.ref_zmp(1.9 + k * dt)
+    x0 = np.array([[0.01, 0.1, -0.02, -0.05, 1.02, 0.03], [0.0, 0.0, 0.0, 0.0, 1.0, 0.0]])
+    u_init = np.tile(np.array([0.0, 0.0, mass * G]), (2, N, 1))
+    ps = problem.DdpZmpProblemSet(ref_zmp, np.ones((1, N + 1)), [0, 0], x0, mass, dt, u_init=u_init)
+    res = oracle.ddp_zmp_solve(ps, problem.ddp_config())
+    assert (res.status == 1).all()
+    w = ps.weights
+
+    def total_cost(b, u):
+        x, c = x0[b].copy(), 0.0
+        for k in range(N):
+            rz = ref_zmp[0, k]
+            c += 0.5 * (w[0] * (x[4] - 1.0) ** 2 + w[1] * ((u[k, :2] - rz[:2]) ** 2).sum() + w[2] * (u[k, 2] - mass * G) ** 2)
+            h = mass * (x[4] - rz[2])
+            x = x + dt * np.array([x[1], (x[0] - u[k, 0]) * u[k, 2] / h, x[3], (x[2] - u[k, 1]) * u[k, 2] / h, x[5],
+                                   u[k, 2] / mass - G])
+        rz = ref_zmp[0, N]
+        return c + 0.5 * (w[3] * ((x[[0, 2]] - rz[:2]) ** 2).sum() + w[4] * (x[4] - 1.0) ** 2 + w[5] * (x[[1, 3, 5]] ** 2).sum())
+
+    def gradient(b, u):
+        g = np.zeros_like(u)
+        for k in range(N):
+            for j in range(3):
+                e = np.zeros_like(u)
+                e[k, j] = 1e-5 * max(1.0, abs(u[k, j]))
+                g[k, j] = (total_cost(b, u + e) - total_cost(b, u - e)) / (2 * e[k, j])
+        return g
+
+    for b in range(2):
+        assert abs(total_cost(b, res.u[b]) - res.cost[b]) < 1e-12 * res.cost[b]
+        g_start, g_end = np.abs(gradient(b, u_init[b])).max(), np.abs(gradient(b, res.u[b])).max()
+        assert g_start > 5e-3 and g_end < 1e-5 and g_end < 1e-2 * g_start
+
+
 def test_emulated_kernel_matches_oracle(oracle):
     fm = walking_plan()
     fm.update(1.9)

@@ -95,6 +95,62 @@ def test_state_eq_matches_plain_numpy(oracle):
     assert np.allclose(a["xn"], x + 0.03 * xdot, rtol=1e-12, atol=1e-12)
 
 
+def test_solution_is_a_kkt_point_of_the_reference_problem(oracle):
+    """Solver-independent pin: dynamics and costs of reference src/DdpSingleRigidBody.cpp:52-112 in plain numpy
+    (libm sin/cos, numpy solve for the inertia), over a horizon that spans contact A, the flight phase and contact
+    B.  The returned inputs must reproduce the returned cost, and the central-difference gradient of the total
+    cost w.r.t. every input, projected on the box [u_lo, u_hi], must vanish."""
+    N, dt, mass = 30, 0.03, 100.0
+    sched, _, _ = workloads.ddp_srb_test_schedule(N, dt, 0.9)
+    assert set(sched.m[0]) == {0, 16}
+    w_run, w_term = workloads.srb_weights_test()
+    rng = np.random.Generator(np.random.PCG64(7))
+    x0 = np.zeros((2, 12))
+    x0[:, 2] = 1.0
+    x0[1] += np.concatenate([0.02 * rng.standard_normal(3), 0.05 * rng.standard_normal(6), 0.1 * rng.standard_normal(3)])
+    ps = problem.DdpSrbProblemSet(sched, [0, 0], x0, mass, dt, w_run, w_term)
+    res = oracle.ddp_srb_solve(ps, problem.ddp_srb_config())
+    assert (res.status == 1).all()
+
+    def total_cost(x_start, U):  # U[P][N][m_max]: P input sequences rolled out side by side
+        x, c = np.tile(x_start, (U.shape[0], 1)), np.zeros(U.shape[0])
+        for k in range(N):
+            m = sched.m[0, k]
+            r, v, inertia = sched.ridge[0, k, :m], sched.vertex[0, k, :m], sched.inertia[0, k].reshape(3, 3)
+            u = U[:, k, :m]
+            e = x.copy()
+            e[:, 0:6] -= sched.ref[0, k]
+            c += 0.5 * (w_run[:12] * e * e).sum(1) + 0.5 * w_run[12] * (u * u).sum(1)
+            ca, sa, cb, sb = np.cos(x[:, 3]), np.sin(x[:, 3]), np.cos(x[:, 4]), np.sin(x[:, 4])
+            om = x[:, 9:12]
+            euler_dot = np.stack([ca * sb / cb * om[:, 0] + sb * sa / cb * om[:, 1] + om[:, 2],
+                                  -sa * om[:, 0] + ca * om[:, 1], ca / cb * om[:, 0] + sa / cb * om[:, 1]], 1)
+            moment = (u[:, :, None] * np.cross(v[None] - x[:, None, 0:3], r[None])).sum(1)
+            om_dot = np.linalg.solve(inertia, (-np.cross(om, om @ inertia.T) + moment).T).T
+            x = x + dt * np.concatenate([x[:, 6:9], euler_dot, (u @ r) / mass - np.array([0, 0, 9.80665]), om_dot], 1)
+        e = x.copy()
+        e[:, 0:6] -= sched.ref[0, N]
+        return c + 0.5 * (w_term * e * e).sum(1)
+
+    idx = [(k, j) for k in range(N) for j in range(sched.m[0, k])]
+    for b in range(2):
+        u = res.u[b]
+        cost = total_cost(x0[b], u[None])[0]
+        assert abs(cost - res.cost[b]) < 1e-12 * cost
+        up, um, h = np.tile(u, (len(idx), 1, 1)), np.tile(u, (len(idx), 1, 1)), np.zeros(len(idx))
+        for i, (k, j) in enumerate(idx):
+            h[i] = 1e-4 * max(1.0, abs(u[k, j]))
+            up[i, k, j] += h[i]
+            um[i, k, j] -= h[i]
+        grad = (total_cost(x0[b], up) - total_cost(x0[b], um)) / (2 * h)
+        at = np.array([u[k, j] for k, j in idx])
+        proj = grad.copy()
+        proj[(at <= ps.u_lo) & (grad > 0)] = 0
+        proj[(at >= ps.u_hi) & (grad < 0)] = 0
+        assert (at <= ps.u_lo).any() and np.abs(grad).max() > 1e-5
+        assert np.abs(proj).max() < 1e-6 and np.abs(proj).max() < 1e-2 * np.abs(grad).max()
+
+
 def test_plan_once_closed_loop(oracle):
     """tests/src/TestDdpSingleRigidBody.cpp:15-175 with the reference's tolerances."""
     sim, rp, ro, tick_ok, iters = run_ddp_srb_closed_loop(lambda ps, cfg: oracle.ddp_srb_solve(ps, cfg))
