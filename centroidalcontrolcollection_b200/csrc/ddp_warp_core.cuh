@@ -122,11 +122,14 @@ struct DdpWarp
   int b, sched, lane;
   int cur; // index of the nominal trajectory buffer (0/1)
   double lambda, dlambda, dV0, dV1, J;
-  double krel; // running max of |k|/(|u|+1) of the last backward pass (per lane)
+  // Per-stage accumulations of the backward pass, one quantity per lane group (warp_sum4_scattered): lanes 0-7 dV[0],
+  // lanes 8-15 dV[1], lanes 16-23 max_k ||k_k|| / (||u_k|| + 1) (nmpc_ddp's small-gradient measure), lanes 24-31 unused.
+  double acc4;
+  double krel;
 
   CCC_DEV DdpWarp(const DdpParams<M> & p, double * smem, int prob)
   : P(p), s(smem), b(prob), sched(p.sched_id[prob]), lane(lane_id()), cur(0), lambda(0), dlambda(0), dV0(0), dV1(0),
-    J(0), krel(0)
+    J(0), acc4(0), krel(0)
   {
   }
 
@@ -507,17 +510,12 @@ struct DdpWarp
     }
     if(P.out_clamped && lane == 0) P.out_clamped[(size_t)b * N + k] = clamped;
 
-    // store gains (coalesced rows) and track max |k| / (|u| + 1)
+    // store gains (coalesced rows)
     {
       double * g = gain(k);
       g[lane] = kk;
       CCC_UNROLL
       for(int c = 0; c < NX; c++) g[(1 + c) * 32 + lane] = K[c];
-      if(active)
-      {
-        double r = ddiv(dabs(kk), dabs(u) + 1.0);
-        krel = krel < r ? r : krel;
-      }
     }
 
     // ---- cost-to-go update with the unregularised Quu ------------------------------------
@@ -554,10 +552,20 @@ struct DdpWarp
       if(NX & 1) Z[NX - 1] = dfma(h, KB[j * NXP + NX - 1], Z[NX - 1]);
     }
     {
-      double dv[2] = {active ? kk * Qu : 0.0, active ? kk * Quuk : 0.0};
-      warp_sum2(dv);
-      dV0 = dV0 + dv[0];
-      dV1 = dfma(0.5, dv[1], dV1);
+      // k'Qu, k'Quu k (dV) and ||k||^2, ||u||^2 (small-gradient measure) through one scattered 4-way tree sum
+      const double v4[4] = {active ? kk * Qu : 0.0, active ? kk * Quuk : 0.0, active ? kk * kk : 0.0, active ? u * u : 0.0};
+      const double tot = warp_sum4_scattered(v4);
+      const double other = warp_shfl_xor(tot, 8); // lanes 16-23: ||u||^2
+      const int grp = lane >> 3;
+      if(grp == 0)
+        acc4 = acc4 + tot;
+      else if(grp == 1)
+        acc4 = dfma(0.5, tot, acc4);
+      else if(grp == 2)
+      {
+        const double r = ddiv(dsqrt(tot), dsqrt(other) + 1.0);
+        acc4 = acc4 < r ? r : acc4;
+      }
     }
     CCC_UNROLL
     for(int c = 0; c < NX; c++) ZB[lane * NXP + c] = active ? Z[c] : 0.0;
@@ -657,9 +665,7 @@ struct DdpWarp
       s[sm::VX + lane] = lane < NREF ? P.w_term[lane] * (xv - rr) : P.w_term[lane] * xv;
     }
     warp_sync();
-    dV0 = 0.0;
-    dV1 = 0.0;
-    krel = 0.0;
+    acc4 = 0.0;
     double k_next = 0.0;
     int m_next = -1;
     CCC_NOUNROLL
@@ -667,6 +673,9 @@ struct DdpWarp
     {
       if(!backward_stage(k, k_next, m_next)) return false;
     }
+    dV0 = warp_shfl(acc4, 0);
+    dV1 = warp_shfl(acc4, 8);
+    krel = warp_shfl(acc4, 16);
     return true;
   }
 
@@ -824,8 +833,7 @@ struct DdpWarp
         rv = -1;
         break;
       }
-      const double k_rel_norm = warp_max(krel);
-      if(k_rel_norm < P.cfg.k_rel_norm_thre && lambda < P.cfg.lambda_thre)
+      if(krel < P.cfg.k_rel_norm_thre && lambda < P.cfg.lambda_thre)
       {
         decrease_lambda();
         trace(iter, -2);

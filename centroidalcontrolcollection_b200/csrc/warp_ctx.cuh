@@ -160,6 +160,37 @@ CCC_DEV void warp_sum2(double (&v)[2])
   v[1] = up ? keep : other;
 }
 
+/** Four pairwise-tree sums by the same halving, WITHOUT the final broadcast: 6 shuffles, after which a lane holds the
+ *  total of value 2 * bit4(lane) + bit3(lane).  For per-stage accumulations whose totals are only needed at the end of
+ *  a pass (dV, the small-gradient norm): every lane group accumulates its own quantity and the pass ends with one
+ *  broadcast per quantity.  Same (16, 8, 4, 2, 1) tree and bits as warp_sum. */
+CCC_DEV double warp_sum4_scattered(const double (&v)[4])
+{
+  const int lane = lane_id();
+  double a[2];
+  {
+    const bool up = (lane & 16) != 0;
+    CCC_UNROLL
+    for(int i = 0; i < 2; i++)
+    {
+      const double send = up ? v[i] : v[2 + i];
+      const double keep = up ? v[2 + i] : v[i];
+      a[i] = keep + warp_shfl_xor(send, 16);
+    }
+  }
+  double r;
+  {
+    const bool up = (lane & 8) != 0;
+    const double send = up ? a[0] : a[1];
+    const double keep = up ? a[1] : a[0];
+    r = keep + warp_shfl_xor(send, 8);
+  }
+  r = r + warp_shfl_xor(r, 4);
+  r = r + warp_shfl_xor(r, 2);
+  r = r + warp_shfl_xor(r, 1);
+  return r;
+}
+
 /** Eight pairwise-tree sums at once by halving the value set at each butterfly level
  *  ("transpose-reduce"): level 16 exchanges 4 of the 8 values, level 8 two, level 4 one, levels
  *  2 and 1 finish the single value a lane is left with — 9 shuffles instead of 40.  Every value

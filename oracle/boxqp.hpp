@@ -49,10 +49,29 @@ struct FreeLlt
     L.assign(static_cast<size_t>(nf) * nf, 0.0);
     C.assign(static_cast<size_t>(nf) * nf, 0.0);
     invd.assign(nf, 0.0);
+    if(kTextbook)
+    {
+      // Eigen::LLT<Lower>, unblocked: L[k][k] = sqrt(pivot), column divided by it
+      for(int k = 0; k < nf; k++)
+      {
+        double acc = H[idx[k] * ld + idx[k]];
+        for(int j = 0; j < k; j++) acc = acc - L[k * nf + j] * L[k * nf + j];
+        if(!(acc > 0.0)) return false;
+        const double d = std::sqrt(acc);
+        L[k * nf + k] = d;
+        for(int i = k + 1; i < nf; i++)
+        {
+          double a = H[idx[i] * ld + idx[k]];
+          for(int j = 0; j < k; j++) a = a - L[i * nf + j] * L[k * nf + j];
+          L[i * nf + k] = a / d;
+        }
+      }
+      return true;
+    }
     for(int k = 0; k < nf; k++)
     {
       double d = H[idx[k] * ld + idx[k]];
-      for(int j = 0; j < k; j++) d = std::fma(-L[k * nf + j], C[k * nf + j], d);
+      for(int j = 0; j < k; j++) d = fmad(-L[k * nf + j], C[k * nf + j], d);
       if(!(d > 0.0)) return false;
       const double inv = 1.0 / d;
       C[k * nf + k] = d;
@@ -60,7 +79,7 @@ struct FreeLlt
       for(int i = k + 1; i < nf; i++)
       {
         double a = H[idx[i] * ld + idx[k]]; // lower triangle of H, like Eigen::LLT<Lower>
-        for(int j = 0; j < k; j++) a = std::fma(-L[i * nf + j], C[k * nf + j], a);
+        for(int j = 0; j < k; j++) a = fmad(-L[i * nf + j], C[k * nf + j], a);
         C[i * nf + k] = a;
         L[i * nf + k] = a * inv;
       }
@@ -71,17 +90,33 @@ struct FreeLlt
   /** Solve (L D L') y = b in place on a compact vector of length nf (stride sb). */
   void solve(double * b, int sb) const
   {
+    if(kTextbook)
+    {
+      for(int i = 0; i < nf; i++)
+      {
+        double acc = b[i * sb];
+        for(int j = 0; j < i; j++) acc = acc - L[i * nf + j] * b[j * sb];
+        b[i * sb] = acc / L[i * nf + i];
+      }
+      for(int i = nf - 1; i >= 0; i--)
+      {
+        double acc = b[i * sb];
+        for(int j = nf - 1; j > i; j--) acc = acc - L[j * nf + i] * b[j * sb];
+        b[i * sb] = acc / L[i * nf + i];
+      }
+      return;
+    }
     for(int i = 0; i < nf; i++)
     {
       double acc = b[i * sb];
-      for(int j = 0; j < i; j++) acc = std::fma(-L[i * nf + j], b[j * sb], acc);
+      for(int j = 0; j < i; j++) acc = fmad(-L[i * nf + j], b[j * sb], acc);
       b[i * sb] = acc;
     }
     for(int i = 0; i < nf; i++) b[i * sb] = b[i * sb] * invd[i];
     for(int i = nf - 1; i >= 0; i--)
     {
       double acc = b[i * sb];
-      for(int j = nf - 1; j > i; j--) acc = std::fma(-L[j * nf + i], b[j * sb], acc);
+      for(int j = nf - 1; j > i; j--) acc = fmad(-L[j * nf + i], b[j * sb], acc);
       b[i * sb] = acc;
     }
   }
@@ -105,7 +140,7 @@ struct DenseLlt
     for(int k = 0; k < nf; k++)
     {
       double acc = H[idx[k] * ld + idx[k]];
-      for(int j = 0; j < k; j++) acc = std::fma(-L[k * nf + j], L[k * nf + j], acc);
+      for(int j = 0; j < k; j++) acc = fmad(-L[k * nf + j], L[k * nf + j], acc);
       if(!(acc > 0.0)) return false;
       double d = std::sqrt(acc);
       double inv = 1.0 / d;
@@ -114,7 +149,7 @@ struct DenseLlt
       for(int i = k + 1; i < nf; i++)
       {
         double a = H[idx[i] * ld + idx[k]];
-        for(int j = 0; j < k; j++) a = std::fma(-L[i * nf + j], L[k * nf + j], a);
+        for(int j = 0; j < k; j++) a = fmad(-L[i * nf + j], L[k * nf + j], a);
         L[i * nf + k] = a * inv;
       }
     }
@@ -126,13 +161,13 @@ struct DenseLlt
     for(int i = 0; i < nf; i++)
     {
       double acc = b[i * sb];
-      for(int j = 0; j < i; j++) acc = std::fma(-L[i * nf + j], b[j * sb], acc);
+      for(int j = 0; j < i; j++) acc = fmad(-L[i * nf + j], b[j * sb], acc);
       b[i * sb] = acc * invd[i];
     }
     for(int i = nf - 1; i >= 0; i--)
     {
       double acc = b[i * sb];
-      for(int j = nf - 1; j > i; j--) acc = std::fma(-L[j * nf + i], b[j * sb], acc);
+      for(int j = nf - 1; j > i; j--) acc = fmad(-L[j * nf + i], b[j * sb], acc);
       b[i * sb] = acc * invd[i];
     }
   }
@@ -154,10 +189,22 @@ struct BoxQp
     // 0.5 x'Hx + g'x as ONE tree sum of x_i (0.5 (Hx)_i + g_i): the engine's evaluation is a chain of dependent
     // shuffle levels, and one reduction is a level shorter than two interleaved ones
     double t[32];
+    if(kTextbook)
+    {
+      // x.dot(g) + 0.5 * x.dot(H * x)
+      double xg = 0.0, xHx = 0.0;
+      for(int i = 0; i < m; i++)
+      {
+        Hx[i] = dot4(H + i * m, 1, x, 1, m);
+        xg = xg + x[i] * g[i];
+        xHx = xHx + x[i] * Hx[i];
+      }
+      return xg + 0.5 * xHx;
+    }
     for(int i = 0; i < m; i++)
     {
       Hx[i] = dot4(H + i * m, 1, x, 1, m);
-      t[i] = x[i] * std::fma(0.5, Hx[i], g[i]);
+      t[i] = x[i] * fmad(0.5, Hx[i], g[i]);
     }
     return tree_sum32(t, m);
   }
@@ -223,7 +270,7 @@ struct BoxQp
       for(int i = 0; i < m; i++) tmp[i] = clamped[i] ? 0.0 : grad[i] * grad[i];
       // boxQP.m: norm(grad(free)) < minGrad, tested on the squares (no square root on the iteration's chain)
       double gnorm2 = tree_sum32(tmp.data(), m);
-      if(gnorm2 < cfg.grad_thre * cfg.grad_thre)
+      if(kTextbook ? std::sqrt(gnorm2) < cfg.grad_thre : gnorm2 < cfg.grad_thre * cfg.grad_thre)
       {
         retval = 5;
         break;
@@ -244,7 +291,7 @@ struct BoxQp
       // descent check
       for(int i = 0; i < m; i++) tmp[i] = search[i] * grad[i];
       double sdotg = tree_sum32(tmp.data(), m);
-      if(sdotg >= 0) // should not happen
+      if(choice(kChoiceDescentTol) ? sdotg > 1e-10 : sdotg >= 0) // should not happen
       {
         retval = 0;
         break;
@@ -252,17 +299,21 @@ struct BoxQp
 
       // Armijo line search
       double step = 1.0;
-      for(int i = 0; i < m; i++) xc[i] = clampd(std::fma(step, search[i], x[i]), lo[i], hi[i]);
+      for(int i = 0; i < m; i++) xc[i] = clampd(fmad(step, search[i], x[i]), lo[i], hi[i]);
       double objc = objective(H, m, g, xc.data(), Hxc.data());
       bool ls_fail = false;
       // boxQP.m: while (vc - oldvalue) / (step * sdotg) < Armijo.  step * sdotg < 0 here, so the ratio
       // test is evaluated cross-multiplied (no division in the backtracking loop); the two forms differ
       // only if the ratio is within rounding of the threshold
-      while((objc - old_obj) > cfg.armijo * (step * sdotg))
+      auto armijo_fails = [&]() {
+        if(kTextbook) return (objc - old_obj) / (step * sdotg) < cfg.armijo;
+        return (objc - old_obj) > cfg.armijo * (step * sdotg);
+      };
+      while(armijo_fails())
       {
         step = step * cfg.step_factor;
         ls_steps++;
-        for(int i = 0; i < m; i++) xc[i] = clampd(std::fma(step, search[i], x[i]), lo[i], hi[i]);
+        for(int i = 0; i < m; i++) xc[i] = clampd(fmad(step, search[i], x[i]), lo[i], hi[i]);
         objc = objective(H, m, g, xc.data(), Hxc.data());
         if(step < cfg.min_step)
         {

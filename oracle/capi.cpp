@@ -257,17 +257,17 @@ int32_t ccc_oracle_ddp_centroidal_closed_loop(const ccc_ddp_centroidal_loop_t * 
         cross3(d, rho, cr);
         for(int a = 0; a < 3; a++)
         {
-          f[a] = std::fma(uj, rho[a], f[a]);
-          n[a] = std::fma(uj, cr[a], n[a]);
+          f[a] = fmad(uj, rho[a], f[a]);
+          n[a] = fmad(uj, cr[a], n[a]);
         }
       }
       const double sim_dt = lp->sim_dt, half_dt2 = 0.5 * (sim_dt * sim_dt);
       for(int a = 0; a < 3; a++)
       {
         const double acc = f[a] / lp->mass + (a == 2 ? -9.80665 : 0.0);
-        pos[a] = std::fma(half_dt2, acc, std::fma(sim_dt, vel[a], pos[a]));
-        vel[a] = std::fma(sim_dt, acc, vel[a]);
-        L[a] = std::fma(sim_dt, n[a], L[a]);
+        pos[a] = fmad(half_dt2, acc, fmad(sim_dt, vel[a], pos[a]));
+        vel[a] = fmad(sim_dt, acc, vel[a]);
+        L[a] = fmad(sim_dt, n[a], L[a]);
         if(tick == lp->disturb_tick) vel[a] = vel[a] + lp->disturb_vel[a];
       }
       double * lg = log + static_cast<size_t>(tick + 1) * 9;
@@ -523,11 +523,11 @@ int32_t ccc_oracle_preview_input(int32_t batch, int32_t N, const double * K, con
     for(int l = 0; l < 32; l++)
     {
       double acc = 0.0;
-      for(int i = l; i < N; i += 32) acc = std::fma(F[i], ref_seq[static_cast<size_t>(b) * N + i], acc);
+      for(int i = l; i < N; i += 32) acc = fmad(F[i], ref_seq[static_cast<size_t>(b) * N + i], acc);
       part[l] = acc;
     }
     double kx = 0.0;
-    for(int i = 0; i < 3; i++) kx = std::fma(K[i], x[static_cast<size_t>(b) * 3 + i], kx);
+    for(int i = 0; i < 3; i++) kx = fmad(K[i], x[static_cast<size_t>(b) * 3 + i], kx);
     u[b] = (-kx) + tree_sum32(part, 32);
   }
   return CCC_OK;
@@ -537,6 +537,19 @@ int32_t ccc_oracle_preview_input(int32_t batch, int32_t N, const double * K, con
 void ccc_oracle_sincos(double x, double * s, double * c)
 {
   sincos_canon(x, s, c);
+}
+
+/** Select the unpinned algorithmic alternatives (num.hpp `Choice` bits; 0 = the oracle's definition).  Process-wide;
+ *  used by tools/srb_robustness.py and tests/test_oracle_textbook.py only. */
+void ccc_oracle_set_choices(uint32_t bits)
+{
+  choiceBits() = bits;
+}
+
+/** 1 for libccc_oracle_textbook.so (-DORACLE_TEXTBOOK), 0 for the canonical build. */
+int32_t ccc_oracle_is_textbook(void)
+{
+  return kTextbook ? 1 : 0;
 }
 
 int32_t ccc_oracle_hardware_threads(void)

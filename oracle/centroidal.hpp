@@ -61,12 +61,12 @@ struct CentroidalProblem : public DdpProblem
     const double inv_mass = 1 / mass;
     for(int a = 0; a < 3; a++)
     {
-      xdot[a] = x[3 + a] * inv_mass;
+      xdot[a] = kTextbook ? x[3 + a] / mass : x[3 + a] * inv_mass; // reference :44 divides
       xdot[3 + a] = f[a];
       xdot[6 + a] = n[a];
     }
     xdot[5] = f[2] + (-1 * mass * kGravity);
-    for(int i = 0; i < 9; i++) xn[i] = std::fma(dt, xdot[i], x[i]);
+    for(int i = 0; i < 9; i++) xn[i] = fmad(dt, xdot[i], x[i]);
   }
 
   static double quad9(const double * w, const double * x, const double * ref)
@@ -75,9 +75,9 @@ struct CentroidalProblem : public DdpProblem
     for(int a = 0; a < 3; a++)
     {
       double d = x[a] - ref[a];
-      c = std::fma(w[a], d * d, c);
+      c = fmad(w[a], d * d, c);
     }
-    for(int a = 3; a < 9; a++) c = std::fma(w[a], x[a] * x[a], c);
+    for(int a = 3; a < 9; a++) c = fmad(w[a], x[a] * x[a], c);
     return c;
   }
 
@@ -87,7 +87,7 @@ struct CentroidalProblem : public DdpProblem
     double usq[32];
     for(int j = 0; j < m; j++) usq[j] = u[j] * u[j];
     double c = quad9(w_run, x, ref_pos + 3 * k);
-    return std::fma(0.5 * w_run[9], tree_sum32(usq, m), 0.5 * c);
+    return fmad(0.5 * w_run[9], tree_sum32(usq, m), 0.5 * c);
   }
 
   double terminalCost(const double * x) const override { return 0.5 * quad9(w_term, x, ref_pos + 3 * N); }

@@ -195,10 +195,28 @@ struct DdpSolver
     }
 
     // termination on small gradient
+    // nmpc_ddp: max over the stages of k_list[i].norm() / (u_list[i].norm() + 1); the squared norms are
+    // summed with the fixed 32-leaf tree like every other reduction over the input index
     double k_rel_norm = 0;
     for(int k = 0; k < N; k++)
-      for(size_t j = 0; j < k_list[k].size(); j++)
-        k_rel_norm = std::max(k_rel_norm, std::fabs(k_list[k][j]) / (std::fabs(u[k][j]) + 1.0));
+    {
+      const size_t m = k_list[k].size();
+      if(choice(kChoiceKRelElementwise))
+      {
+        for(size_t j = 0; j < m; j++)
+          k_rel_norm = std::max(k_rel_norm, std::fabs(k_list[k][j]) / (std::fabs(u[k][j]) + 1.0));
+        continue;
+      }
+      double kk2[32], uu2[32];
+      for(size_t j = 0; j < m; j++)
+      {
+        kk2[j] = k_list[k][j] * k_list[k][j];
+        uu2[j] = u[k][j] * u[k][j];
+      }
+      const double kn = std::sqrt(tree_sum32(kk2, static_cast<int>(m)));
+      const double un = std::sqrt(tree_sum32(uu2, static_cast<int>(m)));
+      k_rel_norm = std::max(k_rel_norm, kn / (un + 1.0));
+    }
     tr.k_rel_norm = k_rel_norm;
     if(k_rel_norm < cfg.k_rel_norm_thre && lambda < cfg.lambda_thre)
     {
@@ -217,7 +235,7 @@ struct DdpSolver
       double alpha = cfg.alpha_list[a];
       forwardPass(alpha);
       actual = J - sum_seq(costc);
-      expected = -(alpha * std::fma(alpha, dV[1], dV[0]));
+      expected = -(alpha * fmad(alpha, dV[1], dV[0]));
       double ratio;
       if(expected > 0)
         ratio = actual / expected;
@@ -309,8 +327,9 @@ struct DdpSolver
             hi[j] = hi[j] - u[k][j];
           }
           // warm start from the gain of the next stage (iLQG.m: k(:,min(i+1,N-1)))
-          const std::vector<double> & kn = k_list[std::min(k + 1, N - 1)];
-          if(static_cast<int>(kn.size()) == m) k0 = kn;
+          const std::vector<double> & kn =
+              choice(kChoiceBoxQpWarmSameStage) ? k_list[k] : k_list[std::min(k + 1, N - 1)];
+          if(static_cast<int>(kn.size()) == m && !choice(kChoiceBoxQpColdStart)) k0 = kn;
           BoxQp qp;
           qp.cfg = cfg.boxqp;
           int r = qp.solve(QuuF.data(), Qu.data(), lo.data(), hi.data(), k0.data(), m);
@@ -364,6 +383,7 @@ struct DdpSolver
       clamped_mask[k] = mask;
 
       // cost-to-go update (unregularised Quu)
+      if(choice(kChoiceVxxRegularised)) Quu = QuuF;
       std::vector<double> Quuk(m), QuuK(m * nx), t1(m), t2(m);
       for(int i = 0; i < m; i++)
       {
@@ -373,7 +393,7 @@ struct DdpSolver
         t2[i] = kk[i] * Quuk[i];
       }
       dV[0] = dV[0] + tree_sum32(t1.data(), m);
-      dV[1] = std::fma(0.5, tree_sum32(t2.data(), m), dV[1]);
+      dV[1] = fmad(0.5, tree_sum32(t2.data(), m), dV[1]);
 
       for(int c = 0; c < nx; c++)
       {
@@ -415,7 +435,7 @@ struct DdpSolver
       for(int j = 0; j < m; j++)
       {
         double fb = dot_seq(K_list[k].data() + j * nx, 1, dx.data(), 1, nx);
-        double v = std::fma(alpha, k_list[k][j], u[k][j]) + fb;
+        double v = fmad(alpha, k_list[k][j], u[k][j]) + fb;
         if(cfg.with_input_constraint) v = clampd(v, lo[j], hi[j]);
         uc[k][j] = v;
       }

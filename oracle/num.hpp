@@ -25,11 +25,55 @@ namespace oracle
 {
 constexpr double kGravity = 9.80665; // reference include/CCC/Constants.h:10
 
+// ---- arithmetic variant (compile time) -------------------------------------------------------
+// The default build is the CANONICAL arithmetic above, the one the engine reproduces bit for bit.
+// -DORACLE_TEXTBOOK builds the same algorithm in the arithmetic a straightforward Eigen/libm
+// program would use (libccc_oracle_textbook.so): no fused multiply-add, plain left-to-right sums,
+// Cholesky with square roots and divisions (Eigen::LLT), divided Armijo ratio, two-term BoxQP
+// objective, gradient norm with its square root, P / m as a division, libm sin/cos, sequential
+// Givens sweep in the QP.  tests/test_oracle_textbook.py compares the two builds: every place where
+// the canonical form departs from the textbook one for the engine's sake is covered by that test.
+#ifdef ORACLE_TEXTBOOK
+constexpr bool kTextbook = true;
+#else
+constexpr bool kTextbook = false;
+#endif
+
+// ---- algorithmic choices that nmpc_ddp's source would pin (run time, study only) ------------------
+// nmpc_ddp is not under /root/reference; where the recollection of its source leaves a choice open,
+// the oracle's default is the recalled form and the alternative is selectable here so that
+// tools/srb_robustness.py can measure what each choice does to the reference's closed-loop tests.
+enum Choice : uint32_t
+{
+  kChoiceKRelElementwise = 1u << 0, // small-gradient test on max_ij |k_ij| / (|u_ij| + 1) (iLQG.m) instead of
+                                    // max_i ||k_i|| / (||u_i|| + 1) (nmpc_ddp)
+  kChoiceBoxQpColdStart = 1u << 1,  // BoxQP starts from 0 instead of the gain of the next stage
+  kChoiceVxxRegularised = 1u << 2,  // dV / Vx / Vxx built with Quu + lambda I instead of Quu
+  kChoiceDescentTol = 1u << 3,      // BoxQP 'no descent' test: s'g > 1e-10 instead of s'g >= 0
+  kChoiceBoxQpWarmSameStage = 1u << 4, // BoxQP starts from this stage's gain of the previous backward pass
+};
+inline uint32_t & choiceBits()
+{
+  static uint32_t bits = 0;
+  return bits;
+}
+inline bool choice(uint32_t c)
+{
+  return (choiceBits() & c) != 0;
+}
+
+/** a * b + c: one rounding (IEEE fma) in the canonical build, two in the textbook build. */
+inline double fmad(double a, double b, double c)
+{
+  if(kTextbook) return a * b + c;
+  return std::fma(a, b, c);
+}
+
 /** Sequential fma chain: sum_i a[i*sa] * b[i*sb], ascending i, starting from +0.0. */
 inline double dot_seq(const double * a, int sa, const double * b, int sb, int n)
 {
   double acc = 0.0;
-  for(int i = 0; i < n; i++) acc = std::fma(a[i * sa], b[i * sb], acc);
+  for(int i = 0; i < n; i++) acc = fmad(a[i * sa], b[i * sb], acc);
   return acc;
 }
 
@@ -38,14 +82,21 @@ inline double dot_seq(const double * a, int sa, const double * b, int sb, int n)
  *  (H x in BoxQP, Quu k in the backward pass): the usual 4-way unrolled dot product. */
 inline double dot4(const double * a, int sa, const double * b, int sb, int n)
 {
+  if(kTextbook) return dot_seq(a, sa, b, sb, n);
   double s[4] = {0.0, 0.0, 0.0, 0.0};
-  for(int i = 0; i < n; i++) s[i & 3] = std::fma(a[i * sa], b[i * sb], s[i & 3]);
+  for(int i = 0; i < n; i++) s[i & 3] = fmad(a[i * sa], b[i * sb], s[i & 3]);
   return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 /** Pairwise tree over 32 zero-padded leaves: level strides 16, 8, 4, 2, 1. */
 inline double tree_sum32(const double * p, int m)
 {
+  if(kTextbook)
+  {
+    double acc = 0.0;
+    for(int i = 0; i < m; i++) acc = acc + p[i];
+    return acc;
+  }
   double t[32];
   for(int i = 0; i < 32; i++) t[i] = i < m ? p[i] : 0.0;
   for(int off = 16; off >= 1; off >>= 1)
@@ -56,9 +107,16 @@ inline double tree_sum32(const double * p, int m)
 /** Cross product with one rounded product and one fma per component. */
 inline void cross3(const double * a, const double * b, double * out)
 {
-  out[0] = std::fma(a[1], b[2], -(a[2] * b[1]));
-  out[1] = std::fma(a[2], b[0], -(a[0] * b[2]));
-  out[2] = std::fma(a[0], b[1], -(a[1] * b[0]));
+  if(kTextbook)
+  {
+    out[0] = a[1] * b[2] - a[2] * b[1];
+    out[1] = a[2] * b[0] - a[0] * b[2];
+    out[2] = a[0] * b[1] - a[1] * b[0];
+    return;
+  }
+  out[0] = fmad(a[1], b[2], -(a[2] * b[1]));
+  out[1] = fmad(a[2], b[0], -(a[0] * b[2]));
+  out[2] = fmad(a[0], b[1], -(a[1] * b[0]));
 }
 
 /** sin and cos from +,-,*,fma and rint only, so that a GPU implementation of the same sequence
@@ -67,25 +125,31 @@ inline void cross3(const double * a, const double * b, double * out)
  *  [-pi/4, pi/4], quadrant fix-up.  Error vs the true value is ~1 ulp for |x| < 1e5. */
 inline void sincos_canon(double x, double * s_out, double * c_out)
 {
+  if(kTextbook)
+  {
+    *s_out = std::sin(x);
+    *c_out = std::cos(x);
+    return;
+  }
   const double j = std::nearbyint(x * 6.36619772367581382433e-01);
-  double r = std::fma(-j, 1.57079632673412561417e+00, x);
-  r = std::fma(-j, 6.07710050650619224932e-11, r);
-  r = std::fma(-j, 2.02226624879595063154e-21, r);
+  double r = fmad(-j, 1.57079632673412561417e+00, x);
+  r = fmad(-j, 6.07710050650619224932e-11, r);
+  r = fmad(-j, 2.02226624879595063154e-21, r);
   const double z = r * r;
   double ps = 1.58969099521155010221e-10;
-  ps = std::fma(ps, z, -2.50507602534068634195e-08);
-  ps = std::fma(ps, z, 2.75573137070700676789e-06);
-  ps = std::fma(ps, z, -1.98412698298579493134e-04);
-  ps = std::fma(ps, z, 8.33333333332248946124e-03);
-  ps = std::fma(ps, z, -1.66666666666666324348e-01);
-  const double sr = std::fma(r * z, ps, r);
+  ps = fmad(ps, z, -2.50507602534068634195e-08);
+  ps = fmad(ps, z, 2.75573137070700676789e-06);
+  ps = fmad(ps, z, -1.98412698298579493134e-04);
+  ps = fmad(ps, z, 8.33333333332248946124e-03);
+  ps = fmad(ps, z, -1.66666666666666324348e-01);
+  const double sr = fmad(r * z, ps, r);
   double pc = -1.13596475577881948265e-11;
-  pc = std::fma(pc, z, 2.08757232129817482790e-09);
-  pc = std::fma(pc, z, -2.75573143513906633035e-07);
-  pc = std::fma(pc, z, 2.48015872894767294178e-05);
-  pc = std::fma(pc, z, -1.38888888888741095749e-03);
-  pc = std::fma(pc, z, 4.16666666666666019037e-02);
-  const double cr = std::fma(z * z, pc, std::fma(-0.5, z, 1.0));
+  pc = fmad(pc, z, 2.08757232129817482790e-09);
+  pc = fmad(pc, z, -2.75573143513906633035e-07);
+  pc = fmad(pc, z, 2.48015872894767294178e-05);
+  pc = fmad(pc, z, -1.38888888888741095749e-03);
+  pc = fmad(pc, z, 4.16666666666666019037e-02);
+  const double cr = fmad(z * z, pc, fmad(-0.5, z, 1.0));
   const long long q = static_cast<long long>(j) & 3;
   *s_out = q == 0 ? sr : q == 1 ? cr : q == 2 ? -sr : -cr;
   *c_out = q == 0 ? cr : q == 1 ? -sr : q == 2 ? -cr : sr;

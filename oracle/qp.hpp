@@ -38,6 +38,12 @@ inline int qp_tree_leaves(int n)
 /** Pairwise tree over `leaves` zero-padded leaves: strides leaves/2, ..., 1. */
 inline double tree_sum_leaves(const double * p, int n, int leaves)
 {
+  if(kTextbook)
+  {
+    double acc = 0.0;
+    for(int i = 0; i < n; i++) acc = acc + p[i];
+    return acc;
+  }
   double t[256];
   for(int i = 0; i < leaves; i++) t[i] = i < n ? p[i] : 0.0;
   for(int off = leaves / 2; off >= 1; off >>= 1)
@@ -57,12 +63,12 @@ inline double givens_hypot(double a, double b)
   if(a1 > b1)
   {
     const double t = b1 / a1;
-    return a1 * std::sqrt(std::fma(t, t, 1.0));
+    return a1 * std::sqrt(fmad(t, t, 1.0));
   }
   if(b1 > a1)
   {
     const double t = a1 / b1;
-    return b1 * std::sqrt(std::fma(t, t, 1.0));
+    return b1 * std::sqrt(fmad(t, t, 1.0));
   }
   return a1 * std::sqrt(2.0);
 }
@@ -81,7 +87,7 @@ struct DenseQpShared
     for(int k = 0; k < n; k++)
     {
       double acc = Q[k * n + k];
-      for(int j = 0; j < k; j++) acc = std::fma(-L[k * n + j], L[k * n + j], acc);
+      for(int j = 0; j < k; j++) acc = fmad(-L[k * n + j], L[k * n + j], acc);
       if(!(acc > 0.0)) return ok = false;
       const double d = std::sqrt(acc);
       L[k * n + k] = d;
@@ -89,7 +95,7 @@ struct DenseQpShared
       for(int i = k + 1; i < n; i++)
       {
         double a = Q[i * n + k];
-        for(int j = 0; j < k; j++) a = std::fma(-L[i * n + j], L[k * n + j], a);
+        for(int j = 0; j < k; j++) a = fmad(-L[i * n + j], L[k * n + j], a);
         L[i * n + k] = a * invd[k];
       }
     }
@@ -101,7 +107,7 @@ struct DenseQpShared
       for(int r = 0; r < n; r++)
       {
         double acc = r == i ? 1.0 : 0.0;
-        for(int j = 0; j < r; j++) acc = std::fma(-L[r * n + j], z[j], acc);
+        for(int j = 0; j < r; j++) acc = fmad(-L[r * n + j], z[j], acc);
         z[r] = acc * invd[r];
       }
       for(int j = 0; j < n; j++) J[i * n + j] = z[j];
@@ -151,20 +157,20 @@ struct DenseQpSolver
     {
       double acc = 0.0;
       if(c)
-        for(int i = 0; i < n; i++) acc = std::fma(J[i * n + j], c[i], acc);
+        for(int i = 0; i < n; i++) acc = fmad(J[i * n + j], c[i], acc);
       tmp[j] = acc;
     }
     for(int i = 0; i < n; i++)
     {
       double acc = 0.0;
-      for(int j = 0; j < n; j++) acc = std::fma(J[i * n + j], tmp[j], acc);
+      for(int j = 0; j < n; j++) acc = fmad(J[i * n + j], tmp[j], acc);
       x[i] = -acc;
     }
 
     auto slack = [&](int id) {
       // n_id . x + offset  (>= 0 when satisfied; equalities: = 0)
       double acc = 0.0;
-      for(int j = 0; j < n; j++) acc = std::fma(normal(id, j), x[j], acc);
+      for(int j = 0; j < n; j++) acc = fmad(normal(id, j), x[j], acc);
       return id < me ? acc - b[id] : acc + dvec[id - me];
     };
     auto compute_dzr = [&]() {
@@ -175,8 +181,9 @@ struct DenseQpSolver
       for(int i = q - 1; i >= 0; i--)
       {
         double acc = d[i];
-        for(int j = q - 1; j > i; j--) acc = std::fma(-R[i * n + j], r[j], acc);
-        r[i] = acc * Rinv[i]; // reciprocal of the diagonal kept by add / delete: no division in the sweep
+        for(int j = q - 1; j > i; j--) acc = fmad(-R[i * n + j], r[j], acc);
+        // reciprocal of the diagonal kept by add / delete: no division in the sweep
+        r[i] = kTextbook ? acc / R[i * n + i] : acc * Rinv[i];
       }
     };
     // Givens sweep that folds d[q..n-1] into d[q] and rotates the columns of J (Goldfarb-Idnani's
@@ -187,6 +194,41 @@ struct DenseQpSolver
     // one step's parameters).  T_j is summed by a Kogge-Stone scan (fixed association, zeros are exact), the
     // sign of the running value at j is the sign of d[j] (the sweep normalises cc >= 0).
     auto add_constraint = [&]() -> bool {
+      if(kTextbook)
+      {
+        // the sweep as Goldfarb-Idnani implementations write it (QuadProg++ add_constraint): one dependent
+        // hypot / division step per column
+        for(int j = n - 1; j >= q + 1; j--)
+        {
+          double cc = d[j - 1], ss = d[j];
+          const double h = givens_hypot(cc, ss);
+          if(std::fabs(h) < eps) continue;
+          d[j] = 0.0;
+          ss = ss / h;
+          cc = cc / h;
+          if(cc < 0.0)
+          {
+            cc = -cc;
+            ss = -ss;
+            d[j - 1] = -h;
+          }
+          else
+            d[j - 1] = h;
+          const double xny = ss / (1.0 + cc);
+          for(int k = 0; k < n; k++)
+          {
+            const double t1 = J[k * n + j - 1], t2 = J[k * n + j];
+            J[k * n + j - 1] = t1 * cc + t2 * ss;
+            J[k * n + j] = xny * (t1 + J[k * n + j - 1]) - t2;
+          }
+        }
+        q++;
+        for(int i = 0; i < q; i++) R[i * n + q - 1] = d[i];
+        Rinv[q - 1] = 1.0 / d[q - 1];
+        if(std::fabs(d[q - 1]) <= eps * R_norm) return false;
+        R_norm = std::max(R_norm, std::fabs(d[q - 1]));
+        return true;
+      }
       std::vector<double> Ta(n + 1, 0.0), Tb(n + 1, 0.0), gc(n, -1.0), gs(n, 0.0), gx(n, 0.0);
       for(int j = q; j < n; j++) Ta[j] = d[j] * d[j];
       for(int off = 1; off < n - q; off <<= 1)
@@ -215,9 +257,9 @@ struct DenseQpSolver
           const double cc = gc[j];
           if(cc < 0.0) continue;
           const double t1 = J[k * n + j - 1], t2 = J[k * n + j];
-          const double a = std::fma(t2, gs[j], t1 * cc);
+          const double a = fmad(t2, gs[j], t1 * cc);
           J[k * n + j - 1] = a;
-          J[k * n + j] = std::fma(gx[j], t1 + a, -t2);
+          J[k * n + j] = fmad(gx[j], t1 + a, -t2);
         }
       d[q] = dq;
       q++;
@@ -269,16 +311,16 @@ struct DenseQpSolver
         for(int k = j + 1; k < q; k++)
         {
           const double t1 = R[j * n + k], t2 = R[(j + 1) * n + k];
-          const double a = std::fma(t2, ss, t1 * cc);
+          const double a = fmad(t2, ss, t1 * cc);
           R[j * n + k] = a;
-          R[(j + 1) * n + k] = std::fma(xny, t1 + a, -t2);
+          R[(j + 1) * n + k] = fmad(xny, t1 + a, -t2);
         }
         for(int k = 0; k < n; k++)
         {
           const double t1 = J[k * n + j], t2 = J[k * n + j + 1];
-          const double a = std::fma(t2, ss, t1 * cc);
+          const double a = fmad(t2, ss, t1 * cc);
           J[k * n + j] = a;
-          J[k * n + j + 1] = std::fma(xny, t1 + a, -t2);
+          J[k * n + j + 1] = fmad(xny, t1 + a, -t2);
         }
       }
       for(int j = qq; j < q; j++) Rinv[j] = 1.0 / R[j * n + j];
@@ -297,9 +339,9 @@ struct DenseQpSolver
       const double zz = dot_tree(z, z);
       double t2 = 0.0;
       if(std::fabs(zz) > eps) t2 = (-slack(e)) / dot_tree(z, np);
-      for(int i = 0; i < n; i++) x[i] = std::fma(t2, z[i], x[i]);
+      for(int i = 0; i < n; i++) x[i] = fmad(t2, z[i], x[i]);
       u[q] = t2;
-      for(int k = 0; k < q; k++) u[k] = std::fma(-t2, r[k], u[k]);
+      for(int k = 0; k < q; k++) u[k] = fmad(-t2, r[k], u[k]);
       A[q] = e;
       is_active[e] = 1;
       if(!add_constraint())
@@ -379,15 +421,15 @@ struct DenseQpSolver
       if(!(t2 < std::numeric_limits<double>::infinity()))
       {
         // step in dual space only, drop constraint l
-        for(int k = 0; k < q; k++) u[k] = std::fma(-t, r[k], u[k]);
+        for(int k = 0; k < q; k++) u[k] = fmad(-t, r[k], u[k]);
         u[q] = u[q] + t;
         is_active[l] = 0;
         delete_constraint(l);
         need_pick = false;
         continue;
       }
-      for(int i = 0; i < n; i++) x[i] = std::fma(t, z[i], x[i]);
-      for(int k = 0; k < q; k++) u[k] = std::fma(-t, r[k], u[k]);
+      for(int i = 0; i < n; i++) x[i] = fmad(t, z[i], x[i]);
+      for(int k = 0; k < q; k++) u[k] = fmad(-t, r[k], u[k]);
       u[q] = u[q] + t;
       if(t == t2)
       {

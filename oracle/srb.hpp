@@ -97,7 +97,7 @@ struct SrbProblem : public DdpProblem
     for(int a = 0; a < 3; a++) rhs[a] = (-cw[a]) + n[a];
     inertiaLlt(k).solve(rhs, 1);
     for(int a = 0; a < 3; a++) xdot[9 + a] = rhs[a];
-    for(int i = 0; i < 12; i++) xn[i] = std::fma(dt, xdot[i], x[i]);
+    for(int i = 0; i < 12; i++) xn[i] = fmad(dt, xdot[i], x[i]);
   }
 
   static double quad12(const double * w, const double * x, const double * r)
@@ -106,9 +106,9 @@ struct SrbProblem : public DdpProblem
     for(int a = 0; a < 6; a++)
     {
       double d = x[a] - r[a];
-      c = std::fma(w[a], d * d, c);
+      c = fmad(w[a], d * d, c);
     }
-    for(int a = 6; a < 12; a++) c = std::fma(w[a], x[a] * x[a], c);
+    for(int a = 6; a < 12; a++) c = fmad(w[a], x[a] * x[a], c);
     return c;
   }
 
@@ -117,7 +117,7 @@ struct SrbProblem : public DdpProblem
     const int m = m_tab[k];
     double usq[32];
     for(int j = 0; j < m; j++) usq[j] = u[j] * u[j];
-    return std::fma(0.5 * w_run[12], tree_sum32(usq, m), 0.5 * quad12(w_run, x, ref + 6 * k));
+    return fmad(0.5 * w_run[12], tree_sum32(usq, m), 0.5 * quad12(w_run, x, ref + 6 * k));
   }
 
   double terminalCost(const double * x) const override { return 0.5 * quad12(w_term, x, ref + 6 * N); }

@@ -30,7 +30,7 @@ struct ZmpProblem : public DdpProblem
     xdot[3] = (x[2] - u[1]) * u[2] / (mass * (x[4] - zz));
     xdot[4] = x[5];
     xdot[5] = u[2] / mass - kGravity;
-    for(int i = 0; i < 6; i++) xn[i] = std::fma(dt, xdot[i], x[i]);
+    for(int i = 0; i < 6; i++) xn[i] = fmad(dt, xdot[i], x[i]);
   }
 
   void uref(int k, double * r) const
@@ -56,9 +56,9 @@ struct ZmpProblem : public DdpProblem
     for(int a = 0; a < 6; a++)
     {
       const double d = x[a] - rx[a];
-      q = std::fma(wx[a], d * d, q);
+      q = fmad(wx[a], d * d, q);
     }
-    return std::fma(0.5 * 1.0, tree_sum32(t, 3), 0.5 * q);
+    return fmad(0.5 * 1.0, tree_sum32(t, 3), 0.5 * q);
   }
 
   void termWeights(double * w, double * r) const
@@ -79,7 +79,7 @@ struct ZmpProblem : public DdpProblem
     for(int a = 0; a < 6; a++)
     {
       const double d = x[a] - r[a];
-      q = std::fma(w[a], d * d, q);
+      q = fmad(w[a], d * d, q);
     }
     return 0.5 * q;
   }

@@ -7,16 +7,18 @@ from centroidalcontrolcollection_b200.contact import total_wrench
 from sim_models import CentroidalSim
 
 
-def run_ddp_srb_closed_loop(solve, end_time=3.0, horizon_steps=100, horizon_dt=0.03, later_max_iter=2):
+def run_ddp_srb_closed_loop(solve, end_time=3.0, horizon_steps=100, horizon_dt=0.03, later_max_iter=1):
     """solve(problem_set, cfg) -> DdpResultArrays.  Returns (sim, ref_pos, ref_ori, tick_ok, iters).
 
-    Deviation from the reference test, which sets max_iter = 1 after the first tick (:133): with one
-    iteration per tick this scenario is numerically chaotic for the restated solver — every time the
-    sliding horizon re-zeroes the contact-switch stage the open-loop warm-start rollout departs far
-    from the previous plan (cost spikes of 1e4..1e12), and whether one DDP iteration recovers depends
-    on rounding: of six runs with 1e-9 perturbations of the initial state five end within 0.004 of the
-    reference pose and one diverges to NaN at the Euler singularity.  With two iterations per tick
-    every run passes with a 30x margin on the reference's tolerances, so that is what pins the oracle."""
+    As the reference test (:133), one DDP iteration per tick after the first (`later_max_iter = 1`).  The scenario is
+    a single deterministic sample of a numerically sensitive loop: the warm start is the previous plan, unshifted,
+    rolled out open loop over 3 s of an unstable plant, and re-zeroed at the contact switch every sixth tick, so the
+    warm-start rollout cost jumps from ~5 to 1e2..1e7 again and again and one DDP iteration only partly recovers.
+    tools/srb_robustness.py (profiles/r02_srb_robustness.txt) measures it: with 1e-9 perturbations of the first
+    initial state 66-85 % of the runs pass the reference tolerances, for every unpinned choice of the restated
+    solver, for the textbook-arithmetic build, and for 1, 2 or 3 iterations per tick alike — the sensitivity belongs
+    to the scenario, not to one of the restatement's choices.  The unperturbed scenario passes, which
+    is what the reference's CI shows for the reference."""
     sim_dt, mass = 0.005, 100.0
     sim = CentroidalSim(mass, (40.0, 20.0, 10.0), sim_dt)
     _, motion, ref = workloads.ddp_srb_test_schedule(horizon_steps, horizon_dt)
@@ -35,7 +37,7 @@ def run_ddp_srb_closed_loop(solve, end_time=3.0, horizon_steps=100, horizon_dt=0
             u_init[0, sched.m[0] != m_prev] = 0.0
         ps = problem.DdpSrbProblemSet(sched, [0], x0, mass, horizon_dt, w_run, w_term, u_init=u_init)
         res = solve(ps, cfg)
-        cfg.max_iter = later_max_iter  # the reference uses 1 (:133), see the docstring
+        cfg.max_iter = later_max_iter  # :133
         u_prev, m_prev = res.u.copy(), sched.m[0].copy()
         iters.append(int(res.iters[0]))
         m0 = int(sched.m[0, 0])
