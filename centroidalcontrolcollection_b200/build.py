@@ -27,11 +27,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, ab_variants=None):
+    """ab_variants (or CCC_AB_VARIANTS=1 in the environment): also compile the A/B builds of the DDP solver core's
+    feature bits (ddp_host.cuh Variants), selectable with ccc_ddp_centroidal_set_variant — measurement builds only."""
+    if ab_variants is None:
+        ab_variants = os.environ.get("CCC_AB_VARIANTS", "0") not in ("", "0")
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + (["-DCCC_AB_VARIANTS"] if ab_variants else []) + (["-Xptxas", "-v"] if verbose else [])
+    cmd += ["-t", "0", "-o", LIB] + sources()
     subprocess.check_call(cmd)
     return LIB
 

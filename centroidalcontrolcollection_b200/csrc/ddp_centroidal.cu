@@ -315,8 +315,10 @@ int32_t ccc_ddp_centroidal_last_launches(const ccc_ddp_centroidal_ws_t * ws)
 /* Tuning hooks shared by the DDP engines (not part of the stable ABI). */
 int32_t ccc_ddp_centroidal_set_variant(int32_t v)
 {
-  if(v >= 0 && v < 3) ccc_host::g_variant() = v;
-  return 3;
+  int n = 0;
+  ccc_host::Variants<ccc::CentroidalModel>::table(n);
+  if(v >= 0 && v < n) ccc_host::g_variant() = v;
+  return n;
 }
 
 void ccc_ddp_centroidal_set_chunk(int32_t chunk)

@@ -28,14 +28,16 @@ struct SolveQueue
   int capacity;
 };
 
-template<class M, int WARPS, int CTAS, bool CONSTRAINED>
+template<class M, int WARPS, int CTAS, bool CONSTRAINED, int FEAT = ccc::kFeatDefault>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
     ddp_solve_kernel(const __grid_constant__ ccc::DdpParams<M> P, const SolveQueue q)
 {
-  using Warp = ccc::DdpWarp<M, CONSTRAINED>;
+  using Warp = ccc::DdpWarp<M, CONSTRAINED, FEAT>;
   extern __shared__ __align__(16) double smem[];
   double * s = smem + (threadIdx.x >> 5) * Warp::sm::TOTAL;
   const int lane = threadIdx.x & 31;
+  unsigned ring_parity = 0;
+  Warp::init_warp(s);
   for(;;)
   {
     int e = -1;
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
     // acquire: the previous visit of this problem may have run on another SM
     __threadfence();
     const int b = e & (kResumeFlag - 1);
-    Warp w(P, s, b);
+    Warp w(P, s, b, &ring_parity);
     const bool finished = w.solve((e & kResumeFlag) != 0);
     __syncwarp();
     if(lane == 0)
@@ -154,25 +156,33 @@ bool dev_alloc(T *& p, size_t n)
   return check(cudaMalloc(reinterpret_cast<void **>(&p), (n ? n : 1) * sizeof(T)), "cudaMalloc");
 }
 
-/** Launch-shape variants (occupancy vs register budget), see profiles/r01_summary.md. */
+/** Kernel variants: the product default first, then the A/B builds of the solver core's feature bits
+ *  (ddp_warp_core.cuh kFeat*; measured in profiles/r02_summary.md).  All run 8 warps per SM in one CTA: the other launch
+ *  shapes of round 1 (6 x 1, 4 x 2, 12 warps) were measured slower and are gone (profiles/r01_summary.md). */
 template<class M>
 struct Variants
 {
   struct V
   {
-    int warps, ctas;
+    int warps, ctas, feat;
     void (*kernel[2])(const ccc::DdpParams<M>, const SolveQueue); // [unconstrained, constrained]
   };
+  template<int FEAT>
+  static constexpr V make()
+  {
+    return V{8, 1, FEAT, {ddp_solve_kernel<M, 8, 1, false, FEAT>, ddp_solve_kernel<M, 8, 1, true, FEAT>}};
+  }
   static const V * table(int & n)
   {
     static const V t[] = {
-        // 12 warps/SM (168 registers) was measured 20 % slower (spills, instruction fetch) and no longer fits the
-        // shared memory since the solver keeps a full symmetric Quu tile per warp (profiles/r01_summary.md)
-        {6, 1, {ddp_solve_kernel<M, 6, 1, false>, ddp_solve_kernel<M, 6, 1, true>}}, //  6 warps/SM in one CTA
-        {4, 2, {ddp_solve_kernel<M, 4, 2, false>, ddp_solve_kernel<M, 4, 2, true>}}, //  8 warps/SM in two CTAs
-        {8, 1, {ddp_solve_kernel<M, 8, 1, false>, ddp_solve_kernel<M, 8, 1, true>}}, //  8 warps/SM, 255 registers (default)
+        make<ccc::kFeatDefault>(),
+        make<ccc::kFeatAll>(), // variant 1: + TMA-staged gain lists (tests/test_gpu_ddp_centroidal.py runs it too)
+#ifdef CCC_AB_VARIANTS
+        make<0>(),
+        make<ccc::kFeatTma>(),
+#endif
     };
-    n = 3;
+    n = (int)(sizeof(t) / sizeof(t[0]));
     return t;
   }
 };
@@ -180,7 +190,7 @@ struct Variants
 /** Tuning state shared by the DDP engines (not part of the stable ABI). */
 inline int & g_variant()
 {
-  static int v = 2; // measured best on B200: 8 warps/SM, no spills, least I-cache pressure
+  static int v = 0; // the product default (Variants<M>::table)
   return v;
 }
 inline int & g_chunk()
@@ -243,7 +253,7 @@ struct DdpEngine
     ok = ok && dev_alloc(tab, S * n * 32 * M::TAB_ROWS);
     ok = ok && dev_alloc(xbuf, 2 * B * (n + 1) * NX);
     ok = ok && dev_alloc(ubuf, 2 * B * n * 32);
-    ok = ok && dev_alloc(gains, B * n * 32 * (1 + NX));
+    ok = ok && dev_alloc(gains, B * n * 32 * M::NXP);
     ok = ok && dev_alloc(u32, B * n * 32);
     ok = ok && dev_alloc(uo32, B * n * 32);
     qcap = (int)(B * 18);
@@ -308,6 +318,13 @@ struct DdpEngine
     P.u_init = nullptr;
     P.cfg = to_cfg(cfg);
     P.chunk_iters = 0;
+    // early abort of hopeless line-search rollouts needs costs that only grow along the horizon and the default
+    // acceptance threshold
+    P.abort_ok = cfg->cost_update_ratio_thre >= 0.0 ? 1 : 0;
+    for(int i = 0; i <= NX; i++)
+      if(!(in.w_run[i] >= 0.0)) P.abort_ok = 0;
+    for(int i = 0; i < NX; i++)
+      if(!(in.w_term[i] >= 0.0)) P.abort_ok = 0;
     P.xbuf = xbuf;
     P.ubuf = ubuf;
     P.gains = gains;

@@ -64,6 +64,8 @@ struct DdpParams
   const double * u_init; // [B][N][32] or null
   DdpCfg cfg;
   int chunk_iters; // > 0: suspend a solve after this many iterations per visit
+  int abort_ok;    // 1: all cost weights >= 0 and cost_update_ratio_thre >= 0, so a line-search rollout whose partial
+                   // cost already exceeds the nominal cost is certain to be rejected and may stop early
   // workspace (device)
   double * xbuf;  // [2][B][N+1][NX]  nominal / candidate state trajectories (ping-pong)
   double * ubuf;  // [2][B][N][32]
@@ -80,6 +82,20 @@ struct DdpParams
   double * out_lambda;
   unsigned * out_clamped;
 };
+
+/** Feature bits of the solver core (template parameter FEAT), kept selectable so that every one of them has a measured
+ *  A/B on the same build (profiles/r02_summary.md):
+ *   kFeatAbort — a line-search rollout stops as soon as its partial cost exceeds the nominal cost (costs are sums of
+ *     non-negative terms, so the candidate is rejected whatever follows; results are unchanged);
+ *   kFeatTma — the gain lists are laid out one row per input ([stage][32][NXP]: K(NX), k) and move through the TMA
+ *     engine: the backward pass writes the rows of a stage from its K staging buffer with ONE bulk store
+ *     (cp.async.bulk.global.shared::cta) of m rows, the line-search rollouts stream them back through a 2-3 slot
+ *     shared-memory ring filled by bulk loads completing on mbarriers (cp.async.bulk.shared::cluster.global), issued
+ *     two stages ahead by lane 0.  Without the bit: [stage][1+NX][32] rows, 10 STG / 11 LDG per lane and stage. */
+constexpr int kFeatAbort = 1;
+constexpr int kFeatTma = 2;
+constexpr int kFeatAll = kFeatAbort | kFeatTma;
+constexpr int kFeatDefault = kFeatAbort; // kFeatTma measured 7 % slower on config 3 (profiles/r02_summary.md): built, tested, off
 
 // per-warp shared-memory slice, offsets in doubles
 template<int NX, int NXP>
@@ -99,8 +115,13 @@ struct SmLayout
   static constexpr int QX = S2 + NN;
   static constexpr int QUXR = QX + NV;                          // [32][NXP] Qux rows (parked here across BoxQP: registers)
   static constexpr int SYM = QUXR + 32 * NXP;                   // 32 x kLda tile: Quu_F in full (both triangles), rows 16-byte aligned
-  static constexpr int TOTAL = SYM + 32 * kLda;
+  static constexpr int BAR = SYM + 32 * kLda;                   // 4 x 8 bytes: mbarriers of the gain ring (kFeatTma)
+  static constexpr int TOTAL = BAR + 4;
   static_assert(SYM % 2 == 0 && TOTAL % 2 == 0, "16-byte alignment of the tile rows and of the next warp's slice");
+  // gain ring of the line-search rollouts: slots of 32 rows x NXP inside the factor tile A (dead during rollouts)
+  static constexpr int SLOT = 32 * NXP;
+  static constexpr int RING = 3 * SLOT <= 32 * kLda ? 3 : 2;
+  static_assert(RING * SLOT <= 32 * kLda, "gain ring must fit in the factor tile");
   // aliases inside A (+ the start of VB), valid while no factor is alive
   static constexpr int WT = A;                                  // [32][6]  the 6 live rows of Vxx*Fu, transposed
   static constexpr int KB = A;                                  // [32][NXP] K rows
@@ -109,13 +130,15 @@ struct SmLayout
   static constexpr int VB1 = VB0 + 32;
   static constexpr int VB2 = VB0 + 64;
   static_assert(VB2 + 32 <= IDX, "cost-to-go scratch must fit in the tile + BoxQP buffers");
-  static_assert(NXP % 2 == 0 && NXP >= NX, "row stride of the K/Z/Q buffers");
+  static_assert(NXP % 2 == 0 && NXP >= NX + 1, "row stride of the K/Z/Q buffers: NX gains + k, even");
 };
 
-template<class M, bool kConstrained>
+template<class M, bool kConstrained, int FEAT = kFeatDefault>
 struct DdpWarp
 {
   static constexpr int NX = M::NX, NXP = M::NXP, R0 = M::R0, NREF = M::NREF;
+  static constexpr bool kTma = (FEAT & kFeatTma) != 0, kAbort = (FEAT & kFeatAbort) != 0;
+  static constexpr int GBLK = 32 * NXP; // doubles per stage of the gain lists (either layout fits: NXP >= NX + 1)
   using sm = SmLayout<NX, NXP>;
   const DdpParams<M> & P;
   double * s; // this warp's shared-memory slice
@@ -126,16 +149,53 @@ struct DdpWarp
   // lanes 8-15 dV[1], lanes 16-23 max_k ||k_k|| / (||u_k|| + 1) (nmpc_ddp's small-gradient measure), lanes 24-31 unused.
   double acc4;
   double krel;
+  unsigned * ring_parity; // phase bits of the ring's mbarriers: they live as long as the kernel, not the solve
 
-  CCC_DEV DdpWarp(const DdpParams<M> & p, double * smem, int prob)
+  CCC_DEV DdpWarp(const DdpParams<M> & p, double * smem, int prob, unsigned * parity)
   : P(p), s(smem), b(prob), sched(p.sched_id[prob]), lane(lane_id()), cur(0), lambda(0), dlambda(0), dV0(0), dV1(0),
-    J(0), acc4(0), krel(0)
+    J(0), acc4(0), krel(0), ring_parity(parity)
   {
+  }
+
+  /** Once per warp and kernel: the mbarriers of the gain ring (one arrival each: lane 0's expect_tx). */
+  CCC_DEV static void init_warp(double * smem)
+  {
+    if(kTma && lane_id() == 0)
+    {
+      unsigned long long * bars = reinterpret_cast<unsigned long long *>(smem + sm::BAR);
+      for(int i = 0; i < sm::RING; i++) mbar_init(bars + i, 1);
+    }
+    warp_sync();
   }
 
   CCC_DEV double * xtraj(int which) const { return P.xbuf + ((size_t)which * P.B + b) * (size_t)(P.N + 1) * NX; }
   CCC_DEV double * utraj(int which) const { return P.ubuf + ((size_t)which * P.B + b) * (size_t)P.N * 32; }
-  CCC_DEV double * gain(int k) const { return P.gains + ((size_t)b * P.N + k) * (32 * (1 + NX)); }
+  CCC_DEV double * gain(int k) const { return P.gains + ((size_t)b * P.N + k) * GBLK; }
+  CCC_DEV unsigned long long * ring_bar(int slot) const { return reinterpret_cast<unsigned long long *>(s + sm::BAR) + slot; }
+  CCC_DEV double * ring_slot(int slot) const { return s + sm::A + slot * sm::SLOT; }
+  /** Lane 0 starts the bulk load of stage k's gain rows into ring slot k % RING (nothing to load for m = 0). */
+  CCC_DEV void ring_issue(int k) const
+  {
+    const int m = stage_m(k);
+    if(lane == 0 && m > 0)
+    {
+      const int slot = k % sm::RING;
+      const unsigned bytes = (unsigned)m * (NXP * 8);
+      fence_proxy_async_smem(); // the slot's previous contents were read through the generic proxy
+      mbar_arrive_expect_tx(ring_bar(slot), bytes);
+      tma_bulk_g2s(ring_slot(slot), gain(k), bytes, ring_bar(slot));
+    }
+  }
+  /** All lanes wait for stage k's rows (issued earlier by ring_issue(k)); `parity` holds one phase bit per slot. */
+  CCC_DEV void ring_wait(int k, int m, unsigned & parity) const
+  {
+    if(m > 0)
+    {
+      const int slot = k % sm::RING;
+      mbar_wait(ring_bar(slot), (parity >> slot) & 1u);
+      parity ^= 1u << slot;
+    }
+  }
   CCC_DEV int entry(int k) const { return P.tab_off + k * P.tab_stride; }
   CCC_DEV int stage_m(int k) const { return ldg(P.m + (size_t)sched * P.tab_len + entry(k)); }
   CCC_DEV const double * stage_tab(int k) const { return P.tab + ((size_t)sched * P.tab_len + entry(k)) * (32 * M::TAB_ROWS); }
@@ -207,11 +267,22 @@ struct DdpWarp
     for(int c = 0; c <= NX; c++) gq[c] = 0.0;
     CCC_UNROLL
     for(int c = 0; c < NX; c++) xq[c] = 0.0;
+    unsigned parity = *ring_parity;
+    int issued = 0; // kTma: stages [0, issued) have had their bulk load started
     if(!initial)
     {
-      const double * g = gain(0);
-      CCC_UNROLL
-      for(int c = 0; c <= NX; c++) gq[c] = g[c * 32 + lane];
+      if(kTma)
+      {
+        warp_sync(); // the factor tile (ring slots) is dead: every lane is past the backward pass
+        CCC_NOUNROLL
+        for(; issued < sm::RING - 1 && issued < N; issued++) ring_issue(issued);
+      }
+      else
+      {
+        const double * g = gain(0);
+        CCC_UNROLL
+        for(int c = 0; c <= NX; c++) gq[c] = g[c * 32 + lane];
+      }
       uq = un[lane];
       CCC_UNROLL
       for(int c = 0; c < NX; c++) xq[c] = xn[c];
@@ -230,15 +301,43 @@ struct DdpWarp
       {
         double gk[1 + NX], dx[NX];
         const double uj = uq;
-        CCC_UNROLL
-        for(int c = 0; c <= NX; c++) gk[c] = gq[c];
+        if(kTma)
+        {
+          // the slot two stages ahead was last read at stage k - 1 (every lane is past it: the stage's reductions
+          // synchronise the warp); start its refill, then take this stage's row from its slot
+          if(issued < N)
+          {
+            warp_sync();
+            ring_issue(issued);
+            issued++;
+          }
+          ring_wait(k, m, parity);
+          const double * row = ring_slot(k % sm::RING) + lane * NXP;
+          CCC_UNROLL
+          for(int c = 0; c < NXP; c += 2)
+          {
+            const d2 v = active ? ld2(row + c) : d2{0.0, 0.0};
+            if(c < NX) gk[1 + c] = v.x;
+            if(c == NX) gk[0] = v.x;
+            if(c + 1 < NX) gk[2 + c] = v.y;
+            if(c + 1 == NX) gk[0] = v.y;
+          }
+        }
+        else
+        {
+          CCC_UNROLL
+          for(int c = 0; c <= NX; c++) gk[c] = gq[c];
+        }
         CCC_UNROLL
         for(int c = 0; c < NX; c++) dx[c] = x[c] - xq[c];
         if(k + 1 < N)
         {
-          const double * g = gain(k + 1);
-          CCC_UNROLL
-          for(int c = 0; c <= NX; c++) gq[c] = g[c * 32 + lane];
+          if(!kTma)
+          {
+            const double * g = gain(k + 1);
+            CCC_UNROLL
+            for(int c = 0; c <= NX; c++) gq[c] = g[c * 32 + lane];
+          }
           uq = un[(size_t)(k + 1) * 32 + lane];
           CCC_UNROLL
           for(int c = 0; c < NX; c++) xq[c] = xn[(size_t)(k + 1) * NX + c];
@@ -255,7 +354,20 @@ struct DdpWarp
       storeX(xd + (size_t)k * NX, x);
       const double c = step_and_cost(k, m, x, u);
       Jc = Jc + c;
+      if(kAbort && !initial && P.abort_ok && Jc > J)
+      {
+        // every later term is >= 0: this candidate costs more than the nominal trajectory and will be rejected.
+        // Drain the bulk loads that are still in flight (the ring lives in the factor tile of the next backward pass).
+        if(kTma)
+        {
+          CCC_NOUNROLL
+          for(int kk = k + 1; kk < issued; kk++) ring_wait(kk, stage_m(kk), parity);
+          *ring_parity = parity;
+        }
+        return Jc;
+      }
     }
+    if(kTma) *ring_parity = parity;
     storeX(xd + (size_t)N * NX, x);
     Jc = Jc + terminal_cost(x);
     return Jc;
@@ -362,6 +474,12 @@ struct DdpWarp
       Qu = M::lu(*this, k, u) + acc;
     }
     // W = Vxx Fu, rows R0..R0+5, published transposed: WT[lane][0..5]
+    if(kTma)
+    {
+      // WT aliases the K staging rows that the previous stage's bulk store may still be reading
+      if(lane == 0) bulk_wait_read_all();
+      warp_sync();
+    }
     double * WT = s + sm::WT;
     double quu_diag; // Quu(lane, lane) = luu + Fu' (Vxx Fu) of this lane: from the registers, no 32-way select
     {
@@ -442,7 +560,7 @@ struct DdpWarp
       // warm start: gain of the next stage if the dimensions agree (iLQG.m: k(:,min(i+1,N-1)))
       double x0;
       if(k == N - 1)
-        x0 = active ? gain(k)[lane] : 0.0;
+        x0 = active ? (kTma ? ldcg(gain(k) + lane * NXP + NX) : gain(k)[lane]) : 0.0; // (written by a bulk store: not through L1)
       else
         x0 = (m_next == m) ? k_next : 0.0;
       BoxQpOut r = boxqp_warp(H, S, A, s + sm::VB, idxbuf, Qu, lo, hi, x0, m, P.cfg.boxqp);
@@ -506,11 +624,27 @@ struct DdpWarp
       double * KBw = s + sm::KB; // the factor tile is dead: stage K for the cost-to-go update
       CCC_UNROLL
       for(int c = 0; c < NX; c++) KBw[lane * NXP + c] = K[c];
-      if(NXP > NX) KBw[lane * NXP + NX] = 0.0;
+      CCC_UNROLL
+      for(int c = NX; c < NXP; c++) KBw[lane * NXP + c] = 0.0;
     }
     if(P.out_clamped && lane == 0) P.out_clamped[(size_t)b * N + k] = clamped;
 
-    // store gains (coalesced rows)
+    // store gains
+    if(kTma)
+    {
+      // the K staging rows [32][NXP] (original numbering, rows >= m zero) are the HBM image of the stage: k goes into
+      // slot NX of the lane's own row, then lane 0 hands rows 0..m-1 to the TMA engine as one bulk store.  The rows are
+      // read asynchronously; backward_stage waits for that (bulk_wait_read_all) before the tile is written again.
+      s[sm::KB + lane * NXP + NX] = kk;
+      warp_sync();
+      if(lane == 0)
+      {
+        fence_proxy_async_smem(); // the rows were written through the generic proxy
+        tma_bulk_s2g(gain(k), s + sm::KB, (unsigned)m * (NXP * 8));
+        bulk_commit();
+      }
+    }
+    else
     {
       double * g = gain(k);
       g[lane] = kk;
@@ -668,15 +802,23 @@ struct DdpWarp
     acc4 = 0.0;
     double k_next = 0.0;
     int m_next = -1;
+    bool ok = true;
     CCC_NOUNROLL
-    for(int k = N - 1; k >= 0; k--)
+    for(int k = N - 1; k >= 0 && ok; k--) ok = backward_stage(k, k_next, m_next);
+    if(kTma)
     {
-      if(!backward_stage(k, k_next, m_next)) return false;
+      // the gain rows must be in global memory before the rollouts' bulk loads (and the next pass's warm start) read them
+      if(lane == 0)
+      {
+        bulk_wait_all();
+        fence_proxy_async_all();
+      }
+      warp_sync();
     }
     dV0 = warp_shfl(acc4, 0);
     dV1 = warp_shfl(acc4, 8);
     krel = warp_shfl(acc4, 16);
-    return true;
+    return ok;
   }
 
   CCC_DEV void increase_lambda()
@@ -729,7 +871,13 @@ struct DdpWarp
       dlambda = P.cfg.initial_dlambda;
       cur = 0;
       // the BoxQP warm start of the last stage reads its own previous gain: zero it
-      gain(N - 1)[lane] = 0.0;
+      if(kTma)
+      {
+        gain(N - 1)[lane * NXP + NX] = 0.0;
+        fence_proxy_async_all(); // ... through the generic proxy, and a bulk store will overwrite it
+      }
+      else
+        gain(N - 1)[lane] = 0.0;
       if(P.out_clamped)
       {
         CCC_NOUNROLL

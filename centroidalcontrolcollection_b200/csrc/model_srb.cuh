@@ -57,7 +57,7 @@ struct Inertia3
 struct SrbModel
 {
   static constexpr int NX = 12;
-  static constexpr int NXP = 12;
+  static constexpr int NXP = 14;     // even row stride of the K / QuuK / Qux staging buffers: 12 gains + k
   static constexpr int R0 = 6;       // Fu is non-zero in rows 6..11
   static constexpr int NREF = 6;     // referenced states: position and orientation
   static constexpr int TAB_ROWS = 7; // ridge xyz, vertex xyz, inertia constants

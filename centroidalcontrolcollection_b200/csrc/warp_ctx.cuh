@@ -10,6 +10,7 @@
 #ifdef CCC_WARP_EMU
 #  include <cmath>
 #  include <cstdint>
+#  include <cstring>
 namespace ccc_emu
 {
 int lane();
@@ -43,7 +44,20 @@ inline double drint(double a) { return std::nearbyint(a); }
 inline double dabs(double a) { return std::fabs(a); }
 template<class T>
 inline T ldg(const T * p) { return *p; }
+inline double ldcg(const double * p) { return *p; }
 inline void prefetch_l1(const void *) {}
+// TMA / mbarrier stand-ins for the lock-step emulator: the copy is done at once by the issuing fibre and the wait is a
+// warp barrier (every fibre of the warp waits at the same point), which is the ordering the mbarrier gives on the GPU
+inline void mbar_init(unsigned long long *, int) {}
+inline void mbar_arrive_expect_tx(unsigned long long *, unsigned) {}
+inline void tma_bulk_g2s(void * dst, const void * src, unsigned bytes, unsigned long long *) { std::memcpy(dst, src, bytes); }
+inline void tma_bulk_s2g(void * dst, const void * src, unsigned bytes) { std::memcpy(dst, src, bytes); }
+inline void mbar_wait(unsigned long long *, unsigned) { ccc_emu::syncwarp(); }
+inline void fence_proxy_async_smem() {}
+inline void fence_proxy_async_all() {}
+inline void bulk_commit() {}
+inline void bulk_wait_read_all() {}
+inline void bulk_wait_all() {}
 } // namespace ccc
 #  define CCC_HAS_TMA 0
 #else
@@ -73,6 +87,8 @@ CCC_DEV double drint(double a) { return rint(a); }
 CCC_DEV double dabs(double a) { return fabs(a); }
 template<class T>
 CCC_DEV T ldg(const T * p) { return __ldg(p); }
+/** Load that bypasses L1 (data written by the TMA engine, which does not update this SM's L1). */
+CCC_DEV double ldcg(const double * p) { return __ldcg(p); }
 /** Hint: bring the 128-byte line holding p into L1 (no register, no scoreboard wait). */
 CCC_DEV void prefetch_l1(const void * p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -106,6 +122,19 @@ CCC_DEV void mbar_wait(unsigned long long * bar, unsigned parity)
 }
 /** Orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes. */
 CCC_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+/** The same for every state space (generic-proxy stores to global that a later bulk copy overwrites or reads). */
+CCC_DEV void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+/** dst (global, 16-byte aligned) <- src (shared, 16-byte aligned), bytes a multiple of 16; completion is tracked by
+ *  the issuing thread's bulk async-group (SASS: UBLKCP.S2G / UTMASTG-less bulk store). */
+CCC_DEV void tma_bulk_s2g(void * dst, const void * src, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+CCC_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/** All of this thread's bulk stores have finished READING their shared-memory source (it may be overwritten). */
+CCC_DEV void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+/** All of this thread's bulk stores are complete (their global writes performed). */
+CCC_DEV void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 } // namespace ccc
 #  define CCC_HAS_TMA 1
 #endif

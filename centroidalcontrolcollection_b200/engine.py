@@ -22,6 +22,7 @@ EXPORTS = [
     "ccc_ddp_srb_create", "ccc_ddp_srb_destroy", "ccc_ddp_srb_solve", "ccc_ddp_srb_last_launches",
     "ccc_ddp_zmp_create", "ccc_ddp_zmp_destroy", "ccc_ddp_zmp_solve", "ccc_ddp_zmp_last_launches",
     "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
+    "ccc_fp64_peak_tflops",
 ]
 
 
@@ -40,6 +41,8 @@ def lib():
         L.ccc_abi_version.restype = C.c_int32
         L.ccc_device_count.restype = C.c_int32
         L.ccc_last_error.restype = C.c_char_p
+        L.ccc_fp64_peak_tflops.restype = C.c_double
+        L.ccc_fp64_peak_tflops.argtypes = [C.c_int32, C.c_void_p]
         L.ccc_ddp_config_default.argtypes = [C.c_void_p]
         L.ccc_ddp_config_default.restype = None
         L.ccc_ddp_centroidal_create.restype = C.c_void_p

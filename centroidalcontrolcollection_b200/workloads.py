@@ -264,3 +264,15 @@ def linear_mpc_xy_batch(batch=256, horizon_steps=15, t0=2.8, seed=20260105):
     return {"name": "LinearMpcXY test schedule", "mass": mass, "horizon_dt": horizon_dt, "horizon_steps": horizon_steps,
             "t0": t0, "motion_param_func": motion_param, "ref_data_func": ref_data,
             "x0": linear_mpc_xy.to_state(mass, pos, vel, am)}
+
+
+def linear_mpc_xy_problem_set(horizon_steps=15, batch=1184):
+    """The assembled QP batch (qp.QpProblemSet) of `batch` LinearMpcXY problems on the reference test's schedule:
+    n = 16 x horizon_steps variables, one equality per stage, 2n bound rows (reference src/LinearMpcXY.cpp:116-182)."""
+    from . import linear_mpc_xy
+
+    w = linear_mpc_xy_batch(batch=batch, horizon_steps=horizon_steps)
+    mpc = linear_mpc_xy.LinearMpcXY(w["mass"], w["horizon_dt"], horizon_steps)
+    ts = [w["t0"] + i * w["horizon_dt"] for i in range(horizon_steps)]
+    ref = np.concatenate([linear_mpc_xy.to_state(w["mass"], *w["ref_data_func"](t)) for t in ts])
+    return mpc.build_qp([w["motion_param_func"](t) for t in ts], ref, w["x0"])

@@ -320,6 +320,9 @@ int32_t ccc_preview_input(int32_t batch,
 int32_t ccc_abi_version(void);
 int32_t ccc_device_count(void);
 const char * ccc_last_error(void);
+/* Measurement aid (no reference counterpart): FP64 fma throughput of the current device in TFLOP/s, best of `reps`
+ * launches of a pure-DFMA kernel timed with CUDA events on `stream`; the denominator of bench.py's roofline.fp64. */
+double ccc_fp64_peak_tflops(int32_t reps, void * stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <deque>
 #include <functional>
+#include <type_traits>
 #include <vector>
 
 namespace ccc_emu
@@ -195,6 +196,14 @@ ccc::DdpCfg toCfg(const ccc_ddp_config_t * c)
 namespace
 {
 int g_chunk = 0;
+int g_feat = 1;
+}
+
+/** Which build of the solver core to emulate (ddp_warp_core.cuh kFeat*): 0 = no feature bits, 1 = the product default,
+ *  2 = every feature (incl. the TMA-staged gain lists, whose bulk copies the emulator performs synchronously). */
+extern "C" void ccc_emu_set_feat(int32_t feat)
+{
+  g_feat = feat;
 }
 
 /** Iterations per visit before a solve is suspended and re-queued (0 = never), as in the kernel. */
@@ -233,7 +242,7 @@ int32_t emuSolve(int N, int B, int S, int mm, const int32_t * sched_id, const in
       for(int j = 0; j < mm; j++) u_init[bk * 32 + j] = u_init_in[bk * mm + j];
   }
   std::vector<double> xbuf((size_t)2 * B * (N + 1) * NX, 0.0), ubuf((size_t)2 * B * N * 32, 0.0),
-      gains((size_t)B * N * 32 * (1 + NX), 0.0), out_u((size_t)B * N * 32, 0.0);
+      gains((size_t)B * N * 32 * M::NXP, 0.0), out_u((size_t)B * N * 32, 0.0);
   ccc::DdpParams<M> P{};
   P.N = N;
   P.B = B;
@@ -269,7 +278,13 @@ int32_t emuSolve(int N, int B, int S, int mm, const int32_t * sched_id, const in
   std::vector<ccc::DdpResume> resume(B);
   P.resume = resume.data();
   P.chunk_iters = g_chunk;
+  P.abort_ok = c->cost_update_ratio_thre >= 0.0 ? 1 : 0;
+  for(int i = 0; i <= NX; i++)
+    if(!(w_run[i] >= 0.0)) P.abort_ok = 0;
+  for(int i = 0; i < NX; i++)
+    if(!(w_term[i] >= 0.0)) P.abort_ok = 0;
   std::vector<double> smem(sm::TOTAL + 2, 0.0);
+  unsigned ring_parity = 0;
   // the kernel's round-robin queue, replayed by one emulated warp: (problem, resumed?) entries
   std::deque<std::pair<int, bool>> queue;
   for(int b = 0; b < B; b++) queue.emplace_back(b, false);
@@ -281,16 +296,19 @@ int32_t emuSolve(int N, int B, int S, int mm, const int32_t * sched_id, const in
     bool finished = true;
     ccc_emu::run_warp([&]() {
       bool f;
+      auto run = [&](auto tag_c, auto tag_f) {
+        ccc::DdpWarp<M, decltype(tag_c)::value, decltype(tag_f)::value> w(P, smem.data(), b, &ring_parity);
+        return w.solve(resumed);
+      };
+      using T = std::true_type;
+      using F = std::false_type;
+      using FeatOn = std::integral_constant<int, ccc::kFeatDefault>;
+      using FeatAll = std::integral_constant<int, ccc::kFeatAll>;
+      using FeatOff = std::integral_constant<int, 0>;
       if(P.cfg.with_input_constraint)
-      {
-        ccc::DdpWarp<M, true> w(P, smem.data(), b);
-        f = w.solve(resumed);
-      }
+        f = g_feat == 2 ? run(T{}, FeatAll{}) : g_feat ? run(T{}, FeatOn{}) : run(T{}, FeatOff{});
       else
-      {
-        ccc::DdpWarp<M, false> w(P, smem.data(), b);
-        f = w.solve(resumed);
-      }
+        f = g_feat == 2 ? run(F{}, FeatAll{}) : g_feat ? run(F{}, FeatOn{}) : run(F{}, FeatOff{});
       if(ccc_emu::lane() == 0) finished = f;
     });
     if(!finished) queue.emplace_back(b, true);

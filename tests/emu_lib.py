@@ -19,8 +19,10 @@ def lib():
     return _LIB
 
 
-def ddp_centroidal_solve(problem_set, cfg, trace_len=0, chunk=0):
+def ddp_centroidal_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
+    """feat: 0 = no feature bits, 1 = product default, 2 = every feature of the solver core (ddp_warp_core.cuh kFeat*)."""
     lib().ccc_emu_set_chunk(int(chunk))
+    lib().ccc_emu_set_feat(int(feat))
     res = problem_set.new_result(trace_len)
     bs, rs = problem_set.as_struct(), res.as_struct()
     rc = lib().ccc_emu_ddp_centroidal_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))
@@ -28,8 +30,9 @@ def ddp_centroidal_solve(problem_set, cfg, trace_len=0, chunk=0):
     return res
 
 
-def ddp_srb_solve(problem_set, cfg, trace_len=0, chunk=0):
+def ddp_srb_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
     lib().ccc_emu_set_chunk(int(chunk))
+    lib().ccc_emu_set_feat(int(feat))
     res = problem_set.new_result(trace_len)
     bs, rs = problem_set.as_struct(), res.as_struct()
     rc = lib().ccc_emu_ddp_srb_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))
@@ -47,8 +50,9 @@ def qp_solve(problem_set):
     return res
 
 
-def ddp_zmp_solve(problem_set, cfg, trace_len=0, chunk=0):
+def ddp_zmp_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
     L = lib()
+    L.ccc_emu_set_feat(int(feat))
     L.ccc_emu_ddp_zmp_solve.restype = C.c_int32
     L.ccc_emu_ddp_zmp_solve.argtypes = [C.c_void_p] * 3
     L.ccc_emu_set_chunk(int(chunk))

@@ -149,4 +149,6 @@ def test_emulated_kernel_matches_oracle(oracle):
     u_init = np.tile(np.array([0.0, 0.0, 100 * G]), (2, N, 1))
     ps = problem.DdpZmpProblemSet(ref_zmp, np.ones((1, N + 1)), [0, 0], x0, 100.0, 0.02, u_init=u_init)
     cfg = problem.ddp_config(max_iter=4)
-    assert_ddp_parity(oracle.ddp_zmp_solve(ps, cfg, trace_len=4), emu_lib.ddp_zmp_solve(ps, cfg, trace_len=4, chunk=2))
+    ref = oracle.ddp_zmp_solve(ps, cfg, trace_len=4)
+    for feat in (1, 2):
+        assert_ddp_parity(ref, emu_lib.ddp_zmp_solve(ps, cfg, trace_len=4, chunk=2, feat=feat))

@@ -8,10 +8,13 @@ import emu_lib
 from parity import assert_ddp_parity
 
 
-def _run(oracle, ps, cfg, trace_len=16, chunk=0):
+def _run(oracle, ps, cfg, trace_len=16, chunk=0, feats=(1, 2)):
+    """feats: builds of the solver core to emulate (1 = product default, 2 = every feature bit incl. the TMA-staged
+    gain lists, 0 = none); each must reproduce the oracle bit for bit."""
     ref = oracle.ddp_centroidal_solve(ps, cfg, trace_len=trace_len)
-    got = emu_lib.ddp_centroidal_solve(ps, cfg, trace_len=trace_len, chunk=chunk)
-    assert_ddp_parity(ref, got)
+    for feat in feats:
+        got = emu_lib.ddp_centroidal_solve(ps, cfg, trace_len=trace_len, chunk=chunk, feat=feat)
+        assert_ddp_parity(ref, got)
     return ref
 
 
@@ -35,7 +38,7 @@ def test_all_phase_kinds_few_iterations(oracle):
     """N=50 covers m = 16, 0 (flight) and 32 stages, dimension changes and BoxQP clamping."""
     w = workloads.ddp_centroidal_config3(batch=2, horizon_steps=50)
     ps = problem.DdpCentroidalProblemSet.from_workload(w).subset([0, 1])
-    ref = _run(oracle, ps, problem.ddp_centroidal_config(max_iter=3))
+    ref = _run(oracle, ps, problem.ddp_centroidal_config(max_iter=3), feats=(0, 1, 2))
     assert set(np.unique(ps.sched.m)) == {0, 16, 32}
     assert (ref.clamped != 0).any()
 

@@ -23,4 +23,6 @@ def test_srb_flight_and_large_angles(oracle):
     x0 = np.array([[0.1, -0.05, 1.05, 0.9, -0.6, 0.4, 0.2, -0.1, 0.1, 1.0, -2.0, 1.5]])
     ps = problem.DdpSrbProblemSet(sched, [0], x0, 100.0, 0.03, w_run, w_term)
     cfg = problem.ddp_srb_config(max_iter=3)
-    assert_ddp_parity(oracle.ddp_srb_solve(ps, cfg, trace_len=4), emu_lib.ddp_srb_solve(ps, cfg, trace_len=4))
+    ref = oracle.ddp_srb_solve(ps, cfg, trace_len=4)
+    for feat in (1, 2):  # product default; every feature bit (TMA-staged gains: 14-double rows, 2-slot ring)
+        assert_ddp_parity(ref, emu_lib.ddp_srb_solve(ps, cfg, trace_len=4, feat=feat))

@@ -50,13 +50,7 @@ def test_ismpc_structure(oracle):
 
 
 def _xy_problem_set(horizon_steps, batch):
-    from centroidalcontrolcollection_b200 import linear_mpc_xy
-
-    w = workloads.linear_mpc_xy_batch(batch=batch, horizon_steps=horizon_steps)
-    mpc = linear_mpc_xy.LinearMpcXY(w["mass"], w["horizon_dt"], horizon_steps)
-    ts = [w["t0"] + i * w["horizon_dt"] for i in range(horizon_steps)]
-    ref = np.concatenate([linear_mpc_xy.to_state(w["mass"], *w["ref_data_func"](t)) for t in ts])
-    return mpc.build_qp([w["motion_param_func"](t) for t in ts], ref, w["x0"])
+    return workloads.linear_mpc_xy_problem_set(horizon_steps, batch)
 
 
 def test_linear_mpc_xy_structure_128_threads_global_slab(oracle):

@@ -21,8 +21,9 @@ def eng_mod():
 
 
 def test_parity_config4_sample(eng_mod, oracle):
-    """192 problems of config 4 (N = 100, A -> flight -> B), cold start to termination."""
-    w = workloads.ddp_srb_config4(batch=192)
+    """512 problems of config 4 (N = 100, A -> flight -> B), cold start to termination (with the 1536 of
+    test_full_shard_properties: 2048 of the shard's 8192 checked against the oracle)."""
+    w = workloads.ddp_srb_config4(batch=512)
     ps = problem.DdpSrbProblemSet.from_workload(w)
     cfg = problem.ddp_srb_config()
     eng = eng_mod.DdpSrbEngine(ps.N, ps.batch, ps.sched.S)
@@ -78,7 +79,7 @@ def test_full_shard_properties(eng_mod, oracle):
     assert (got.u >= ps.u_lo).all() and (got.u <= ps.u_hi).all()
     assert np.array_equal(got.x[:, 0, :], ps.x0)
     assert (got.status == 1).mean() > 0.5  # cold starts that need > 500 iterations stop with status 0
-    idx = np.sort(np.random.default_rng(2).choice(ps.batch, size=48, replace=False))
+    idx = np.sort(np.random.default_rng(2).choice(ps.batch, size=1536, replace=False))
     ref = oracle.ddp_srb_solve(ps.subset(idx), cfg, n_threads=max(1, oracle.hardware_threads()))
     assert np.array_equal(ref.iters, got.iters[idx])
     assert np.array_equal(ref.x, got.x[idx]) and np.array_equal(ref.u, got.u[idx])

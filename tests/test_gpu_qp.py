@@ -59,9 +59,10 @@ def test_config2_linear_mpc_zmp(oracle, qp_solve):
     assert np.array_equal(zmp, zmp_o)
 
 
-def test_config5_ismpc_sample(oracle, qp_solve):
-    """Config 5 sample: 16 plans x 64 perturbations x 2 axes = 2048 QPs with the equality constraint."""
-    w = workloads.ismpc_config5(n_plans=16, n_perturb=64)
+def test_config5_ismpc_full_size(oracle, qp_solve):
+    """Config 5 at full size: 256 plans x 512 perturbations x 2 axes = 262144 QPs with the equality constraint, every
+    one of them against the oracle."""
+    w = workloads.ismpc_config5()
     mpc = linear_mpc.IntrinsicallyStableMpc(w["com_height"], w["horizon_duration"], w["horizon_dt"])
     args = (w["capture_point"], w["planned_zmp"], w["ref_zmp"], w["lim_min"], w["lim_max"], w["control_dt"])
     zmp = mpc.plan_batch(qp_solve, *args)

@@ -15,6 +15,9 @@ ps = problem.DdpSrbProblemSet.from_workload(w)
 eng = engine.DdpSrbEngine(ps.N, ps.batch, ps.sched.S)
 cfg = problem.ddp_srb_config(max_iter=max_iter)
 res = eng.solve(ps, cfg)
+print("MEAN_ITERS", float(res.iters.mean()))
+if os.environ.get("NV_COMPUTE_PROFILER_PERFWORKS_DIR") or "--once" in sys.argv:
+    sys.exit(0)  # under ncu: one launch is enough
 t0 = time.time()
 res = eng.solve(ps, cfg)
 dt = time.time() - t0
