@@ -8,6 +8,7 @@
  */
 #pragma once
 #include <cstdint>
+#include <iostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -48,12 +49,19 @@ public:
     n_eq_ = A.rows();
     n_ineq_ = C.rows();
     if(Q.cols() != n_ || (n_eq_ > 0 && A.cols() != n_) || C.cols() != n_) throw std::invalid_argument("QpEngine::setup: shapes");
+    const bool same_dims = ws_ && Q.rows() == Q_.rows() && A.rows() == A_.rows() && C.rows() == C_.rows();
     Q_ = Q;
     A_ = A;
     C_ = C;
-    if(ws_) ccc_qp_destroy(ws_);
-    ws_ = nullptr;
-    ws_batch_ = 0;
+    // LinearMpcXY / LinearMpcZ call setup() every control tick with new matrices of (usually) the same shape: keep the
+    // device workspace then and only re-upload / re-factorise (the reference re-runs QpCoeff::setup only when the
+    // dimensions change, src/LinearMpcXY.cpp:134-138)
+    if(!same_dims)
+    {
+      if(ws_) ccc_qp_destroy(ws_);
+      ws_ = nullptr;
+      ws_batch_ = 0;
+    }
     matrices_resident_ = false;
   }
 
@@ -75,7 +83,10 @@ public:
   double * eqVec(int b) { return b_.data() + static_cast<size_t>(b) * n_eq_; }
   double * ineqVec(int b) { return d_.data() + static_cast<size_t>(b) * n_ineq_; }
 
-  /** Solve the batch; returns x [B][n].  Throws if the call fails or a problem is not solved. */
+  /** Solve the batch; returns x [B][n].  Throws if the call itself fails.  A problem that is not solved (infeasible,
+   *  iteration limit, active set full, Q not positive definite: status 1..4) is reported the way
+   *  QpSolverCollection::QpSolver::solve does it — an error line on std::cerr and the last iterate returned —
+   *  and counted in numFailed(); callers that must not act on such a result check status(b). */
   const std::vector<double> & solve()
   {
     if(!ws_ || batch_ > ws_batch_)
@@ -112,8 +123,22 @@ public:
     const int rc = ccc_qp_solve(ws_, &bt, &rs, CCC_MEM_HOST, nullptr);
     if(rc != CCC_OK) throw std::runtime_error(std::string("ccc_qp_solve: ") + ccc_last_error());
     matrices_resident_ = true;
+    n_failed_ = 0;
+    int first = -1;
+    for(int b = 0; b < batch_; b++)
+      if(status_[b] != 0)
+      {
+        if(first < 0) first = b;
+        n_failed_++;
+      }
+    if(n_failed_ > 0)
+      std::cerr << "[CCC::QpEngine] failed to solve " << n_failed_ << " of " << batch_ << " QPs (first: problem " << first
+                << ", status " << status_[first] << ": 1 infeasible, 2 iteration limit, 3 not positive definite, 4 active set full)"
+                << std::endl;
     return x_;
   }
+  /** Problems of the last solve() whose status is not 0. */
+  int numFailed() const { return n_failed_; }
 
   const double * x(int b) const { return x_.data() + static_cast<size_t>(b) * n_; }
   int status(int b) const { return status_[b]; }
@@ -121,7 +146,7 @@ public:
   int numActive(int b) const { return n_active_[b]; }
 
 private:
-  int n_ = 0, n_eq_ = 0, n_ineq_ = 0, batch_ = 0, ws_batch_ = 0;
+  int n_ = 0, n_eq_ = 0, n_ineq_ = 0, batch_ = 0, ws_batch_ = 0, n_failed_ = 0;
   bool with_c_ = false, matrices_resident_ = false;
   Matrix Q_, A_, C_;
   std::vector<double> c_, b_, d_, x_;

@@ -20,19 +20,31 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 kind = sys.argv[1] if len(sys.argv) > 1 else "centroidal"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else (16384 if kind == "centroidal" else 8192)
 METRICS = ["dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
-           "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+           "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+           "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
            "lts__t_sector_hit_rate.pct", "gpu__time_duration.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
            "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"]
 runner = os.path.join(ROOT, "tools", "profile_solve.py") if kind == "centroidal" else os.path.join(ROOT, "tools", "profile_srb.py")
 args = [str(batch), "0", "500"] if kind == "centroidal" else [str(batch), "500", "--once"]
 cmd = ["ncu", "--metrics", ",".join(METRICS), "--clock-control", "none", "-k", "regex:ddp_solve_kernel", "-c", "1", "--csv",
        sys.executable, runner] + args
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 r = subprocess.run(cmd, capture_output=True, text=True)
 rows = [row for row in csv.reader(io.StringIO(r.stdout)) if len(row) > 10 and row[0].isdigit()]
 if not rows:
     sys.stderr.write(r.stdout[-3000:] + r.stderr[-3000:])
     raise SystemExit("no ncu rows")
-val = {row[-3]: float(row[-1].replace(",", "")) for row in rows}
+open(os.path.join(ROOT, "gpurun_out", f"r02_ddp_{kind}_counters_raw.csv"), "w").write(r.stdout)
+
+
+def _num(v):
+    try:
+        return float(v.replace(",", ""))
+    except ValueError:
+        return None
+
+
+val = {row[-3]: _num(row[-1]) for row in rows}
 unit = {row[-3]: row[-2] for row in rows}
 mean_iters = None
 for ln in r.stdout.splitlines():
@@ -51,11 +63,10 @@ out = {
     "dadd_thread_inst_per_launch": val.get("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"),
     "dmul_thread_inst_per_launch": val.get("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"),
     "warp_inst_per_launch": val["smsp__inst_executed.sum"],
-    "issue_active_pct": val["smsp__issue_active.avg.pct"],
-    "fp64_pipe_active_pct": val["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"],
-    "l2_hit_rate_pct": val["lts__t_sector_hit_rate.pct"], "kernel_s_under_ncu": t,
+    "issue_active_pct": val.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+    "fp64_pipe_active_pct": val.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active") or val.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+    "l2_hit_rate_pct": val.get("lts__t_sector_hit_rate.pct"), "kernel_s_under_ncu": t,
 }
 path = os.path.join(ROOT, "gpurun_out", f"r02_ddp_{kind}_counters.json")
-os.makedirs(os.path.dirname(path), exist_ok=True)
 json.dump(out, open(path, "w"), indent=1)
 print(json.dumps(out, indent=1))
