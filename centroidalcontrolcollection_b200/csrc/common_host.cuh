@@ -22,6 +22,12 @@ inline bool check(cudaError_t e, const char * what)
   std::snprintf(error_buf(), 512, "%s: %s", what, cudaGetErrorString(e));
   return false;
 }
+/** Tuning state of the QP engine (not part of the stable ABI): packed-R two-CTA first pass on / off. */
+inline bool & g_qp_packed()
+{
+  static bool on = true;
+  return on;
+}
 inline int fail(int code, const char * msg)
 {
   set_error(msg);

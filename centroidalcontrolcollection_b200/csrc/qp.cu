@@ -14,9 +14,9 @@ __global__ void __launch_bounds__(ccc::kQpThreads, 1) qp_setup_kernel(int n, int
   ccc::qp_setup_cta(n, me, mi, Q, A, C, Lg, invd, J0, At, Ct, ok_flag, J0s);
 }
 
-template<int NT, bool kGlobal>
-__global__ void __launch_bounds__(NT, 1) qp_solve_kernel(const __grid_constant__ ccc::QpParams P, int * __restrict__ counter,
-                                                         double * __restrict__ gmat)
+template<int NT, bool kGlobal, bool kPackedR>
+__global__ void __launch_bounds__(NT, kPackedR ? 2 : 1) qp_solve_kernel(const __grid_constant__ ccc::QpParams P, int * __restrict__ counter,
+                                                                        double * __restrict__ gmat)
 {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_b;
@@ -25,14 +25,17 @@ __global__ void __launch_bounds__(NT, 1) qp_solve_kernel(const __grid_constant__
   if(!kGlobal && threadIdx.x == 0) ccc::mbar_init(&s_mbar, 1);
   __syncthreads();
   unsigned mbar_phase = 0;
+  // the fallback pass works through the list of problems whose active set outgrew the packed R of the first pass
+  const int total = P.list ? *P.list_count : P.B;
   for(;;)
   {
     if(threadIdx.x == 0) s_b = atomicAdd(counter, 1);
     __syncthreads();
-    const int b = s_b;
+    const int t = s_b;
     __syncthreads();
-    if(b >= P.B) break;
-    ccc::QpCta<NT, kGlobal> cta(P, smem, b, slab);
+    if(t >= total) break;
+    const int b = P.list ? P.list[t] : t;
+    ccc::QpCta<NT, kGlobal, kPackedR> cta(P, smem, b, slab);
     cta.mbar = kGlobal ? nullptr : &s_mbar;
     cta.mbar_phase = mbar_phase;
     cta.solve();
@@ -41,12 +44,23 @@ __global__ void __launch_bounds__(NT, 1) qp_solve_kernel(const __grid_constant__
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
+constexpr size_t kSmemTwoCtas = (228 * 1024 - 2 * 1024) / 2 - 128; // dynamic shared memory of one of two co-resident CTAs
+
+/** Largest number of columns a packed R may have so that two CTAs fit on an SM (0: not even the smallest useful one). */
+int qp_rcap(int n, int me)
+{
+  const int ld = n | 1;
+  int cap = 0;
+  for(int c = 8; c <= n; c++)
+    if(ccc::QpSm<128, false, true>::bytes(n, ld, c) <= kSmemTwoCtas) cap = c;
+  return cap > me + 8 ? cap : 0;
+}
 
 /** 0: 128 threads, J/R in shared memory; 1: 128 threads, J/R in global memory; 2: 256 threads, global. */
 int qp_shape(int n)
 {
   if(n > 128) return 2;
-  return ccc::QpSm<128, false>::bytes(n, n | 1) <= kSmemLimit ? 0 : 1;
+  return ccc::QpSm<128, false, false>::bytes(n, n | 1) <= kSmemLimit ? 0 : 1;
 }
 
 template<class T>
@@ -61,13 +75,19 @@ struct ccc_qp_ws
   int n = 0, me = 0, mi = 0, max_batch = 0, device = 0, launches = 0;
   bool have_setup = false; // the matrices of an earlier call are factorised and resident (reused when Q == NULL)
   double *Lg = nullptr, *invd = nullptr, *J0 = nullptr, *J0s = nullptr, *At = nullptr, *Ct = nullptr;
-  int *ok_flag = nullptr, *counter = nullptr;
+  int *ok_flag = nullptr, *counter = nullptr; // counter[0]: first pass, [1]: fallback pass, [2]: overflow count
+  int * ovf_list = nullptr;                      // problems whose active set outgrew the packed R of the first pass
+  int rcap = 0;                                  // columns of the packed R (0: one CTA per SM with the full R)
   double * gmat = nullptr; // per-CTA J/R slabs when they do not fit in shared memory
   int n_sm = 148;
   // staging for CCC_MEM_HOST
   double *d_Q = nullptr, *d_A = nullptr, *d_C = nullptr, *d_c = nullptr, *d_b = nullptr, *d_d = nullptr, *d_x = nullptr;
   int *d_iters = nullptr, *d_status = nullptr, *d_nact = nullptr, *d_active = nullptr;
   cudaStream_t own_stream = nullptr;
+  // chunked host path: copy streams and their events
+  static constexpr int kMaxChunks = 64;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_setup = nullptr, ev_h2d[kMaxChunks] = {}, ev_solved[kMaxChunks] = {};
 };
 
 extern "C" {
@@ -95,19 +115,36 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
   const size_t N = n, ME = n_eq, MI = n_ineq, B = max_batch;
   bool ok = true;
   ok = ok && dev_alloc(ws->Lg, N * N) && dev_alloc(ws->invd, N) && dev_alloc(ws->J0, N * N) && dev_alloc(ws->J0s, N * (N | 1));
-  ok = ok && dev_alloc(ws->At, N * ME) && dev_alloc(ws->Ct, N * MI) && dev_alloc(ws->ok_flag, 2) && dev_alloc(ws->counter, 1);
+  ok = ok && dev_alloc(ws->At, N * ME) && dev_alloc(ws->Ct, N * MI) && dev_alloc(ws->ok_flag, 2) && dev_alloc(ws->counter, 4) && dev_alloc(ws->ovf_list, B);
   ok = ok && dev_alloc(ws->d_Q, N * N) && dev_alloc(ws->d_A, N * ME) && dev_alloc(ws->d_C, N * MI);
   ok = ok && dev_alloc(ws->d_c, B * N) && dev_alloc(ws->d_b, B * ME) && dev_alloc(ws->d_d, B * MI) && dev_alloc(ws->d_x, B * N);
   ok = ok && dev_alloc(ws->d_iters, B) && dev_alloc(ws->d_status, B) && dev_alloc(ws->d_nact, B) && dev_alloc(ws->d_active, B * N);
   ok = ok && ccc_host::check(cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  ok = ok && ccc_host::check(cudaStreamCreateWithFlags(&ws->h2d_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  ok = ok && ccc_host::check(cudaStreamCreateWithFlags(&ws->d2h_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  ok = ok && ccc_host::check(cudaEventCreateWithFlags(&ws->ev_setup, cudaEventDisableTiming), "cudaEventCreate");
+  const int nchunk_max = max_batch <= 16384 ? 1 : (max_batch + 32767) / 32768;
+  for(int k = 0; ok && nchunk_max > 1 && k < nchunk_max && k < ccc_qp_ws::kMaxChunks; k++)
+    ok = ccc_host::check(cudaEventCreateWithFlags(&ws->ev_h2d[k], cudaEventDisableTiming), "cudaEventCreate")
+         && ccc_host::check(cudaEventCreateWithFlags(&ws->ev_solved[k], cudaEventDisableTiming), "cudaEventCreate");
   const int ld = n | 1;
   cudaDeviceGetAttribute(&ws->n_sm, cudaDevAttrMultiProcessorCount, ws->device);
   const int shape = qp_shape(n);
   if(shape == 0)
+  {
     ok = ok
-         && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)ccc::QpSm<128, false>::bytes(n, ld)),
+         && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)ccc::QpSm<128, false, false>::bytes(n, ld)),
                             "cudaFuncSetAttribute(smem)");
+    ws->rcap = qp_rcap(n, n_eq);
+    if(ws->rcap > 0)
+      ok = ok
+           && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)ccc::QpSm<128, false, true>::bytes(n, ld, ws->rcap)),
+                              "cudaFuncSetAttribute(smem, packed R)")
+           && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
+                              "cudaFuncSetAttribute(carveout)");
+  }
   else
     ok = ok && dev_alloc(ws->gmat, (size_t)ws->n_sm * 2 * N * ld);
   if(!ok)
@@ -121,12 +158,62 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
 void ccc_qp_destroy(ccc_qp_ws_t * ws)
 {
   if(!ws) return;
-  void * ptrs[] = {ws->J0s, ws->gmat, ws->Lg,  ws->invd, ws->J0,  ws->At,  ws->Ct,     ws->ok_flag, ws->counter, ws->d_Q,    ws->d_A,
+  void * ptrs[] = {ws->ovf_list, ws->J0s, ws->gmat, ws->Lg,  ws->invd, ws->J0,  ws->At,  ws->Ct,     ws->ok_flag, ws->counter, ws->d_Q,    ws->d_A,
                    ws->d_C, ws->d_c,  ws->d_b, ws->d_d, ws->d_x,    ws->d_iters, ws->d_status, ws->d_nact, ws->d_active};
   for(void * p : ptrs)
     if(p) cudaFree(p);
   if(ws->own_stream) cudaStreamDestroy(ws->own_stream);
+  if(ws->h2d_stream) cudaStreamDestroy(ws->h2d_stream);
+  if(ws->d2h_stream) cudaStreamDestroy(ws->d2h_stream);
+  if(ws->ev_setup) cudaEventDestroy(ws->ev_setup);
+  for(int k = 0; k < ccc_qp_ws::kMaxChunks; k++)
+  {
+    if(ws->ev_h2d[k]) cudaEventDestroy(ws->ev_h2d[k]);
+    if(ws->ev_solved[k]) cudaEventDestroy(ws->ev_solved[k]);
+  }
   delete ws;
+}
+
+/** Launch the solve kernels for problems [lo, lo + nb) of the batch described by P (device pointers, per-problem
+ *  arrays already offset by the caller) on stream st. */
+static int qp_launch(ccc_qp_ws_t * ws, ccc::QpParams P, cudaStream_t st)
+{
+  using ccc_host::check;
+  const int n = P.n, B = P.B;
+  if(!check(cudaMemsetAsync(ws->counter, 0, 4 * sizeof(int), st), "memset")) return CCC_ERR_CUDA;
+  const int grid = B < ws->n_sm ? B : ws->n_sm;
+  switch(qp_shape(n))
+  {
+    case 0:
+      if(ws->rcap > 0 && ccc_host::g_qp_packed())
+      {
+        // first pass: two CTAs per SM with a packed R of rcap columns; problems that need more are listed ...
+        ccc::QpParams P1 = P;
+        P1.rcap = ws->rcap < n ? ws->rcap : n;
+        P1.ovf_count = ws->counter + 2;
+        P1.ovf_list = ws->ovf_list;
+        const int grid2 = B < 2 * ws->n_sm ? B : 2 * ws->n_sm;
+        qp_solve_kernel<128, false, true><<<grid2, 128, ccc::QpSm<128, false, true>::bytes(n, P.ld, ws->rcap), st>>>(P1, ws->counter, nullptr);
+        ws->launches++;
+        if(P1.rcap >= n) break;
+        // ... and solved again from scratch with the full R (the grid finds an empty list in almost every call)
+        P.list = ws->ovf_list;
+        P.list_count = ws->counter + 2;
+        qp_solve_kernel<128, false, false><<<ws->n_sm, 128, ccc::QpSm<128, false, false>::bytes(n, P.ld), st>>>(P, ws->counter + 1, nullptr);
+      }
+      else
+        qp_solve_kernel<128, false, false><<<grid, 128, ccc::QpSm<128, false, false>::bytes(n, P.ld), st>>>(P, ws->counter, nullptr);
+      break;
+    case 1:
+      qp_solve_kernel<128, true, false><<<grid, 128, ccc::QpSm<128, true, false>::bytes(n, P.ld), st>>>(P, ws->counter, ws->gmat);
+      break;
+    default:
+      qp_solve_kernel<256, true, false><<<grid, 256, ccc::QpSm<256, true, false>::bytes(n, P.ld), st>>>(P, ws->counter, ws->gmat);
+      break;
+  }
+  ws->launches++;
+  if(!check(cudaGetLastError(), "launch qp_solve_kernel")) return CCC_ERR_CUDA;
+  return CCC_OK;
 }
 
 int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_t * res, int32_t mem, void * stream_v)
@@ -141,34 +228,19 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   if(!bt->d || (me && !bt->b) || (!reuse && (!bt->C || (me && !bt->A)))) return ccc_host::fail(CCC_ERR_INVALID, "null input");
   cudaStream_t st = mem == CCC_MEM_HOST ? ws->own_stream : reinterpret_cast<cudaStream_t>(stream_v);
   ws->launches = 0;
-  const double *Q = bt->Q, *A = bt->A, *C = bt->C, *c = bt->c, *b = bt->b, *d = bt->d;
-  double * o_x = res->x;
-  int *o_iters = res->iters, *o_status = res->status, *o_nact = res->n_active, *o_active = res->active;
-  if(mem == CCC_MEM_HOST)
+  const double *Q = bt->Q, *A = bt->A, *C = bt->C;
+#define CCC_H2D(dst, src, nbytes, stream) \
+  if(!check(cudaMemcpyAsync(dst, src, (nbytes), cudaMemcpyHostToDevice, stream), "H2D")) return CCC_ERR_CUDA
+#define CCC_D2H(dst, src, nbytes, stream) \
+  if((dst) && !check(cudaMemcpyAsync(dst, src, (nbytes), cudaMemcpyDeviceToHost, stream), "D2H")) return CCC_ERR_CUDA
+  if(mem == CCC_MEM_HOST && !reuse)
   {
-#define CCC_H2D(dst, src, nbytes) \
-  if(!check(cudaMemcpyAsync(dst, src, (nbytes), cudaMemcpyHostToDevice, st), "H2D")) return CCC_ERR_CUDA
-    if(!reuse)
-    {
-      CCC_H2D(ws->d_Q, Q, sizeof(double) * n * n);
-      if(me) CCC_H2D(ws->d_A, A, sizeof(double) * me * n);
-      CCC_H2D(ws->d_C, C, sizeof(double) * mi * n);
-    }
-    if(c) CCC_H2D(ws->d_c, c, sizeof(double) * B * n);
-    if(me) CCC_H2D(ws->d_b, b, sizeof(double) * B * me);
-    CCC_H2D(ws->d_d, d, sizeof(double) * B * mi);
-#undef CCC_H2D
+    CCC_H2D(ws->d_Q, Q, sizeof(double) * n * n, st);
+    if(me) CCC_H2D(ws->d_A, A, sizeof(double) * me * n, st);
+    CCC_H2D(ws->d_C, C, sizeof(double) * mi * n, st);
     Q = ws->d_Q;
     A = ws->d_A;
     C = ws->d_C;
-    if(c) c = ws->d_c;
-    b = ws->d_b;
-    d = ws->d_d;
-    o_x = res->x ? ws->d_x : nullptr;
-    o_iters = res->iters ? ws->d_iters : nullptr;
-    o_status = res->status ? ws->d_status : nullptr;
-    o_nact = res->n_active ? ws->d_nact : nullptr;
-    o_active = res->active ? ws->d_active : nullptr;
   }
   if(!reuse)
   {
@@ -186,46 +258,77 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   P.J0s = ws->J0s;
   P.At = ws->At;
   P.Ct = ws->Ct;
-  P.c = c;
-  P.b = b;
-  P.d = d;
   P.setup_ok = ws->ok_flag;
   P.max_iter = 1000;
   P.viol_tol = 1e-10;
-  P.out_x = o_x;
-  P.out_iters = o_iters;
-  P.out_status = o_status;
-  P.out_n_active = o_nact;
-  P.out_active = o_active;
-  if(!check(cudaMemsetAsync(ws->counter, 0, sizeof(int), st), "memset")) return CCC_ERR_CUDA;
-  const int grid = B < ws->n_sm ? B : ws->n_sm;
-  switch(qp_shape(n))
+  if(mem != CCC_MEM_HOST)
   {
-    case 0:
-      qp_solve_kernel<128, false><<<grid, 128, ccc::QpSm<128, false>::bytes(n, P.ld), st>>>(P, ws->counter, nullptr);
-      break;
-    case 1:
-      qp_solve_kernel<128, true><<<grid, 128, ccc::QpSm<128, true>::bytes(n, P.ld), st>>>(P, ws->counter, ws->gmat);
-      break;
-    default:
-      qp_solve_kernel<256, true><<<grid, 256, ccc::QpSm<256, true>::bytes(n, P.ld), st>>>(P, ws->counter, ws->gmat);
-      break;
+    P.c = bt->c;
+    P.b = bt->b;
+    P.d = bt->d;
+    P.out_x = res->x;
+    P.out_iters = res->iters;
+    P.out_status = res->status;
+    P.out_n_active = res->n_active;
+    P.out_active = res->active;
+    return qp_launch(ws, P, st);
   }
-  ws->launches++;
-  if(!check(cudaGetLastError(), "launch qp_solve_kernel")) return CCC_ERR_CUDA;
-  if(mem == CCC_MEM_HOST)
+  // Host buffers: the batch goes through in chunks on three streams — H2D of chunk k + 1 and D2H of chunk k - 1 run
+  // while chunk k is being solved (the per-problem vectors are 2.4 KB in, 1.2 KB out per QP at n = 100: for short
+  // solves the copies would otherwise be as long as the kernel).
+  const int chunk = B <= 16384 ? B : 32768;
+  const int nchunk = (B + chunk - 1) / chunk;
+  if(nchunk > ccc_qp_ws::kMaxChunks) return ccc_host::fail(CCC_ERR_ALLOC, "batch too large for the chunked host path");
+  if(!check(cudaEventRecord(ws->ev_setup, st), "event")) return CCC_ERR_CUDA;
+  if(!check(cudaStreamWaitEvent(ws->h2d_stream, ws->ev_setup, 0), "wait")) return CCC_ERR_CUDA; // orders after earlier calls
+  for(int k = 0; k < nchunk; k++)
   {
-#define CCC_D2H(dst, src, nbytes) \
-  if((dst) && !check(cudaMemcpyAsync(dst, src, (nbytes), cudaMemcpyDeviceToHost, st), "D2H")) return CCC_ERR_CUDA
-    CCC_D2H(res->x, ws->d_x, sizeof(double) * B * n);
-    CCC_D2H(res->iters, ws->d_iters, sizeof(int) * B);
-    CCC_D2H(res->status, ws->d_status, sizeof(int) * B);
-    CCC_D2H(res->n_active, ws->d_nact, sizeof(int) * B);
-    CCC_D2H(res->active, ws->d_active, sizeof(int) * B * n);
+    const size_t lo = (size_t)k * chunk;
+    const size_t nb = (size_t)(B - lo < (size_t)chunk ? B - lo : chunk);
+    cudaStream_t hs = nchunk > 1 ? ws->h2d_stream : st, ds = nchunk > 1 ? ws->d2h_stream : st;
+    if(bt->c) CCC_H2D(ws->d_c + lo * n, bt->c + lo * n, sizeof(double) * nb * n, hs);
+    if(me) CCC_H2D(ws->d_b + lo * me, bt->b + lo * me, sizeof(double) * nb * me, hs);
+    CCC_H2D(ws->d_d + lo * mi, bt->d + lo * mi, sizeof(double) * nb * mi, hs);
+    if(nchunk > 1)
+    {
+      if(!check(cudaEventRecord(ws->ev_h2d[k], hs), "event")) return CCC_ERR_CUDA;
+      if(!check(cudaStreamWaitEvent(st, ws->ev_h2d[k], 0), "wait")) return CCC_ERR_CUDA;
+    }
+    ccc::QpParams Pk = P;
+    Pk.B = (int)nb;
+    Pk.c = bt->c ? ws->d_c + lo * n : nullptr;
+    Pk.b = ws->d_b + lo * me;
+    Pk.d = ws->d_d + lo * mi;
+    Pk.out_x = res->x ? ws->d_x + lo * n : nullptr;
+    Pk.out_iters = res->iters ? ws->d_iters + lo : nullptr;
+    Pk.out_status = res->status ? ws->d_status + lo : nullptr;
+    Pk.out_n_active = res->n_active ? ws->d_nact + lo : nullptr;
+    Pk.out_active = res->active ? ws->d_active + lo * n : nullptr;
+    const int rc = qp_launch(ws, Pk, st);
+    if(rc != CCC_OK) return rc;
+    if(nchunk > 1)
+    {
+      if(!check(cudaEventRecord(ws->ev_solved[k], st), "event")) return CCC_ERR_CUDA;
+      if(!check(cudaStreamWaitEvent(ds, ws->ev_solved[k], 0), "wait")) return CCC_ERR_CUDA;
+    }
+    CCC_D2H(res->x ? res->x + lo * n : nullptr, ws->d_x + lo * n, sizeof(double) * nb * n, ds);
+    CCC_D2H(res->iters ? res->iters + lo : nullptr, ws->d_iters + lo, sizeof(int) * nb, ds);
+    CCC_D2H(res->status ? res->status + lo : nullptr, ws->d_status + lo, sizeof(int) * nb, ds);
+    CCC_D2H(res->n_active ? res->n_active + lo : nullptr, ws->d_nact + lo, sizeof(int) * nb, ds);
+    CCC_D2H(res->active ? res->active + lo * n : nullptr, ws->d_active + lo * n, sizeof(int) * nb * n, ds);
+  }
+#undef CCC_H2D
 #undef CCC_D2H
-    if(!check(cudaStreamSynchronize(st), "cudaStreamSynchronize")) return CCC_ERR_CUDA;
-  }
+  if(nchunk > 1 && !check(cudaStreamSynchronize(ws->d2h_stream), "cudaStreamSynchronize")) return CCC_ERR_CUDA;
+  if(!check(cudaStreamSynchronize(st), "cudaStreamSynchronize")) return CCC_ERR_CUDA;
   return CCC_OK;
+}
+
+/* Tuning hook (not part of the stable ABI): 0 = always one CTA per SM with the full R (round-1 kernel), 1 = packed R,
+ * two CTAs per SM, with the full-R fallback pass (default). */
+void ccc_qp_set_packed(int32_t on)
+{
+  ccc_host::g_qp_packed() = on != 0;
 }
 
 int32_t ccc_qp_last_launches(const ccc_qp_ws_t * ws)

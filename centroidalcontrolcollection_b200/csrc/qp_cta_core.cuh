@@ -12,6 +12,10 @@
 // J and R (n x ld doubles each) live in shared memory when they fit (kGlobal = false; ld odd so that
 // row- and column-wise accesses are conflict free; 176 KB at n = 100, one CTA per SM), else in a
 // per-CTA slab of global memory that stays L2 resident (kGlobal = true; LinearMpcXY, n = 240).
+// kPackedR: R only ever holds a q x q upper triangle (q = active constraints), so it is stored packed by columns with
+// room for P.rcap columns — at n = 100 J (80.8 KB) + packed R (62 columns, 15.6 KB) + vectors fit TWICE on an SM, and
+// two CTAs per SM hide each other's barrier and dependency stalls.  A problem whose active set outgrows the cap is
+// recorded in P.ovf_list and solved again from scratch by the full-R kernel (same arithmetic, so the same bits).
 #pragma once
 #include "warp_ctx.cuh"
 
@@ -32,6 +36,11 @@ struct QpParams
   const int * setup_ok; // [0]: Q positive definite; [1]: inequality rows i and i + mi/2 are exact negatives of each other
   int max_iter;
   double viol_tol;
+  int rcap = 0;              // kPackedR: columns the packed R can hold
+  int * ovf_count = nullptr; // kPackedR: number of problems whose active set outgrew rcap ...
+  int * ovf_list = nullptr;  // ... and their ids; the full-R kernel solves them again
+  const int * list = nullptr;       // solve problems list[0 .. *list_count) instead of 0 .. B-1 (the fallback pass)
+  const int * list_count = nullptr;
   double * out_x;
   int * out_iters;
   int * out_status;
@@ -56,20 +65,21 @@ CCC_DEV double givens_hypot(double a, double b)
 }
 
 /** Shared-memory layout of one QP (offsets in doubles). */
-template<int NT, bool kGlobal>
+template<int NT, bool kGlobal, bool kPackedR = false>
 struct QpSm
 {
-  int n, ld;
-  CCC_DEV QpSm(int n_, int ld_) : n(n_), ld(ld_) {}
-  CCC_DEV int mats() const { return kGlobal ? 0 : 2 * n * ld; }
+  int n, ld, rcap;
+  CCC_DEV QpSm(int n_, int ld_, int rcap_ = 0) : n(n_), ld(ld_), rcap(rcap_) {}
+  CCC_HD static int packed(int rcap) { return (rcap * (rcap + 1) / 2 + 1) & ~1; } // doubles of a packed R, even
+  CCC_DEV int mats() const { return kGlobal ? 0 : n * ld + (kPackedR ? packed(rcap) : n * ld); }
   CCC_DEV int J() const { return 0; }
   CCC_DEV int R() const { return n * ld; }
   CCC_DEV int vec(int k) const { return mats() + k * NT; } // x, z, d, np, r, u(+1 in next), tmp, gs, gx, rinv
   CCC_DEV int red() const { return vec(11); }               // 2 NT doubles: two trees / argmin values / scan ping-pong
-  CCC_DEV int ints() const { return vec(11) + 2 * NT; }     // int area: A[NT+4], red_i[NT], is_active[4 NT bytes], ctrl
-  static size_t bytes(int n, int ld)
+  CCC_DEV int ints() const { return vec(11) + 2 * NT; }     // int area (2 NT doubles): A[NT+4], red_i[NT], is_active[4 NT bytes], ctrl
+  static size_t bytes(int n, int ld, int rcap = 0)
   {
-    return (size_t)((kGlobal ? 0 : 2 * n * ld) + 11 * NT + 2 * NT + 4 * NT) * sizeof(double);
+    return (size_t)((kGlobal ? 0 : n * ld + (kPackedR ? packed(rcap) : n * ld)) + 11 * NT + 2 * NT + 2 * NT) * sizeof(double);
   }
 };
 
@@ -80,7 +90,7 @@ struct QpCtrl
   int l, ip, status;
 };
 
-template<int NT, bool kGlobal>
+template<int NT, bool kGlobal, bool kPackedR = false>
 struct QpCta
 {
   const QpParams & P;
@@ -99,7 +109,8 @@ struct QpCta
   CCC_DEV QpCta(const QpParams & p, double * smem, int prob, double * gmat = nullptr)
   : P(p), sm(smem), b(prob), tid(thread_id()), n(p.n), me(p.me), mi(p.mi), ld(p.ld), q(0), R_norm(1.0)
   {
-    QpSm<NT, kGlobal> L(n, ld);
+    static_assert(!(kGlobal && kPackedR), "the packed R exists to fit two CTAs' J into shared memory");
+    QpSm<NT, kGlobal, kPackedR> L(n, ld, p.rcap);
     J = (kGlobal ? gmat : sm) + L.J();
     R = (kGlobal ? gmat : sm) + L.R();
     x = sm + L.vec(0);
@@ -119,6 +130,9 @@ struct QpCta
     is_active = reinterpret_cast<unsigned char *>(ib + 2 * NT + 4); // 4 NT bytes
     ctrl = reinterpret_cast<QpCtrl *>(ib + 3 * NT + 4);
   }
+
+  /** R(i, j), i <= j < q (plus the sub-diagonal R(j + 1, j) in the full layout while a constraint is being deleted). */
+  CCC_DEV double & Rat(int i, int j) const { return kPackedR ? R[j * (j + 1) / 2 + i] : R[i * ld + j]; }
 
   CCC_DEV double normal(int id, int j) const
   {
@@ -293,7 +307,7 @@ struct QpCta
         const double ri = r[i];
         CCC_UNROLL
         for(int s = 0; s < kSlots; s++)
-          if(tid + 32 * s < i) a[s] = dfma(-R[(tid + 32 * s) * ld + i], ri, a[s]);
+          if(tid + 32 * s < i) a[s] = dfma(-Rat(tid + 32 * s, i), ri, a[s]);
       }
     }
     cta_sync();
@@ -385,10 +399,10 @@ struct QpCta
       }
     }
     cta_sync();
-    if(tid < q) R[tid * ld + q] = d[tid];
+    if(tid < q) Rat(tid, q) = d[tid];
     if(tid == 0)
     {
-      R[q * ld + q] = dq;
+      Rat(q, q) = dq;
       rinv[q] = 1.0 / dq;
     }
     q++;
@@ -410,7 +424,23 @@ struct QpCta
       }
     cta_sync();
     if(qq < 0) return;
-    if(tid < n)
+    // drop column qq: the columns to its right move one place left, which leaves one sub-diagonal entry per moved
+    // column (the old diagonal).  Full layout: it lands in R(i + 1, i); packed layout: in sub[i] (the gs vector, free
+    // outside add_constraint).
+    double * sub = gs;
+    if(kPackedR)
+    {
+      if(tid < q)
+        for(int i = (qq > tid - 1 ? qq : tid - 1); i < q - 1; i++)
+        {
+          const double v = Rat(tid, i + 1);
+          if(tid <= i)
+            Rat(tid, i) = v;
+          else
+            sub[i] = v;
+        }
+    }
+    else if(tid < n)
     {
       for(int i = qq; i < q - 1; i++) R[tid * ld + i] = R[tid * ld + i + 1];
     }
@@ -427,13 +457,13 @@ struct QpCta
       u[q] = 0.0;
     }
     cta_sync();
-    if(tid < q) R[tid * ld + q - 1] = 0.0;
+    if(!kPackedR && tid < q) R[tid * ld + q - 1] = 0.0;
     q--;
     cta_sync();
     if(q == 0) return;
     for(int j = qq; j < q; j++)
     {
-      double cc = R[j * ld + j], ss = R[(j + 1) * ld + j];
+      double cc = Rat(j, j), ss = kPackedR ? sub[j] : R[(j + 1) * ld + j];
       cta_sync(); // everyone has read the pivot pair before it is rewritten
       const double h = givens_hypot(cc, ss);
       if(dabs(h) < eps) continue;
@@ -451,15 +481,18 @@ struct QpCta
       const double xny = ss / (1.0 + cc);
       if(tid == 0)
       {
-        R[(j + 1) * ld + j] = 0.0;
-        R[j * ld + j] = rjj;
+        if(kPackedR)
+          sub[j] = 0.0;
+        else
+          R[(j + 1) * ld + j] = 0.0;
+        Rat(j, j) = rjj;
       }
       if(tid > j && tid < q)
       {
-        const double t1 = R[j * ld + tid], t2 = R[(j + 1) * ld + tid];
+        const double t1 = Rat(j, tid), t2 = Rat(j + 1, tid);
         const double a = dfma(t2, ss, t1 * cc);
-        R[j * ld + tid] = a;
-        R[(j + 1) * ld + tid] = dfma(xny, t1 + a, -t2);
+        Rat(j, tid) = a;
+        Rat(j + 1, tid) = dfma(xny, t1 + a, -t2);
       }
       if(tid < n)
       {
@@ -470,7 +503,7 @@ struct QpCta
       }
       cta_sync();
     }
-    if(tid >= qq && tid < q) rinv[tid] = 1.0 / R[tid * ld + tid];
+    if(tid >= qq && tid < q) rinv[tid] = 1.0 / Rat(tid, tid);
     cta_sync();
   }
 
@@ -626,6 +659,11 @@ struct QpCta
           status = 4;
           break;
         }
+        if(kPackedR && q >= P.rcap)
+        {
+          status = 5; // the packed R is full: this problem goes to the full-R kernel (never leaves the library)
+          break;
+        }
         iter++;
         if(iter > P.max_iter)
         {
@@ -725,6 +763,11 @@ struct QpCta
       if(P.out_iters) P.out_iters[b] = iter;
       if(P.out_status) P.out_status[b] = status;
       if(P.out_n_active) P.out_n_active[b] = q;
+#ifndef CCC_WARP_EMU
+      if(kPackedR && status == 5) P.ovf_list[atomicAdd(P.ovf_count, 1)] = b;
+#else
+      if(kPackedR && status == 5) P.ovf_list[(*P.ovf_count)++] = b;
+#endif
     }
     cta_sync();
   }

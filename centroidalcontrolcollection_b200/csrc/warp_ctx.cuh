@@ -23,6 +23,7 @@ int shfl_i(int v, int src);
 unsigned ballot(bool p);
 } // namespace ccc_emu
 #  define CCC_DEV inline
+#  define CCC_HD inline
 #  define CCC_DEV_NOINLINE
 #  define CCC_UNROLL
 #  define CCC_UNROLL_N(n)
@@ -64,6 +65,7 @@ inline void bulk_wait_all() {}
 #  include <cuda_runtime.h>
 #  include <stdint.h>
 #  define CCC_DEV __device__ __forceinline__
+#  define CCC_HD __host__ __device__ __forceinline__
 #  define CCC_DEV_NOINLINE __device__ __noinline__
 #  define CCC_UNROLL _Pragma("unroll")
 #  define CCC_STR_(x) #x

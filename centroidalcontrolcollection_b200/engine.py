@@ -83,6 +83,8 @@ def lib():
         L.ccc_qp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_qp_last_launches.restype = C.c_int32
         L.ccc_qp_last_launches.argtypes = [C.c_void_p]
+        L.ccc_qp_set_packed.restype = None
+        L.ccc_qp_set_packed.argtypes = [C.c_int32]
         L.ccc_preview_input.restype = C.c_int32
         L.ccc_preview_input.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]
         _LIB = L
@@ -207,6 +209,12 @@ class QpEngine:
     @property
     def last_launches(self):
         return int(lib().ccc_qp_last_launches(self._h))
+
+    @staticmethod
+    def set_packed(on):
+        """Tuning hook: 1 (default) = first pass with a packed R, two CTAs per SM, full-R pass for the problems whose
+        active set outgrows it; 0 = the full-R kernel alone (one CTA per SM, round 1)."""
+        lib().ccc_qp_set_packed(int(on))
 
 
 def qp_solver_for(engines=None):

@@ -358,6 +358,23 @@ extern "C" int32_t ccc_emu_ddp_srb_solve(const ccc_ddp_srb_batch_t * bt, const c
                                  });
 }
 
+namespace
+{
+int g_qp_rcap = 0, g_qp_last_overflows = -1;
+}
+
+/** Columns of the packed R of the first pass (0: full R only, the round-1 kernel). */
+extern "C" void ccc_emu_qp_set_rcap(int32_t rcap)
+{
+  g_qp_rcap = rcap;
+}
+
+/** Problems of the last ccc_emu_qp_solve that outgrew the packed R and went through the full-R pass (-1: no packed pass). */
+extern "C" int32_t ccc_emu_qp_last_overflows(void)
+{
+  return g_qp_last_overflows;
+}
+
 extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t * r)
 {
   const int n = bt->n, me = bt->n_eq, mi = bt->n_ineq, B = bt->batch, ld = n | 1;
@@ -367,8 +384,7 @@ extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t *
   ccc_emu::run_cta(ccc::kQpThreads, [&]() {
     ccc::qp_setup_cta(n, me, mi, bt->Q, bt->A, bt->C, Lg.data(), invd.data(), J0.data(), At.data(), Ct.data(), ok_flag_buf);
   });
-  ccc::QpParams P;
-  std::memset(&P, 0, sizeof(P));
+  ccc::QpParams P{};
   P.n = n;
   P.me = me;
   P.mi = mi;
@@ -411,12 +427,34 @@ extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t *
   }
   else
   {
+    // as qp.cu: first pass with the packed R (g_qp_rcap columns; the engine sizes it so that two CTAs fit on an SM),
+    // then the problems that outgrew it once more with the full R
+    std::vector<int> ovf_list(B, -1);
+    int ovf_count = 0;
+    const bool packed = g_qp_rcap > me;
+    if(packed)
+    {
+      ccc::QpParams P1 = P;
+      P1.rcap = g_qp_rcap < n ? g_qp_rcap : n;
+      P1.ovf_count = &ovf_count;
+      P1.ovf_list = ovf_list.data();
+      std::vector<double> smem(ccc::QpSm<128, false, true>::bytes(n, ld, P1.rcap) / sizeof(double) + 2, 0.0);
+      for(int b = 0; b < B; b++)
+        ccc_emu::run_cta(128, [&]() {
+          ccc::QpCta<128, false, true> cta(P1, smem.data(), b);
+          cta.solve();
+        });
+    }
     std::vector<double> smem(ccc::QpSm<128, false>::bytes(n, ld) / sizeof(double) + 2, 0.0);
-    for(int b = 0; b < B; b++)
+    for(int t = 0; t < (packed ? ovf_count : B); t++)
+    {
+      const int b = packed ? ovf_list[t] : t;
       ccc_emu::run_cta(128, [&]() {
         ccc::QpCta<128, false> cta(P, smem.data(), b);
         cta.solve();
       });
+    }
+    g_qp_last_overflows = packed ? ovf_count : -1;
   }
   return CCC_OK;
 }

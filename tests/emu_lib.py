@@ -40,8 +40,11 @@ def ddp_srb_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
     return res
 
 
-def qp_solve(problem_set):
+def qp_solve(problem_set, rcap=0):
+    """rcap > 0: as the engine, a first pass with a packed R of `rcap` columns and the full-R pass for the problems
+    that outgrow it (last_qp_overflows() tells how many did)."""
     L = lib()
+    L.ccc_emu_qp_set_rcap(int(rcap))
     L.ccc_emu_qp_solve.restype = C.c_int32
     L.ccc_emu_qp_solve.argtypes = [C.c_void_p] * 2
     res = problem_set.new_result()
@@ -60,3 +63,7 @@ def ddp_zmp_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
     bs, rs = problem_set.as_struct(), res.as_struct()
     assert L.ccc_emu_ddp_zmp_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs)) == 0
     return res
+
+
+def last_qp_overflows():
+    return int(lib().ccc_emu_qp_last_overflows())

@@ -10,11 +10,21 @@ import emu_lib
 FIELDS = ("x", "iters", "status", "n_active", "active")
 
 
-def _same(oracle, ps):
-    ref, got = oracle.qp_solve(ps), emu_lib.qp_solve(ps)
-    for f in FIELDS:
-        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+def _same(oracle, ps, rcaps=(0,)):
+    """rcaps: packed-R capacities of the first pass to emulate (0 = the full-R kernel alone)."""
+    ref = oracle.qp_solve(ps)
+    for rcap in rcaps:
+        got = emu_lib.qp_solve(ps, rcap=rcap)
+        for f in FIELDS:
+            assert np.array_equal(getattr(ref, f), getattr(got, f)), (f, rcap)
     return ref
+
+
+def ref_cap_tight(oracle, ps):
+    """A packed-R capacity that some but not all problems of the batch outgrow (peak active-set size is at least the
+    final one)."""
+    na = oracle.qp_solve(ps).n_active
+    return max(int(np.median(na)), ps.n_eq + 1)
 
 
 def test_random_qps_with_equalities_and_drops(oracle):
@@ -23,7 +33,9 @@ def test_random_qps_with_equalities_and_drops(oracle):
     M = rng.standard_normal((n, n))
     ps = QpProblemSet(M @ M.T + np.eye(n), rng.standard_normal((mi, n)), rng.uniform(0.05, 0.6, (B, mi)),
                       rng.standard_normal((2, n)), 0.1 * rng.standard_normal((B, 2)), 4 * rng.standard_normal((B, n)))
-    ref = _same(oracle, ps)
+    # packed R: roomy (no overflow), and so tight that some problems overflow into the full-R pass
+    ref = _same(oracle, ps, rcaps=(0, 24, int(ref_cap_tight(oracle, ps))))
+    assert emu_lib.last_qp_overflows() > 0
     assert (ref.status == 0).all()
     assert (ref.iters > ref.n_active - 2).any()  # at least one problem dropped a constraint on the way
     viol, dual = zip(*ps.kkt_residuals(ref.x))
@@ -36,7 +48,7 @@ def test_linear_mpc_zmp_structure(oracle):
     N = mpc.horizon_steps
     ip = np.stack([w["pos"][:, 0], w["vel"][:, 0], w["acc"][:, 0]], axis=1)
     lim = np.stack([w["lim_min"][:, :N, 0], w["lim_max"][:, :N, 0]], axis=2)
-    _same(oracle, mpc.build_qp(ip, lim))
+    _same(oracle, mpc.build_qp(ip, lim), rcaps=(0, 20, 4))
 
 
 def test_ismpc_structure(oracle):
@@ -45,7 +57,7 @@ def test_ismpc_structure(oracle):
     N = mpc.horizon_steps
     ps = mpc.build_qp(w["capture_point"][:, 1], w["planned_zmp"][:, 1], w["ref_zmp"][:, :N, 1],
                       np.stack([w["lim_min"][:, :N, 1], w["lim_max"][:, :N, 1]], axis=2))
-    ref = _same(oracle, ps)
+    ref = _same(oracle, ps, rcaps=(0, 16, 3))
     assert (ref.status == 0).all() and (ref.n_active >= 1).all()
 
 

@@ -65,8 +65,10 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--qp-packed", type=int, default=1, help="0: full-R QP kernel alone (round 1), 1: packed-R first pass (default)")
     args = ap.parse_args()
     build.build()
+    engine.QpEngine.set_packed(args.qp_packed)
     want = lambda k: not args.only or k in args.only.split(",")
 
     if want("2"):
@@ -80,9 +82,7 @@ def main():
         run = lambda q: mpc.plan_batch(q, w["capture_point"], w["planned_zmp"], w["ref_zmp"], w["lim_min"], w["lim_max"], w["control_dt"])
         print(json.dumps(qp_case("config 5: " + w["name"], mpc, run, 2, args.reps, not args.no_cpu)), flush=True)
     if want("xy"):
-        from test_emu_qp import _xy_problem_set
-
-        ps = _xy_problem_set(15, 1184)
+        ps = workloads.linear_mpc_xy_problem_set(15, 1184)
         print(json.dumps(qp_case("LinearMpcXY: reference test schedule, n = 240, 15 equalities, 480 bound rows, batch 1184", None,
                                  lambda q: q(ps), 1, args.reps, not args.no_cpu)), flush=True)
     if want("4"):

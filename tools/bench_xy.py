@@ -8,10 +8,10 @@ import numpy as np
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
 from centroidalcontrolcollection_b200 import engine  # noqa: E402
-from test_emu_qp import _xy_problem_set  # noqa: E402
+from centroidalcontrolcollection_b200 import workloads  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
-ps = _xy_problem_set(15, B)
+ps = workloads.linear_mpc_xy_problem_set(15, B)
 qp = engine.qp_solver_for()
 qp(ps)
 t0 = time.time()
