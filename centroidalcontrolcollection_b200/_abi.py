@@ -148,6 +148,24 @@ class QpResult(C.Structure):
                 ("active", C.c_void_p)]
 
 
+class LinearMpcXyBatch(C.Structure):
+    """ccc_linear_mpc_xy_batch_t"""
+
+    _fields_ = [("horizon_steps", C.c_int32), ("batch", C.c_int32), ("n_sched", C.c_int32), ("m_max", C.c_int32),
+                ("dt", C.c_double), ("mass", C.c_double), ("sched_id", C.c_void_p), ("m", C.c_void_p),
+                ("ridge", C.c_void_p), ("vertex", C.c_void_p), ("com_z", C.c_void_p), ("total_force_z", C.c_void_p),
+                ("ref_output", C.c_void_p), ("w_output", C.c_double * 6), ("w_force", C.c_double),
+                ("force_lo", C.c_double), ("force_hi", C.c_double), ("x0", C.c_void_p)]
+
+
+class LinearMpcXyResult(C.Structure):
+    """ccc_linear_mpc_xy_result_t"""
+
+    _fields_ = [("u", C.c_void_p), ("iters", C.c_void_p), ("status", C.c_void_p), ("n_active", C.c_void_p),
+                ("active", C.c_void_p), ("A_seq", C.c_void_p), ("B_seq", C.c_void_p), ("obj_mat", C.c_void_p),
+                ("obj_vec", C.c_void_p)]
+
+
 def ptr(a):
     """Address of a C-contiguous numpy array (or None)."""
     if a is None:

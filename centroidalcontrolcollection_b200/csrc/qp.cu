@@ -2,16 +2,19 @@
 // QP with shared matrices, one CTA per problem (qp_cta_core.cuh), persistent CTAs pulling problems
 // from an atomic counter.
 #include "../../include/ccc_b200.h"
-#include "common_host.cuh"
-#include "qp_cta_core.cuh"
+#include "qp_host.cuh"
 
 namespace
 {
+/** One CTA per matrix group g = blockIdx.x: Q, A and every output are per group, C (and its transpose) is shared
+ *  and written by group 0 only. */
 __global__ void __launch_bounds__(ccc::kQpThreads, 1) qp_setup_kernel(int n, int me, int mi, const double * Q, const double * A,
                                                                        const double * C, double * Lg, double * invd, double * J0,
                                                                        double * At, double * Ct, int * ok_flag, double * J0s)
 {
-  ccc::qp_setup_cta(n, me, mi, Q, A, C, Lg, invd, J0, At, Ct, ok_flag, J0s);
+  const size_t g = blockIdx.x, nn = (size_t)n * n;
+  ccc::qp_setup_cta(n, me, mi, Q + g * nn, A ? A + g * me * n : nullptr, C, Lg + g * nn, invd + g * n, J0 + g * nn, At + g * n * me, Ct,
+                    ok_flag + 4 * g, J0s ? J0s + g * n * (n | 1) : nullptr, g == 0);
 }
 
 template<int NT, bool kGlobal, bool kPackedR>
@@ -70,32 +73,12 @@ bool dev_alloc(T *& p, size_t n)
 }
 } // namespace
 
-struct ccc_qp_ws
+namespace ccc_host
 {
-  int n = 0, me = 0, mi = 0, max_batch = 0, device = 0, launches = 0;
-  bool have_setup = false; // the matrices of an earlier call are factorised and resident (reused when Q == NULL)
-  double *Lg = nullptr, *invd = nullptr, *J0 = nullptr, *J0s = nullptr, *At = nullptr, *Ct = nullptr;
-  int *ok_flag = nullptr, *counter = nullptr; // counter[0]: first pass, [1]: fallback pass, [2]: overflow count
-  int * ovf_list = nullptr;                      // problems whose active set outgrew the packed R of the first pass
-  int rcap = 0;                                  // columns of the packed R (0: one CTA per SM with the full R)
-  double * gmat = nullptr; // per-CTA J/R slabs when they do not fit in shared memory
-  int n_sm = 148;
-  // staging for CCC_MEM_HOST
-  double *d_Q = nullptr, *d_A = nullptr, *d_C = nullptr, *d_c = nullptr, *d_b = nullptr, *d_d = nullptr, *d_x = nullptr;
-  int *d_iters = nullptr, *d_status = nullptr, *d_nact = nullptr, *d_active = nullptr;
-  cudaStream_t own_stream = nullptr;
-  // chunked host path: copy streams and their events
-  static constexpr int kMaxChunks = 64;
-  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  cudaEvent_t ev_setup = nullptr, ev_h2d[kMaxChunks] = {}, ev_solved[kMaxChunks] = {};
-};
-
-extern "C" {
-
-ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max_batch)
+ccc_qp_ws * qp_ws_create(int n, int n_eq, int n_ineq, int max_batch, int max_groups, bool staging)
 {
   const int nt_threads = n > 128 ? 256 : 128;
-  if(n <= 0 || n > 256 || n_eq < 0 || n_eq > n || n_ineq <= 0 || n_eq + n_ineq > 4 * nt_threads || max_batch <= 0)
+  if(n <= 0 || n > 256 || n_eq < 0 || n_eq > n || n_ineq <= 0 || n_eq + n_ineq > 4 * nt_threads || max_batch <= 0 || max_groups <= 0)
   {
     ccc_host::set_error("ccc_qp_create: sizes outside the kernel's limits (n <= 256, n_eq <= n, n_eq + n_ineq <= 4 x threads)");
     return nullptr;
@@ -111,14 +94,19 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
   ws->me = n_eq;
   ws->mi = n_ineq;
   ws->max_batch = max_batch;
+  ws->max_groups = max_groups;
   cudaGetDevice(&ws->device);
-  const size_t N = n, ME = n_eq, MI = n_ineq, B = max_batch;
+  const size_t N = n, ME = n_eq, MI = n_ineq, B = max_batch, G = max_groups;
   bool ok = true;
-  ok = ok && dev_alloc(ws->Lg, N * N) && dev_alloc(ws->invd, N) && dev_alloc(ws->J0, N * N) && dev_alloc(ws->J0s, N * (N | 1));
-  ok = ok && dev_alloc(ws->At, N * ME) && dev_alloc(ws->Ct, N * MI) && dev_alloc(ws->ok_flag, 2) && dev_alloc(ws->counter, 4) && dev_alloc(ws->ovf_list, B);
-  ok = ok && dev_alloc(ws->d_Q, N * N) && dev_alloc(ws->d_A, N * ME) && dev_alloc(ws->d_C, N * MI);
-  ok = ok && dev_alloc(ws->d_c, B * N) && dev_alloc(ws->d_b, B * ME) && dev_alloc(ws->d_d, B * MI) && dev_alloc(ws->d_x, B * N);
-  ok = ok && dev_alloc(ws->d_iters, B) && dev_alloc(ws->d_status, B) && dev_alloc(ws->d_nact, B) && dev_alloc(ws->d_active, B * N);
+  ok = ok && dev_alloc(ws->Lg, G * N * N) && dev_alloc(ws->invd, G * N) && dev_alloc(ws->J0, G * N * N);
+  ok = ok && (qp_shape(n) != 0 || dev_alloc(ws->J0s, G * N * (N | 1))); // the TMA source of the shared-memory kernels
+  ok = ok && dev_alloc(ws->At, G * N * ME) && dev_alloc(ws->Ct, N * MI) && dev_alloc(ws->ok_flag, 4 * G) && dev_alloc(ws->counter, 4) && dev_alloc(ws->ovf_list, B);
+  if(staging)
+  {
+    ok = ok && dev_alloc(ws->d_Q, N * N) && dev_alloc(ws->d_A, N * ME) && dev_alloc(ws->d_C, N * MI);
+    ok = ok && dev_alloc(ws->d_c, B * N) && dev_alloc(ws->d_b, B * ME) && dev_alloc(ws->d_d, B * MI) && dev_alloc(ws->d_x, B * N);
+    ok = ok && dev_alloc(ws->d_iters, B) && dev_alloc(ws->d_status, B) && dev_alloc(ws->d_nact, B) && dev_alloc(ws->d_active, B * N);
+  }
   ok = ok && ccc_host::check(cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   ok = ok && ccc_host::check(cudaStreamCreateWithFlags(&ws->h2d_stream, cudaStreamNonBlocking), "cudaStreamCreate");
   ok = ok && ccc_host::check(cudaStreamCreateWithFlags(&ws->d2h_stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -155,6 +143,57 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
   return ws;
 }
 
+
+int qp_setup_launch(ccc_qp_ws * ws, int groups, const double * Q, const double * A, const double * C, cudaStream_t st)
+{
+  if(groups <= 0 || groups > ws->max_groups) return fail(CCC_ERR_ALLOC, "more matrix groups than the QP workspace holds");
+  qp_setup_kernel<<<groups, ccc::kQpThreads, 0, st>>>(ws->n, ws->me, ws->mi, Q, A, C, ws->Lg, ws->invd, ws->J0, ws->At, ws->Ct, ws->ok_flag,
+                                                     ws->J0s);
+  ws->launches++;
+  ws->have_setup = true;
+  if(!check(cudaGetLastError(), "launch qp_setup_kernel")) return CCC_ERR_CUDA;
+  return CCC_OK;
+}
+
+ccc::QpParams qp_params(const ccc_qp_ws * ws, int B, const int * grp)
+{
+  ccc::QpParams P;
+  const size_t n = ws->n;
+  P.n = ws->n;
+  P.me = ws->me;
+  P.mi = ws->mi;
+  P.B = B;
+  P.ld = ws->n | 1;
+  P.J0 = ws->J0;
+  P.J0s = ws->J0s;
+  P.At = ws->At;
+  P.Ct = ws->Ct;
+  P.setup_ok = ws->ok_flag;
+  P.max_iter = 1000;
+  P.viol_tol = 1e-10;
+  P.c = P.b = P.d = nullptr;
+  P.out_x = nullptr;
+  P.out_iters = P.out_status = P.out_n_active = P.out_active = nullptr;
+  P.grp = grp;
+  if(grp)
+  {
+    P.gs_J0 = n * n;
+    P.gs_J0s = n * (n | 1);
+    P.gs_At = n * ws->me;
+    P.gs_Ct = 0;
+    P.gs_ok = 4;
+  }
+  return P;
+}
+} // namespace ccc_host
+
+extern "C" {
+
+ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max_batch)
+{
+  return ccc_host::qp_ws_create(n, n_eq, n_ineq, max_batch, 1, true);
+}
+
 void ccc_qp_destroy(ccc_qp_ws_t * ws)
 {
   if(!ws) return;
@@ -174,11 +213,12 @@ void ccc_qp_destroy(ccc_qp_ws_t * ws)
   delete ws;
 }
 
+} // extern "C"
+
 /** Launch the solve kernels for problems [lo, lo + nb) of the batch described by P (device pointers, per-problem
  *  arrays already offset by the caller) on stream st. */
-static int qp_launch(ccc_qp_ws_t * ws, ccc::QpParams P, cudaStream_t st)
+int ccc_host::qp_launch(ccc_qp_ws * ws, ccc::QpParams P, cudaStream_t st)
 {
-  using ccc_host::check;
   const int n = P.n, B = P.B;
   if(!check(cudaMemsetAsync(ws->counter, 0, 4 * sizeof(int), st), "memset")) return CCC_ERR_CUDA;
   const int grid = B < ws->n_sm ? B : ws->n_sm;
@@ -216,6 +256,8 @@ static int qp_launch(ccc_qp_ws_t * ws, ccc::QpParams P, cudaStream_t st)
   return CCC_OK;
 }
 
+extern "C" {
+
 int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_t * res, int32_t mem, void * stream_v)
 {
   using ccc_host::check;
@@ -244,23 +286,10 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   }
   if(!reuse)
   {
-    qp_setup_kernel<<<1, ccc::kQpThreads, 0, st>>>(n, me, mi, Q, A, C, ws->Lg, ws->invd, ws->J0, ws->At, ws->Ct, ws->ok_flag, ws->J0s);
-    ws->launches++;
-    ws->have_setup = true;
+    const int rc = ccc_host::qp_setup_launch(ws, 1, Q, A, C, st);
+    if(rc != CCC_OK) return rc;
   }
-  ccc::QpParams P;
-  P.n = n;
-  P.me = me;
-  P.mi = mi;
-  P.B = B;
-  P.ld = n | 1;
-  P.J0 = ws->J0;
-  P.J0s = ws->J0s;
-  P.At = ws->At;
-  P.Ct = ws->Ct;
-  P.setup_ok = ws->ok_flag;
-  P.max_iter = 1000;
-  P.viol_tol = 1e-10;
+  ccc::QpParams P = ccc_host::qp_params(ws, B, nullptr);
   if(mem != CCC_MEM_HOST)
   {
     P.c = bt->c;
@@ -271,7 +300,7 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
     P.out_status = res->status;
     P.out_n_active = res->n_active;
     P.out_active = res->active;
-    return qp_launch(ws, P, st);
+    return ccc_host::qp_launch(ws, P, st);
   }
   // Host buffers: the batch goes through in chunks on three streams — H2D of chunk k + 1 and D2H of chunk k - 1 run
   // while chunk k is being solved (the per-problem vectors are 2.4 KB in, 1.2 KB out per QP at n = 100: for short
@@ -304,7 +333,7 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
     Pk.out_status = res->status ? ws->d_status + lo : nullptr;
     Pk.out_n_active = res->n_active ? ws->d_nact + lo : nullptr;
     Pk.out_active = res->active ? ws->d_active + lo * n : nullptr;
-    const int rc = qp_launch(ws, Pk, st);
+    const int rc = ccc_host::qp_launch(ws, Pk, st);
     if(rc != CCC_OK) return rc;
     if(nchunk > 1)
     {

@@ -33,7 +33,13 @@ struct QpParams
   const double * c;  // [B][n] or null
   const double * b;  // [B][me]
   const double * d;  // [B][mi]
-  const int * setup_ok; // [0]: Q positive definite; [1]: inequality rows i and i + mi/2 are exact negatives of each other
+  const int * setup_ok; // [0]: Q positive definite; [1]: inequality rows i and i + mi/2 are exact negatives of each other;
+                        // [2]: C is exactly [-I; I] (the box x_min <= x <= x_max of a QpCoeff, src/LinearMpcXY.cpp:177-178)
+  // matrix groups (LinearMpcXY over a sweep of schedules: one Q / A per schedule): problem b uses group grp[b] and the
+  // per-group arrays are gs_* doubles apart (0: shared by all groups); grp == nullptr: one group
+  const int * grp = nullptr;
+  size_t gs_J0 = 0, gs_J0s = 0, gs_At = 0, gs_Ct = 0;
+  int gs_ok = 0;
   int max_iter;
   double viol_tol;
   int rcap = 0;              // kPackedR: columns the packed R can hold
@@ -96,6 +102,9 @@ struct QpCta
   const QpParams & P;
   double * sm;
   int b, tid, n, me, mi, ld;
+  const double *gJ0, *gJ0s, *gAt, *gCt; // this problem's group of batch-shared matrices
+  const int * gok;
+  bool box = false; // C = [-I; I] (setup flag 2, read in solve())
   double *J, *R, *x, *z, *d, *np, *r, *u, *tmp, *gs, *gx, *rinv, *red;
   int *A, *red_i;
   unsigned char * is_active;
@@ -110,6 +119,12 @@ struct QpCta
   : P(p), sm(smem), b(prob), tid(thread_id()), n(p.n), me(p.me), mi(p.mi), ld(p.ld), q(0), R_norm(1.0)
   {
     static_assert(!(kGlobal && kPackedR), "the packed R exists to fit two CTAs' J into shared memory");
+    const size_t g = p.grp ? static_cast<size_t>(ldg(p.grp + prob)) : 0;
+    gJ0 = p.J0 + g * p.gs_J0;
+    gJ0s = p.J0s ? p.J0s + g * p.gs_J0s : nullptr;
+    gAt = p.At + g * p.gs_At;
+    gCt = p.Ct + g * p.gs_Ct;
+    gok = p.setup_ok + g * p.gs_ok;
     QpSm<NT, kGlobal, kPackedR> L(n, ld, p.rcap);
     J = (kGlobal ? gmat : sm) + L.J();
     R = (kGlobal ? gmat : sm) + L.R();
@@ -136,7 +151,7 @@ struct QpCta
 
   CCC_DEV double normal(int id, int j) const
   {
-    return id < me ? ldg(P.At + (size_t)j * me + id) : -ldg(P.Ct + (size_t)j * mi + (id - me));
+    return id < me ? ldg(gAt + (size_t)j * me + id) : -ldg(gCt + (size_t)j * mi + (id - me));
   }
 
   /** n_id . x + offset (>= 0 when satisfied) */
@@ -149,6 +164,9 @@ struct QpCta
   /** n_id . x */
   CCC_DEV double slack_dot(int id) const
   {
+    // C = [-I; I]: the chain over an identity row is x_i or -x_i (its zero terms leave the sum unchanged, `+ 0.0` is
+    // the chain's -0 -> +0)
+    if(box && id >= me) return id - me < n ? x[id - me] + 0.0 : (-x[id - me - n]) + 0.0;
     // the fma chain is sequential (oracle order); the loads (L2-resident constraint matrix) are not: the next
     // block of 16 is in flight while the chain consumes the current one
     constexpr int kBlk = 16;
@@ -512,7 +530,7 @@ struct QpCta
     const double inf = 1.0 / 0.0;
     const double eps = 2.220446049250313e-16;
     int status = 0, iter = 0;
-    if(ldg(P.setup_ok) == 0)
+    if(ldg(gok) == 0)
     {
       if(tid < n && P.out_x) P.out_x[(size_t)b * n + tid] = 0.0;
       if(tid == 0)
@@ -530,17 +548,17 @@ struct QpCta
     // one TMA bulk copy brings the pre-strided factor (n x ld doubles, 80.8 KB at n = 100) into shared memory
     // while the threads reset the bookkeeping; the previous problem's generic accesses to J are ordered before
     // the async-proxy write by the fence (every thread passed the barrier that ends solve())
-    by_tma = !kGlobal && mbar != nullptr && P.J0s != nullptr && ((n * ld) & 1) == 0;
+    by_tma = !kGlobal && mbar != nullptr && gJ0s != nullptr && ((n * ld) & 1) == 0;
     if(by_tma && tid == 0)
     {
       fence_proxy_async_smem();
       const unsigned bytes = static_cast<unsigned>(n * ld * sizeof(double));
       mbar_arrive_expect_tx(mbar, bytes);
-      tma_bulk_g2s(J, P.J0s, bytes, mbar);
+      tma_bulk_g2s(J, gJ0s, bytes, mbar);
     }
 #endif
     if(!by_tma)
-      for(int e = tid; e < n * n; e += NT) J[(e / n) * ld + (e % n)] = ldg(P.J0 + e);
+      for(int e = tid; e < n * n; e += NT) J[(e / n) * ld + (e % n)] = ldg(gJ0 + e);
     for(int e = tid; e < me + mi; e += NT) is_active[e] = 0;
     for(int e = tid; e <= n; e += NT)
     {
@@ -599,7 +617,8 @@ struct QpCta
       if(!add_constraint()) status = 1;
     }
 
-    const bool paired = ldg(P.setup_ok + 1) != 0;
+    const bool paired = ldg(gok + 1) != 0;
+    box = ldg(gok + 2) != 0;
     bool need_pick = true;
     int ip = -1;
     double s_ip = 0.0;
@@ -779,7 +798,8 @@ namespace ccc
 /** Batch-invariant setup, one CTA: L = chol(Q) (scratch Lg), J0 = L^-T, transposed A and C.
  *  Evaluation order: oracle/qp.hpp DenseQpShared::setup. */
 CCC_DEV void qp_setup_cta(int n, int me, int mi, const double * Q, const double * A, const double * C, double * Lg,
-                          double * invd, double * J0, double * At, double * Ct, int * ok_flag, double * J0s = nullptr)
+                          double * invd, double * J0, double * At, double * Ct, int * ok_flag, double * J0s = nullptr,
+                          bool write_ct = true)
 {
   const int tid = thread_id();
   if(tid == 0) *ok_flag = 1;
@@ -826,7 +846,8 @@ CCC_DEV void qp_setup_cta(int n, int me, int mi, const double * Q, const double 
     for(int e = tid; e < n * ld; e += kQpThreads) J0s[e] = (e % ld) < n ? J0[(e / ld) * n + (e % ld)] : 0.0;
   }
   for(int e = tid; e < n * me; e += kQpThreads) At[e] = A[(e % me) * n + e / me];
-  for(int e = tid; e < n * mi; e += kQpThreads) Ct[e] = C[(size_t)(e % mi) * n + e / mi];
+  if(write_ct)
+    for(int e = tid; e < n * mi; e += kQpThreads) Ct[e] = C[(size_t)(e % mi) * n + e / mi];
   // two-sided constraints lo <= G x <= hi arrive as C = [-G; G] (reference src/LinearMpcZmp.cpp:25,
   // src/IntrinsicallyStableMpc.cpp:42; the box rows of LinearMpcXY): if row i + mi/2 is the exact negative of
   // row i for every i, the solve kernel evaluates one product per pair (the other one is its exact negative)
@@ -842,6 +863,21 @@ CCC_DEV void qp_setup_cta(int n, int me, int mi, const double * Q, const double 
       same = same && (C[(size_t)(i + h) * n + j] == -C[(size_t)i * n + j]);
     }
     if(!same) ok_flag[1] = 0;
+  }
+  cta_sync();
+  // C == [-I; I] exactly (the bounds of a QpCoeff as inequality rows): the solve kernel reads x_i instead of
+  // streaming the identity
+  if(tid == 0) ok_flag[2] = (mi == 2 * n) ? 1 : 0;
+  cta_sync();
+  if(mi == 2 * n)
+  {
+    bool ident = true;
+    for(int e = tid; e < n * n; e += kQpThreads)
+    {
+      const int i = e / n, j = e % n;
+      ident = ident && (C[(size_t)i * n + j] == (i == j ? -1.0 : 0.0)) && (C[(size_t)(n + i) * n + j] == (i == j ? 1.0 : 0.0));
+    }
+    if(!ident) ok_flag[2] = 0;
   }
   cta_sync();
 }

@@ -23,6 +23,7 @@ EXPORTS = [
     "ccc_ddp_zmp_create", "ccc_ddp_zmp_destroy", "ccc_ddp_zmp_solve", "ccc_ddp_zmp_last_launches",
     "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
     "ccc_fp64_peak_tflops",
+    "ccc_linear_mpc_xy_create", "ccc_linear_mpc_xy_destroy", "ccc_linear_mpc_xy_solve", "ccc_linear_mpc_xy_last_launches",
 ]
 
 
@@ -87,6 +88,14 @@ def lib():
         L.ccc_qp_set_packed.argtypes = [C.c_int32]
         L.ccc_preview_input.restype = C.c_int32
         L.ccc_preview_input.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]
+        L.ccc_linear_mpc_xy_create.restype = C.c_void_p
+        L.ccc_linear_mpc_xy_create.argtypes = [C.c_int32] * 5
+        L.ccc_linear_mpc_xy_destroy.argtypes = [C.c_void_p]
+        L.ccc_linear_mpc_xy_destroy.restype = None
+        L.ccc_linear_mpc_xy_solve.restype = C.c_int32
+        L.ccc_linear_mpc_xy_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ccc_linear_mpc_xy_last_launches.restype = C.c_int32
+        L.ccc_linear_mpc_xy_last_launches.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -215,6 +224,40 @@ class QpEngine:
         """Tuning hook: 1 (default) = first pass with a packed R, two CTAs per SM, full-R pass for the problems whose
         active set outgrows it; 0 = the full-R kernel alone (one CTA per SM, round 1)."""
         lib().ccc_qp_set_packed(int(on))
+
+
+class LinearMpcXyEngine:
+    """Device pipeline of CCC::LinearMpcXY::planOnce over a sweep of schedules (ccc_linear_mpc_xy_*): stage models,
+    closed-form discretisation, condensing, the tensor-core B_seq' W B_seq, per-problem vectors and the QP, with one
+    QP factorisation per schedule.  One workspace per QP shape (n, n_eq)."""
+
+    def __init__(self, horizon_steps, n, n_eq, max_batch, max_sched):
+        self._h = lib().ccc_linear_mpc_xy_create(int(horizon_steps), int(n), int(n_eq), int(max_batch), int(max_sched))
+        if not self._h:
+            raise EngineError(f"ccc_linear_mpc_xy_create failed: {last_error()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ccc_linear_mpc_xy_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def solve(self, sweep, intermediates=False, result=None):
+        """Host buffers in / out for a linear_mpc_xy.XySweepProblemSet."""
+        res = result if result is not None else sweep.new_result(intermediates)
+        bs, rs = sweep.as_struct(), res.as_struct()
+        _check(lib().ccc_linear_mpc_xy_solve(self._h, C.addressof(bs), C.addressof(rs), _abi.CCC_MEM_HOST, None),
+               "ccc_linear_mpc_xy_solve")
+        return res
+
+    def solve_device(self, batch_struct, result_struct, stream=0):
+        _check(lib().ccc_linear_mpc_xy_solve(self._h, C.addressof(batch_struct), C.addressof(result_struct),
+                                             _abi.CCC_MEM_DEVICE, C.c_void_p(stream)), "ccc_linear_mpc_xy_solve")
+
+    @property
+    def last_launches(self):
+        return int(lib().ccc_linear_mpc_xy_last_launches(self._h))
 
 
 def qp_solver_for(engines=None):

@@ -10,6 +10,8 @@ call, like planOnce does, reference :96-115); the initial states differ per prob
 """
 import numpy as np
 
+from . import _abi
+from ._abi import ptr
 from .linear_models import G, StateSpaceModel, VariantSequentialExtension
 from .qp import QpProblemSet
 
@@ -110,3 +112,99 @@ class LinearMpcXY:
         res = qp_solve(ps)
         self.last_problem, self.last_result = ps, res
         return res.x[:, :self.first_input_dim]
+
+
+class XySweepResultArrays:
+    """ccc_linear_mpc_xy_result_t with every optional output allocated."""
+
+    def __init__(self, batch, n_sched, horizon_steps, n, intermediates=True):
+        self.u = np.zeros((batch, n))
+        self.iters = np.zeros(batch, dtype=np.int32)
+        self.status = np.zeros(batch, dtype=np.int32)
+        self.n_active = np.zeros(batch, dtype=np.int32)
+        self.active = np.full((batch, n), -1, dtype=np.int32)
+        rows = 6 * horizon_steps
+        self.A_seq = np.zeros((n_sched, rows, 6)) if intermediates else None
+        self.B_seq = np.zeros((n_sched, rows, n)) if intermediates else None
+        self.obj_mat = np.zeros((n_sched, n, n)) if intermediates else None
+        self.obj_vec = np.zeros((batch, n)) if intermediates else None
+
+    def as_struct(self):
+        r = _abi.LinearMpcXyResult()
+        r.u, r.iters, r.status, r.n_active, r.active = (ptr(self.u), ptr(self.iters), ptr(self.status), ptr(self.n_active),
+                                                        ptr(self.active))
+        r.A_seq, r.B_seq, r.obj_mat, r.obj_vec = ptr(self.A_seq), ptr(self.B_seq), ptr(self.obj_mat), ptr(self.obj_vec)
+        return r
+
+    def active_sets(self):
+        return [tuple(sorted(int(v) for v in row[:k])) for row, k in zip(self.active, self.n_active)]
+
+
+class XySweepProblemSet:
+    """Flat form of LinearMpcXY::planOnce for B initial states over S sampled schedules
+    (ccc_linear_mpc_xy_batch_t): everything after the callback sampling happens behind the C-ABI."""
+
+    def __init__(self, mpc, horizon_steps, n_sched, m_max=32):
+        self.mpc, self.N, self.S, self.m_max = mpc, int(horizon_steps), int(n_sched), int(m_max)
+        N, S = self.N, self.S
+        self.m = np.zeros((S, N), dtype=np.int32)
+        self.ridge = np.zeros((S, N, m_max, 3))
+        self.vertex = np.zeros((S, N, m_max, 3))
+        self.com_z = np.zeros((S, N))
+        self.total_force_z = np.zeros((S, N))
+        self.ref_output = np.zeros((S, N, 6))
+        self.sched_id = np.zeros(0, dtype=np.int32)
+        self.x0 = np.zeros((0, 6))
+
+    def sample(self, s, motion_param_func, ref_data_func, current_time):
+        """What planOnce reads through its callbacks (src/LinearMpcXY.cpp:104-110) into schedule s."""
+        for i in range(self.N):
+            t = current_time + i * self.mpc.horizon_dt
+            mp = motion_param_func(t)
+            k = len(mp.ridge)
+            assert k <= self.m_max
+            self.m[s, i] = k
+            self.ridge[s, i, :k] = mp.ridge
+            self.vertex[s, i, :k] = mp.vertex
+            self.com_z[s, i], self.total_force_z[s, i] = mp.com_z, mp.total_force_z
+            self.ref_output[s, i] = to_state(self.mpc.mass, *ref_data_func(t))
+
+    def set_initial_states(self, x0, sched_id):
+        self.x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, 6)
+        self.sched_id = np.ascontiguousarray(sched_id, dtype=np.int32)
+        assert len(self.x0) == len(self.sched_id)
+
+    @property
+    def n(self):
+        return int(self.m[0].sum())
+
+    @property
+    def n_eq(self):
+        return int((self.m[0] > 0).sum())
+
+    @property
+    def batch(self):
+        return len(self.x0)
+
+    def as_struct(self):
+        b = _abi.LinearMpcXyBatch()
+        b.horizon_steps, b.batch, b.n_sched, b.m_max = self.N, self.batch, self.S, self.m_max
+        b.dt, b.mass = self.mpc.horizon_dt, self.mpc.mass
+        b.sched_id, b.m, b.ridge, b.vertex = ptr(self.sched_id), ptr(self.m), ptr(self.ridge), ptr(self.vertex)
+        b.com_z, b.total_force_z, b.ref_output, b.x0 = ptr(self.com_z), ptr(self.total_force_z), ptr(self.ref_output), ptr(self.x0)
+        w = self.mpc.weight_param.output_weight(1)
+        for i in range(6):
+            b.w_output[i] = w[i]
+        b.w_force = self.mpc.weight_param.force
+        b.force_lo, b.force_hi = self.mpc.force_range
+        return b
+
+    def new_result(self, intermediates=True):
+        return XySweepResultArrays(self.batch, self.S, self.N, self.n, intermediates)
+
+    def host_problem(self, s, idx):
+        """The QpProblemSet the host path (build_qp: scipy expm, numpy condensing) makes of schedule s and the
+        initial states idx — the independent check of the closed-form discretisation."""
+        mps = [MotionParam(self.com_z[s, i], self.total_force_z[s, i], self.vertex[s, i, :self.m[s, i]],
+                           self.ridge[s, i, :self.m[s, i]]) for i in range(self.N)]
+        return self.mpc.build_qp(mps, self.ref_output[s].reshape(-1), self.x0[idx])

@@ -276,3 +276,51 @@ def linear_mpc_xy_problem_set(horizon_steps=15, batch=1184):
     ts = [w["t0"] + i * w["horizon_dt"] for i in range(horizon_steps)]
     ref = np.concatenate([linear_mpc_xy.to_state(w["mass"], *w["ref_data_func"](t)) for t in ts])
     return mpc.build_qp([w["motion_param_func"](t) for t in ts], ref, w["x0"])
+
+
+def linear_mpc_xy_sweep(n_sched=64, per_sched=16, horizon_steps=15, seed=20260106):
+    """A sweep of contact / reference schedules for LinearMpcXY (linear_mpc_xy.XySweepProblemSet): the reference
+    test's scenario (tests/src/TestLinearMpcXY.cpp:17-83) sampled at n_sched start times t0 = 2.0 + 4.2 s / n_sched
+    (so the horizons see every contact change), each with its own foot-width scale U(0.8, 1.2), CoM height
+    U(0.9, 1.1) and vertical force (1 + U(-0.1, 0.1)) m g per stage, times per_sched perturbed initial states as
+    in linear_mpc_xy_batch.  Every stage has one rectangle: n = 16 x horizon_steps, one equality per stage."""
+    from . import contact, linear_mpc_xy
+    from .linear_models import G
+
+    mass, horizon_dt = 100.0, 0.1
+    rng = np.random.default_rng(seed)
+    mpc = linear_mpc_xy.LinearMpcXY(mass, horizon_dt, horizon_steps)
+    sweep = linear_mpc_xy.XySweepProblemSet(mpc, horizon_steps, n_sched, m_max=16)
+    x0, sid = [], []
+    for s in range(n_sched):
+        t0 = 2.0 + 4.2 * s / n_sched
+        wy, cz = rng.uniform(0.8, 1.2), rng.uniform(0.9, 1.1)
+        fz_scale = 1.0 + rng.uniform(-0.1, 0.1, horizon_steps)
+
+        def motion_param(t, wy=wy, cz=cz, fz_scale=fz_scale, t0=t0):
+            if t < 3.0:
+                rect = ((0.9, -0.15 * wy), (1.1, 0.15 * wy))
+            elif t < 4.0:
+                rect = ((0.9, 0.05 * wy), (1.1, 0.15 * wy))
+            elif t < 5.0:
+                rect = ((1.15, -0.15 * wy), (1.35, -0.05 * wy))
+            elif t < 6.0:
+                rect = ((1.4, 0.05 * wy), (1.6, 0.15 * wy))
+            else:
+                rect = ((1.4, -0.15 * wy), (1.6, 0.15 * wy))
+            vertex, ridge = contact.contact_from_rect(*rect)
+            k = min(max(int(round((t - t0) / horizon_dt)), 0), horizon_steps - 1)
+            return linear_mpc_xy.MotionParam(cz, fz_scale[k] * mass * G, vertex, ridge)
+
+        def ref_data(t, wy=wy):
+            pos = (1.0, 0.0) if t < 3.0 else (1.0, 0.1 * wy) if t < 4.0 else (1.25, -0.1 * wy) if t < 5.0 else (1.5, 0.1 * wy) if t < 6.0 else (1.5, 0.0)
+            return np.array(pos), np.zeros(2), np.zeros(2)
+
+        sweep.sample(s, motion_param, ref_data, t0)
+        pos = ref_data(t0)[0][None, :] + rng.uniform(-0.03, 0.03, (per_sched, 2))
+        vel = rng.uniform(-0.15, 0.15, (per_sched, 2))
+        am = rng.uniform(-0.5, 0.5, (per_sched, 2))
+        x0.append(linear_mpc_xy.to_state(mass, pos, vel, am))
+        sid.append(np.full(per_sched, s, dtype=np.int32))
+    sweep.set_initial_states(np.concatenate(x0), np.concatenate(sid))
+    return sweep

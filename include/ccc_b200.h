@@ -301,6 +301,64 @@ void ccc_qp_destroy(ccc_qp_ws_t * ws);
 int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * batch, ccc_qp_result_t * result, int32_t mem, void * stream);
 int32_t ccc_qp_last_launches(const ccc_qp_ws_t * ws);
 
+/* ---- CCC::LinearMpcXY::planOnce on the device, over a sweep of contact / reference schedules -------------
+ * Everything LinearMpcXY::planOnce does after sampling its callbacks (reference src/LinearMpcXY.cpp:102-181),
+ * for B initial states that use S sampled schedules (problem b uses sched_id[b]):
+ *  per stage     Model::Model (:59-83) and StateSpaceModel::calcDiscMatrix (include/CCC/StateSpaceModel.h:164-216);
+ *                the model's A is nilpotent (A^3 = 0, no offset vector), so the zero-order hold is the finite
+ *                polynomial Ad = I + A dt + A^2 dt^2/2, Bd = (I dt + A dt^2/2 + A^2 dt^3/6) B;
+ *  per schedule  VariantSequentialExtension<6>::setup (include/CCC/VariantSequentialExtension.h:110-186): A_seq, B_seq;
+ *                obj_mat = B_seq' W B_seq + w_force I (src :141-144) as an FP64 tensor-core GEMM; eq_mat (:149-176);
+ *  per problem   obj_vec = -B_seq' W (ref_output_seq - A_seq x) (:145-146), eq_vec, x_min / x_max (:177-178);
+ *  QP            qp_solver_->solve(qp_coeff_) (:181) on the ccc_qp engine, one factorisation per schedule.
+ * The schedules of one call must agree in the QP's shape: sum_k m[s][k] = n and the number of contact stages
+ * (m[s][k] > 0) = n_eq for every s; group a sweep by shape on the host.  Stage tables as for DdpCentroidal. */
+typedef struct
+{
+  int32_t horizon_steps; /* N */
+  int32_t batch;         /* B */
+  int32_t n_sched;       /* S */
+  int32_t m_max;         /* row stride of ridge / vertex, any value >= max m */
+  double dt;             /* horizon_dt [s] */
+  double mass;           /* [kg] */
+  const int32_t * sched_id;     /* [B] */
+  const int32_t * m;            /* [S][N] ridges of each stage's contacts (0: no contact) */
+  const double * ridge;         /* [S][N][m_max][3] */
+  const double * vertex;        /* [S][N][m_max][3] */
+  const double * com_z;         /* [S][N] MotionParam.com_z */
+  const double * total_force_z; /* [S][N] MotionParam.total_force_z */
+  const double * ref_output;    /* [S][N][6] RefData::toOutput(mass) (src :33-38) */
+  double w_output[6];   /* WeightParam::outputWeight of one stage (src :45-50) */
+  double w_force;       /* WeightParam.force */
+  double force_lo, force_hi; /* force_range_ (src :91) */
+  const double * x0;    /* [B][6] InitialParam::toState(mass) (src :26-31) */
+} ccc_linear_mpc_xy_batch_t;
+
+typedef struct
+{
+  double * u;         /* [B][n] force scales of every stage; the first m[s][0] entries are planOnce's return value */
+  int32_t * iters;    /* [B] as ccc_qp_result_t */
+  int32_t * status;   /* [B] */
+  int32_t * n_active; /* [B] */
+  int32_t * active;   /* [B][n] */
+  /* intermediate results (optional; what the parity tests compare stage by stage) */
+  double * A_seq;     /* [S][6N][6] */
+  double * B_seq;     /* [S][6N][n] */
+  double * obj_mat;   /* [S][n][n]  */
+  double * obj_vec;   /* [B][n]     */
+} ccc_linear_mpc_xy_result_t;
+
+typedef struct ccc_linear_mpc_xy_ws ccc_linear_mpc_xy_ws_t;
+/* n = total input dimension, n_eq = contact stages of every schedule of the calls to come (n <= 256). */
+ccc_linear_mpc_xy_ws_t * ccc_linear_mpc_xy_create(int32_t horizon_steps, int32_t n, int32_t n_eq, int32_t max_batch, int32_t max_sched);
+void ccc_linear_mpc_xy_destroy(ccc_linear_mpc_xy_ws_t * ws);
+int32_t ccc_linear_mpc_xy_solve(ccc_linear_mpc_xy_ws_t * ws,
+                                const ccc_linear_mpc_xy_batch_t * batch,
+                                ccc_linear_mpc_xy_result_t * result,
+                                int32_t mem,
+                                void * stream);
+int32_t ccc_linear_mpc_xy_last_launches(const ccc_linear_mpc_xy_ws_t * ws);
+
 /* ---- CCC::PreviewControl<3,1,1>::calcOptimalInput ------------------------------------------------
  * Batched online part of preview control:  u[b] = -K x[b] + F ref_seq[b]   (gains K (1x3), F (1xN) shared).
  * Replaces: PreviewControl::calcOptimalInput (reference include/CCC/PreviewControl.h:86-89) as called from

@@ -51,6 +51,8 @@ class Oracle:
             L.ccc_oracle_hardware_threads.restype = C.c_int32
             L.ccc_oracle_qp_solve.restype = C.c_int32
             L.ccc_oracle_qp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+            L.ccc_oracle_linear_mpc_xy_solve.restype = C.c_int32
+            L.ccc_oracle_linear_mpc_xy_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
             L.ccc_oracle_set_choices.argtypes = [C.c_uint32]
             L.ccc_oracle_set_choices.restype = None
             L.ccc_oracle_is_textbook.restype = C.c_int32
@@ -93,6 +95,15 @@ class Oracle:
             raise RuntimeError(f"oracle returned {rc}")
         return res
 
+    def linear_mpc_xy_solve(self, sweep, n_threads=1, intermediates=True):
+        """Run the oracle on a centroidalcontrolcollection_b200.linear_mpc_xy.XySweepProblemSet."""
+        res = sweep.new_result(intermediates)
+        bs, rs = sweep.as_struct(), res.as_struct()
+        rc = self.lib().ccc_oracle_linear_mpc_xy_solve(C.addressof(bs), C.addressof(rs), int(n_threads))
+        if rc != 0:
+            raise RuntimeError(f"oracle returned {rc}")
+        return res
+
     def ddp_centroidal_closed_loop(self, loop, cfg, n_threads=1):
         """Run the oracle's closed loop on a centroidalcontrolcollection_b200.closed_loop.CentroidalLoop."""
         res = loop.new_result()
@@ -121,4 +132,5 @@ ddp_centroidal_solve = _CANON.ddp_centroidal_solve
 ddp_srb_solve = _CANON.ddp_srb_solve
 ddp_zmp_solve = _CANON.ddp_zmp_solve
 qp_solve = _CANON.qp_solve
+linear_mpc_xy_solve = _CANON.linear_mpc_xy_solve
 ddp_centroidal_closed_loop = _CANON.ddp_centroidal_closed_loop

@@ -10,6 +10,7 @@
 #include "centroidal.hpp"
 #include "srb.hpp"
 #include "qp.hpp"
+#include "xy.hpp"
 #include "zmp.hpp"
 
 #include <atomic>
@@ -510,6 +511,70 @@ int32_t ccc_oracle_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t * r, int3
         r->active[static_cast<size_t>(b) * n + i] = i < static_cast<int>(res.active.size()) ? res.active[i] : -1;
   });
   return CCC_OK;
+}
+
+/** Same contract as ccc_linear_mpc_xy_solve with host pointers (oracle/xy.hpp); n_threads host threads. */
+int32_t ccc_oracle_linear_mpc_xy_solve(const ccc_linear_mpc_xy_batch_t * bt, ccc_linear_mpc_xy_result_t * r, int32_t n_threads)
+{
+  if(!bt || !r || bt->horizon_steps <= 0 || bt->n_sched <= 0 || bt->batch < 0) return CCC_ERR_INVALID;
+  const int S = bt->n_sched, B = bt->batch, N = bt->horizon_steps, rows = 6 * N;
+  std::vector<XySchedule> sch(S);
+  std::vector<DenseQpShared> shared(S);
+  parallelFor(S, n_threads, [&](int s) {
+    sch[s].build(*bt, s);
+    const int n = sch[s].n;
+    DenseQpShared & Q = shared[s];
+    Q.n = n;
+    Q.me = sch[s].n_eq;
+    Q.mi = 2 * n;
+    Q.Q = sch[s].H;
+    Q.A = sch[s].Aeq;
+    Q.C.assign(static_cast<size_t>(2 * n) * n, 0.0);
+    for(int j = 0; j < n; j++)
+    {
+      Q.C[static_cast<size_t>(j) * n + j] = -1.0;
+      Q.C[static_cast<size_t>(n + j) * n + j] = 1.0;
+    }
+    Q.setup();
+  });
+  const int n = sch[0].n, me = sch[0].n_eq;
+  for(int s = 1; s < S; s++)
+    if(sch[s].n != n || sch[s].n_eq != me) return CCC_ERR_INVALID;
+  if(n <= 0 || n > 256) return CCC_ERR_INVALID;
+  for(int s = 0; s < S; s++)
+  {
+    if(r->A_seq) std::copy(sch[s].A_seq.begin(), sch[s].A_seq.end(), r->A_seq + static_cast<size_t>(s) * rows * 6);
+    if(r->B_seq) std::copy(sch[s].B_seq.begin(), sch[s].B_seq.end(), r->B_seq + static_cast<size_t>(s) * rows * n);
+    if(r->obj_mat) std::copy(sch[s].H.begin(), sch[s].H.end(), r->obj_mat + static_cast<size_t>(s) * n * n);
+  }
+  std::atomic<int> bad(0);
+  parallelFor(B, n_threads, [&](int b) {
+    const int s = bt->sched_id[b];
+    if(s < 0 || s >= S)
+    {
+      bad = 1;
+      return;
+    }
+    std::vector<double> g(n), d(2 * n);
+    sch[s].objVec(*bt, s, bt->x0 + static_cast<size_t>(b) * 6, g.data());
+    for(int j = 0; j < n; j++)
+    {
+      d[j] = -bt->force_lo;
+      d[n + j] = bt->force_hi;
+    }
+    if(r->obj_vec) std::copy(g.begin(), g.end(), r->obj_vec + static_cast<size_t>(b) * n);
+    DenseQpSolver solver(shared[s]);
+    DenseQpResult res = solver.solve(g.data(), me ? sch[s].beq.data() : nullptr, d.data());
+    if(r->u)
+      for(int i = 0; i < n; i++) r->u[static_cast<size_t>(b) * n + i] = res.x[i];
+    if(r->iters) r->iters[b] = res.iters;
+    if(r->status) r->status[b] = res.status;
+    if(r->n_active) r->n_active[b] = static_cast<int32_t>(res.active.size());
+    if(r->active)
+      for(int i = 0; i < n; i++)
+        r->active[static_cast<size_t>(b) * n + i] = i < static_cast<int>(res.active.size()) ? res.active[i] : -1;
+  });
+  return bad ? CCC_ERR_INVALID : CCC_OK;
 }
 
 /** u[b] = -K x[b] + F ref_seq[b] (reference include/CCC/PreviewControl.h:86-89) in canonical order:

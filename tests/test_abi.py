@@ -35,6 +35,9 @@ def test_struct_sizes_match_header():
     # ccc_ddp_centroidal_loop_t: 4 int32, 3 double, 4 int32, 5 pointers, 10 + 9 + 2 double, pointer, 2 int32, 3 double
     assert C.sizeof(_abi.DdpCentroidalLoop) == 4 * 4 + 3 * 8 + 4 * 4 + 5 * 8 + 21 * 8 + 8 + 2 * 4 + 3 * 8
     assert C.sizeof(_abi.DdpCentroidalLoopResult) == 3 * 8
+    # ccc_linear_mpc_xy_batch_t: 4 int32, 2 double, 7 pointers, 6 + 1 + 2 double, pointer; result: 9 pointers
+    assert C.sizeof(_abi.LinearMpcXyBatch) == 4 * 4 + 2 * 8 + 7 * 8 + 9 * 8 + 8
+    assert C.sizeof(_abi.LinearMpcXyResult) == 9 * 8
 
 
 def test_default_config_matches_host_mirror():

@@ -109,3 +109,34 @@ def test_linear_mpc_xy_closed_loop(oracle):
     assert np.linalg.norm(sim.pos - ref_pos) < 0.1
     assert np.linalg.norm(sim.vel) < 0.1
     assert np.linalg.norm(sim.angular_momentum) < 0.1
+
+
+def test_xy_sweep_oracle_vs_host_path(oracle):
+    """oracle/xy.hpp (closed-form zero-order hold of the nilpotent model, canonical condensing, obj_mat / obj_vec)
+    against the independent host path (scipy expm of the augmented matrix as StateSpaceModel::calcDiscMatrix does,
+    numpy condensing): the matrices agree to rounding, and the QP solutions / active sets of the two agree."""
+    from centroidalcontrolcollection_b200 import workloads
+
+    sweep = workloads.linear_mpc_xy_sweep(n_sched=6, per_sched=3)
+    res = oracle.linear_mpc_xy_solve(sweep, n_threads=4)
+    assert (res.status == 0).all()
+    n = sweep.n
+    assert n == 240 and sweep.n_eq == 15
+    for s in range(sweep.S):
+        idx = np.where(sweep.sched_id == s)[0]
+        ps = sweep.host_problem(s, idx)
+        scale = np.abs(ps.Q).max()
+        assert np.abs(res.obj_mat[s] - ps.Q).max() < 1e-12 * scale
+        assert np.abs(res.obj_vec[idx] - ps.c).max() < 1e-11 * np.abs(ps.c).max()
+        ref = oracle.qp_solve(ps)
+        assert (ref.status == 0).all()
+        assert np.abs(ref.x - res.u[idx]).max() < 1e-6 * np.abs(ref.x).max()
+        assert ref.active_sets() == [res.active_sets()[i] for i in idx]
+    # the condensed prediction equals the iterated discrete model (TestVariantSequentialExtension's identity)
+    s, b = 2, int(np.where(sweep.sched_id == 2)[0][0])
+    ps = sweep.host_problem(s, [b])
+    x_pred = res.A_seq[s] @ sweep.x0[b] + res.B_seq[s] @ res.u[b]
+    models = [linear_mpc_xy.Model(sweep.mpc.mass, linear_mpc_xy.MotionParam(
+        sweep.com_z[s, i], sweep.total_force_z[s, i], sweep.vertex[s, i, :16], sweep.ridge[s, i, :16])).calc_disc_matrix(0.1)
+        for i in range(sweep.N)]
+    assert np.linalg.norm(x_pred - _iterate(models, res.u[b], sweep.x0[b], False)) < 1e-9 * np.linalg.norm(x_pred)
