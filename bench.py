@@ -252,6 +252,32 @@ def other_configs(threads):
     qp_case("LinearMpcXY: reference test schedule, n = 240, 15 equalities, 480 bound rows, batch 1184", lambda q: q(psxy), 1,
             6 * 8 + 240 * 8 + 240 * 8 + 8 + 32, 128)
 
+    # LinearMpcXY over a sweep of schedules, everything after the callback sampling on the device
+    sweep = workloads.linear_mpc_xy_sweep(n_sched=256, per_sched=16)
+    engxy = engine.LinearMpcXyEngine(sweep.N, sweep.n, sweep.n_eq, sweep.batch, sweep.S)
+    resxy = sweep.new_result(intermediates=False)
+    engxy.solve(sweep, result=resxy)
+    _, dtxy = _timed(lambda: engxy.solve(sweep, result=resxy), 2)
+    launches_xy = engxy.last_launches
+    engxy.close()
+    sub = sweep.first_schedules(8)
+    refxy = binding.linear_mpc_xy_solve(sub, n_threads=threads, intermediates=False)
+    k = sub.batch
+    parity_xy = bool(np.array_equal(refxy.u, resxy.u[sub.index]) and np.array_equal(refxy.iters, resxy.iters[sub.index])
+                     and np.array_equal(refxy.active, resxy.active[sub.index]))
+    t0 = time.perf_counter()
+    for s_ in range(4):
+        sweep.host_problem(s_, np.where(sweep.sched_id == s_)[0])
+    host_setup_s = (time.perf_counter() - t0) / 4
+    out.append({"workload": "LinearMpcXY sweep: 256 schedules x 16 initial states, n = 240, 15 equalities, 480 bound rows",
+                "unit": "solves/s", "e2e": sweep.batch / dtxy, "qps": int(sweep.batch), "schedules": int(sweep.S), "n": sweep.n,
+                "n_eq": sweep.n_eq, "n_ineq": 2 * sweep.n, "mean_active_set_iterations": float(resxy.iters.mean()),
+                "solved_frac": float((resxy.status == 0).mean()), "gpu_launches": launches_xy,
+                "algorithmic_bytes_per_solve": 6 * 8 + 4 + 240 * 8 + 240 * 4 + 12,
+                "host_setup_s_per_schedule_numpy": host_setup_s,
+                "parity": {"bit_exact_vs_oracle": parity_xy, "checked": int(k), "of": int(sweep.batch)},
+                "api": "ccc_linear_mpc_xy_solve(CCC_MEM_HOST): stage models, ZOH, condensing, DMMA B'WB, QP setup per schedule, QP"})
+
     w4 = workloads.ddp_srb_config4(batch=8192)
     ps4 = problem.DdpSrbProblemSet.from_workload(w4)
     eng4 = engine.DdpSrbEngine(ps4.N, ps4.batch, ps4.sched.S)

@@ -8,9 +8,11 @@
  * planOnce (:224-227, src :96-115), procOnce (src :117-182).  The box x_min <= x <= x_max of the
  * reference's QpCoeff enters the engine as 2n inequality rows (include/ccc_b200.h, QP section).
  * Eigen is absent: Vector2d = std::array<double,2>, VectorXd = std::vector<double>.
- * New: planBatch() — a batch of initial states sharing the sampled contact / reference schedule (the
- * condensing and the QP matrices are built once per call).  Header-only; link with libccc_b200.so; no CPU
- * fallback.
+ * planOnce samples the two callbacks on the horizon grid (src :104-110) and hands the flat stage tables to
+ * ccc_linear_mpc_xy_solve: stage models, closed-form discretisation, condensing, B_seq' W B_seq (FP64 tensor
+ * cores), the QP vectors and the QP all run on the device.
+ * New: planBatch() — a batch of initial states sharing one sampled schedule; planSweep() — initial states over a
+ * sweep of schedules, one QP factorisation per schedule.  Header-only; link with libccc_b200.so; no CPU fallback.
  */
 #pragma once
 #include <array>
@@ -20,10 +22,14 @@
 #include <utility>
 #include <vector>
 
+#include <cstdio>
+#include <string>
+
 #include "Gravity.h"
 #include "Contact.h"
-#include "VariantSequentialExtension.h"
+#include "StateSpaceModel.h"
 #include "detail/QpEngine.h"
+#include "detail/RidgeTables.h"
 
 namespace CCC
 {
@@ -135,6 +141,13 @@ public:
   {
   }
 
+  ~LinearMpcXY()
+  {
+    if(ws_) ccc_linear_mpc_xy_destroy(ws_);
+  }
+  LinearMpcXY(const LinearMpcXY &) = delete;
+  LinearMpcXY & operator=(const LinearMpcXY &) = delete;
+
   /** Plan one step: planned force scales of the first stage. */
   VectorXd planOnce(const std::function<MotionParam(double)> & motion_param_func,
                     const std::function<RefData(double)> & ref_data_func,
@@ -150,106 +163,119 @@ public:
                                   const std::vector<InitialParam> & initial_params,
                                   double current_time)
   {
-    std::vector<std::shared_ptr<StateSpaceModel>> model_list(horizon_steps_);
-    VectorXd ref_output_seq(static_cast<size_t>(horizon_steps_) * RefData::outputDim());
-    for(int i = 0; i < horizon_steps_; i++)
-    {
-      const double t = current_time + i * horizon_dt_;
-      model_list[i] = std::make_shared<Model>(mass_, motion_param_func(t));
-      model_list[i]->calcDiscMatrix(horizon_dt_);
-      const StateDimVector out = ref_data_func(t).toOutput(mass_);
-      for(int j = 0; j < 6; j++) ref_output_seq[static_cast<size_t>(i) * 6 + j] = out[j];
-    }
-    std::vector<StateDimVector> xs(initial_params.size());
-    for(size_t b = 0; b < initial_params.size(); b++) xs[b] = initial_params[b].toState(mass_);
-    return procBatch(model_list, xs, ref_output_seq);
+    return planSweep({Schedule{motion_param_func, ref_data_func, current_time}}, initial_params,
+                     std::vector<int>(initial_params.size(), 0));
   }
 
-  int lastStatus(int b = 0) const { return qp_.status(b); }
-  int lastIter(int b = 0) const { return qp_.iters(b); }
-
-protected:
-  std::vector<VectorXd> procBatch(const std::vector<std::shared_ptr<StateSpaceModel>> & model_list,
-                                  const std::vector<StateDimVector> & current_xs,
-                                  const VectorXd & ref_output_seq)
+  /** One contact / reference schedule of a sweep: the callbacks of planOnce and the time they are sampled from. */
+  struct Schedule
   {
-    VariantSequentialExtension seq_ext(model_list, false);
-    const int n = seq_ext.totalInputDim(), rows = seq_ext.totalStateDim(), B = static_cast<int>(current_xs.size());
+    std::function<MotionParam(double)> motion_param_func;
+    std::function<RefData(double)> ref_data_func;
+    double current_time = 0;
+  };
+
+  /** planOnce for initial_params[b] on schedules[sched_id[b]], all in one call: the callbacks are sampled on the
+   *  horizon grid here (src/LinearMpcXY.cpp:104-110); stage models, discretisation, condensing, B_seq' W B_seq, the QP
+   *  vectors and the QPs (one factorisation per schedule) run on the device (ccc_linear_mpc_xy_solve).  The
+   *  schedules of one call must agree in total input dimension and number of contact stages. */
+  std::vector<VectorXd> planSweep(const std::vector<Schedule> & schedules,
+                                  const std::vector<InitialParam> & initial_params,
+                                  const std::vector<int> & sched_id)
+  {
+    const int S = static_cast<int>(schedules.size()), B = static_cast<int>(initial_params.size()), N = horizon_steps_;
+    if(S == 0 || B == 0 || sched_id.size() != initial_params.size()) throw std::invalid_argument("[LinearMpcXY] empty sweep");
+    tables_.reset(S, N);
+    std::vector<double> com_z(static_cast<size_t>(S) * N), fz(static_cast<size_t>(S) * N), ref(static_cast<size_t>(S) * N * 6);
+    int n = 0, n_eq = 0;
+    for(int s = 0; s < S; s++)
+    {
+      int ns = 0, es = 0;
+      for(int i = 0; i < N; i++)
+      {
+        const double t = schedules[s].current_time + i * horizon_dt_;
+        const MotionParam mp = schedules[s].motion_param_func(t);
+        const int mk = tables_.setStage(s, i, mp.contact_list);
+        ns += mk;
+        es += mk > 0 ? 1 : 0; // no total_force_z constraint on stages without contact (src :128-132)
+        com_z[static_cast<size_t>(s) * N + i] = mp.com_z;
+        fz[static_cast<size_t>(s) * N + i] = mp.total_force_z;
+        const StateDimVector out = schedules[s].ref_data_func(t).toOutput(mass_);
+        for(int j = 0; j < 6; j++) ref[(static_cast<size_t>(s) * N + i) * 6 + j] = out[j];
+      }
+      if(s == 0)
+      {
+        n = ns;
+        n_eq = es;
+      }
+      else if(ns != n || es != n_eq)
+        throw std::invalid_argument("[LinearMpcXY] the schedules of one sweep must agree in total input dimension and contact stages");
+    }
     if(n == 0) throw std::runtime_error("[LinearMpcXY] no contact in the whole horizon");
-    int dim_eq = 0;
-    for(const auto & model : model_list)
-      if(model->inputDim() > 0) dim_eq++; // no total_force_z constraint on stages without contact
-    const VectorXd output_weight = weight_param_.outputWeight(model_list.size());
-    const detail::Matrix & Bs = seq_ext.B_seq_;
-    // obj_mat = B_seq' W B_seq + w_force I
-    detail::Matrix WB(rows, n);
-    for(int r = 0; r < rows; r++)
-      for(int j = 0; j < n; j++) WB(r, j) = output_weight[r] * Bs(r, j);
-    const detail::Matrix BtW = WB.transpose();
-    detail::Matrix Q = BtW * Bs;
-    const VectorXd input_weight = weight_param_.inputWeight(n);
-    for(int j = 0; j < n; j++) Q(j, j) += input_weight[j];
-    // equalities: total vertical force of every contact stage
-    detail::Matrix A(dim_eq, n);
-    VectorXd eq_vec(dim_eq, 0.0);
-    int accum_eq_dim = 0, accum_input_dim = 0;
-    for(const auto & _model : model_list)
+    if(!ws_ || n != ws_n_ || n_eq != ws_eq_ || B > ws_batch_ || S > ws_sched_)
     {
-      const auto model = std::dynamic_pointer_cast<Model>(_model);
-      if(!model) throw std::runtime_error("[LinearMpcXY] model_list must hold LinearMpcXY::Model");
-      if(model->inputDim() == 0) continue;
-      int ridge_idx = 0;
-      for(const auto & contact : model->motion_param_.contact_list)
-        for(const auto & vr : contact->vertexWithRidgeList_)
-          for(const auto & ridge : vr.ridgeList)
-          {
-            A(accum_eq_dim, accum_input_dim + ridge_idx) = ridge[2];
-            ridge_idx++;
-          }
-      eq_vec[accum_eq_dim] = model->motion_param_.total_force_z;
-      accum_eq_dim++;
-      accum_input_dim += model->inputDim();
+      if(ws_) ccc_linear_mpc_xy_destroy(ws_);
+      ws_batch_ = B > ws_batch_ ? B : ws_batch_;
+      ws_sched_ = S > ws_sched_ ? S : ws_sched_;
+      ws_n_ = n;
+      ws_eq_ = n_eq;
+      ws_ = ccc_linear_mpc_xy_create(N, n, n_eq, ws_batch_, ws_sched_);
+      if(!ws_) throw std::runtime_error(std::string("[LinearMpcXY] ") + ccc_last_error());
     }
-    // x_min <= x <= x_max as inequality rows: -x <= -x_min, x <= x_max
-    detail::Matrix C(2 * n, n);
-    for(int j = 0; j < n; j++)
-    {
-      C(j, j) = -1.0;
-      C(n + j, j) = 1.0;
-    }
-    qp_.setup(Q, A, C);
-    qp_.resize(B, true);
+    std::vector<double> x0(static_cast<size_t>(B) * 6);
     for(int b = 0; b < B; b++)
     {
-      // obj_vec = -B_seq' W (ref_output_seq - A_seq x - E_seq)
-      VectorXd resid(rows);
-      for(int r = 0; r < rows; r++)
-      {
-        double ax = 0;
-        for(int c = 0; c < 6; c++) ax += seq_ext.A_seq_(r, c) * current_xs[b][c];
-        resid[r] = ref_output_seq[r] - ax - seq_ext.E_seq_[r];
-      }
-      double * c = qp_.objVec(b);
-      for(int j = 0; j < n; j++)
-      {
-        double s = 0;
-        for(int r = 0; r < rows; r++) s += BtW(j, r) * resid[r];
-        c[j] = -1 * s;
-      }
-      for(int e = 0; e < dim_eq; e++) qp_.eqVec(b)[e] = eq_vec[e];
-      double * d = qp_.ineqVec(b);
-      for(int j = 0; j < n; j++)
-      {
-        d[j] = -force_range_.first;
-        d[n + j] = force_range_.second;
-      }
+      const StateDimVector x = initial_params[b].toState(mass_);
+      for(int j = 0; j < 6; j++) x0[static_cast<size_t>(b) * 6 + j] = x[j];
     }
-    qp_.solve();
-    const int m0 = model_list[0]->inputDim();
+    std::vector<int32_t> sid(sched_id.begin(), sched_id.end());
+    ccc_linear_mpc_xy_batch_t bt{};
+    bt.horizon_steps = N;
+    bt.batch = B;
+    bt.n_sched = S;
+    bt.m_max = tables_.M;
+    bt.dt = horizon_dt_;
+    bt.mass = mass_;
+    bt.sched_id = sid.data();
+    bt.m = tables_.m.data();
+    bt.ridge = tables_.ridge.data();
+    bt.vertex = tables_.vertex.data();
+    bt.com_z = com_z.data();
+    bt.total_force_z = fz.data();
+    bt.ref_output = ref.data();
+    const VectorXd w = weight_param_.outputWeight(1);
+    for(int j = 0; j < 6; j++) bt.w_output[j] = w[j];
+    bt.w_force = weight_param_.force;
+    bt.force_lo = force_range_.first;
+    bt.force_hi = force_range_.second;
+    bt.x0 = x0.data();
+    u_.assign(static_cast<size_t>(B) * n, 0.0);
+    status_.assign(B, 0);
+    iters_.assign(B, 0);
+    ccc_linear_mpc_xy_result_t rs{};
+    rs.u = u_.data();
+    rs.status = status_.data();
+    rs.iters = iters_.data();
+    if(ccc_linear_mpc_xy_solve(ws_, &bt, &rs, CCC_MEM_HOST, nullptr) != CCC_OK)
+      throw std::runtime_error(std::string("[LinearMpcXY] ") + ccc_last_error());
+    // a failed QP is reported the way QpSolverCollection does it (a message, the last iterate is returned)
+    failed_ = 0;
+    for(int b = 0; b < B; b++)
+      if(status_[b] != 0) failed_++;
+    if(failed_ > 0) std::fprintf(stderr, "[LinearMpcXY] %d of %d QPs failed to solve (lastStatus())\n", failed_, B);
     std::vector<VectorXd> out(B);
-    for(int b = 0; b < B; b++) out[b].assign(qp_.x(b), qp_.x(b) + m0);
+    for(int b = 0; b < B; b++)
+    {
+      const int m0 = tables_.inputDim(sid[b], 0);
+      out[b].assign(u_.begin() + static_cast<size_t>(b) * n, u_.begin() + static_cast<size_t>(b) * n + m0);
+    }
     return out;
   }
+
+  int lastStatus(int b = 0) const { return status_.at(b); }
+  int lastIter(int b = 0) const { return iters_.at(b); }
+  //! QPs of the last call that did not reach status 0
+  int lastFailed() const { return failed_; }
 
 public:
   double mass_ = 0;
@@ -260,6 +286,10 @@ public:
   std::pair<double, double> force_range_;
 
 protected:
-  detail::QpEngine qp_;
+  detail::RidgeTables tables_;
+  ccc_linear_mpc_xy_ws_t * ws_ = nullptr;
+  int ws_n_ = 0, ws_eq_ = 0, ws_batch_ = 0, ws_sched_ = 0, failed_ = 0;
+  std::vector<double> u_;
+  std::vector<int32_t> status_, iters_;
 };
 } // namespace CCC

@@ -202,6 +202,16 @@ class XySweepProblemSet:
     def new_result(self, intermediates=True):
         return XySweepResultArrays(self.batch, self.S, self.N, self.n, intermediates)
 
+    def first_schedules(self, k):
+        """The sub-sweep of schedules 0..k-1 and the initial states that use them."""
+        sub = XySweepProblemSet(self.mpc, self.N, k, self.m_max)
+        for f in ("m", "ridge", "vertex", "com_z", "total_force_z", "ref_output"):
+            setattr(sub, f, np.ascontiguousarray(getattr(self, f)[:k]))
+        keep = self.sched_id < k
+        sub.set_initial_states(self.x0[keep], self.sched_id[keep])
+        sub.index = np.where(keep)[0]
+        return sub
+
     def host_problem(self, s, idx):
         """The QpProblemSet the host path (build_qp: scipy expm, numpy condensing) makes of schedule s and the
         initial states idx — the independent check of the closed-form discretisation."""

@@ -97,5 +97,30 @@ int main(int argc, char ** argv)
     EXPECT_LT(worst, 1e-300);
     std::printf("LinearMpcXY planBatch(12) vs planOnce: max diff %g\n", worst);
   }
+  {
+    // planSweep: three schedules (the scenario sampled at three times), two initial states each == planOnce
+    std::vector<Xy::Schedule> sch;
+    for(double t0 : {2.5, 3.45, 5.2}) sch.push_back({motion_param_func, ref_data_func, t0});
+    std::vector<Xy::InitialParam> ips(6);
+    std::vector<int> sid(6);
+    for(int i = 0; i < 6; i++)
+    {
+      sid[i] = i % 3;
+      const auto rd = ref_data_func(sch[sid[i]].current_time);
+      ips[i].pos = {rd.pos[0] + 0.003 * i, rd.pos[1] - 0.002 * i};
+      ips[i].vel = {0.02 * (i % 2), 0.01 * i};
+    }
+    const auto sweep = mpc.planSweep(sch, ips, sid);
+    EXPECT_TRUE(mpc.lastFailed() == 0);
+    double worst = 0;
+    for(int i = 0; i < 6; i++)
+    {
+      const auto one = mpc.planOnce(motion_param_func, ref_data_func, ips[i], sch[sid[i]].current_time);
+      EXPECT_TRUE(one.size() == sweep[i].size());
+      for(size_t j = 0; j < one.size(); j++) worst = std::max(worst, std::fabs(one[j] - sweep[i][j]));
+    }
+    EXPECT_LT(worst, 1e-300);
+    std::printf("LinearMpcXY planSweep(3 schedules x 2) vs planOnce: max diff %g\n", worst);
+  }
   return finish("TestLinearMpcXY");
 }

@@ -16,6 +16,7 @@ int32_t ccc_oracle_ddp_centroidal_solve(const ccc_ddp_centroidal_batch_t *, cons
 int32_t ccc_oracle_ddp_srb_solve(const ccc_ddp_srb_batch_t *, const ccc_ddp_config_t *, ccc_ddp_result_t *, int32_t);
 int32_t ccc_oracle_ddp_zmp_solve(const ccc_ddp_zmp_batch_t *, const ccc_ddp_config_t *, ccc_ddp_result_t *, int32_t);
 int32_t ccc_oracle_qp_solve(const ccc_qp_batch_t *, ccc_qp_result_t *, int32_t);
+int32_t ccc_oracle_linear_mpc_xy_solve(const ccc_linear_mpc_xy_batch_t *, ccc_linear_mpc_xy_result_t *, int32_t);
 int32_t ccc_oracle_ddp_centroidal_closed_loop(const ccc_ddp_centroidal_loop_t *, const ccc_ddp_config_t *, ccc_ddp_centroidal_loop_result_t *, int32_t);
 int32_t ccc_oracle_preview_input(int32_t, int32_t, const double *, const double *, const double *, const double *, double *);
 int32_t ccc_oracle_hardware_threads(void);
@@ -50,6 +51,13 @@ void ccc_ddp_zmp_destroy(ccc_ddp_zmp_ws_t * w) { delete w; }
 int32_t ccc_ddp_zmp_solve(ccc_ddp_zmp_ws_t *, const ccc_ddp_zmp_batch_t * b, const ccc_ddp_config_t * c, ccc_ddp_result_t * r, int32_t, void *)
 {
   return ccc_oracle_ddp_zmp_solve(b, c, r, ccc_oracle_hardware_threads());
+}
+struct ccc_linear_mpc_xy_ws { int dummy; };
+ccc_linear_mpc_xy_ws_t * ccc_linear_mpc_xy_create(int32_t, int32_t, int32_t, int32_t, int32_t) { return new ccc_linear_mpc_xy_ws; }
+void ccc_linear_mpc_xy_destroy(ccc_linear_mpc_xy_ws_t * w) { delete w; }
+int32_t ccc_linear_mpc_xy_solve(ccc_linear_mpc_xy_ws_t *, const ccc_linear_mpc_xy_batch_t * b, ccc_linear_mpc_xy_result_t * r, int32_t, void *)
+{
+  return ccc_oracle_linear_mpc_xy_solve(b, r, ccc_oracle_hardware_threads());
 }
 ccc_qp_ws_t * ccc_qp_create(int32_t, int32_t, int32_t, int32_t) { return new ccc_qp_ws; }
 void ccc_qp_destroy(ccc_qp_ws_t * w) { delete w; }
