@@ -166,6 +166,36 @@ class LinearMpcXyResult(C.Structure):
                 ("obj_vec", C.c_void_p)]
 
 
+class FootstepPlans(C.Structure):
+    """ccc_footstep_plans_t"""
+
+    _fields_ = [("n_plans", C.c_int32), ("max_steps", C.c_int32), ("horizon_steps", C.c_int32), ("eps_reps", C.c_int32),
+                ("horizon_dt", C.c_double), ("manager_horizon", C.c_double), ("foot_size", C.c_double * 2),
+                ("current_time", C.c_void_p), ("stance0", C.c_void_p), ("n_steps", C.c_void_p), ("foot", C.c_void_p),
+                ("pos", C.c_void_p), ("times", C.c_void_p)]
+
+
+class ZmpTables(C.Structure):
+    """ccc_zmp_tables_t"""
+
+    _fields_ = [("ref_zmp", C.c_void_p), ("lim_min", C.c_void_p), ("lim_max", C.c_void_p)]
+
+
+class ZmpMpcBatch(C.Structure):
+    """ccc_zmp_mpc_batch_t"""
+
+    _fields_ = [("method", C.c_int32), ("horizon_steps", C.c_int32), ("batch", C.c_int32), ("n_plans", C.c_int32),
+                ("control_dt", C.c_double), ("com_height_over_g", C.c_double), ("weight_zmp", C.c_double),
+                ("Q", C.c_void_p), ("A", C.c_void_p), ("C", C.c_void_p), ("A_seq", C.c_void_p), ("P", C.c_void_p),
+                ("plan_id", C.c_void_p), ("state", C.c_void_p), ("tables", ZmpTables)]
+
+
+class ZmpMpcResult(C.Structure):
+    """ccc_zmp_mpc_result_t"""
+
+    _fields_ = [("planned_zmp", C.c_void_p), ("iters", C.c_void_p), ("status", C.c_void_p)]
+
+
 def ptr(a):
     """Address of a C-contiguous numpy array (or None)."""
     if a is None:

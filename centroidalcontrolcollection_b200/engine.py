@@ -23,6 +23,7 @@ EXPORTS = [
     "ccc_ddp_zmp_create", "ccc_ddp_zmp_destroy", "ccc_ddp_zmp_solve", "ccc_ddp_zmp_last_launches",
     "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
     "ccc_fp64_peak_tflops",
+    "ccc_footstep_compile", "ccc_zmp_mpc_create", "ccc_zmp_mpc_destroy", "ccc_zmp_mpc_plan", "ccc_zmp_mpc_last_launches",
     "ccc_linear_mpc_xy_create", "ccc_linear_mpc_xy_destroy", "ccc_linear_mpc_xy_solve", "ccc_linear_mpc_xy_last_launches",
 ]
 
@@ -88,6 +89,16 @@ def lib():
         L.ccc_qp_set_packed.argtypes = [C.c_int32]
         L.ccc_preview_input.restype = C.c_int32
         L.ccc_preview_input.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]
+        L.ccc_footstep_compile.restype = C.c_int32
+        L.ccc_footstep_compile.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ccc_zmp_mpc_create.restype = C.c_void_p
+        L.ccc_zmp_mpc_create.argtypes = [C.c_int32] * 4
+        L.ccc_zmp_mpc_destroy.argtypes = [C.c_void_p]
+        L.ccc_zmp_mpc_destroy.restype = None
+        L.ccc_zmp_mpc_plan.restype = C.c_int32
+        L.ccc_zmp_mpc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ccc_zmp_mpc_last_launches.restype = C.c_int32
+        L.ccc_zmp_mpc_last_launches.argtypes = [C.c_void_p]
         L.ccc_linear_mpc_xy_create.restype = C.c_void_p
         L.ccc_linear_mpc_xy_create.argtypes = [C.c_int32] * 5
         L.ccc_linear_mpc_xy_destroy.argtypes = [C.c_void_p]
@@ -224,6 +235,79 @@ class QpEngine:
         """Tuning hook: 1 (default) = first pass with a packed R, two CTAs per SM, full-R pass for the problems whose
         active set outgrows it; 0 = the full-R kernel alone (one CTA per SM, round 1)."""
         lib().ccc_qp_set_packed(int(on))
+
+
+def footstep_compile(plans, tables=None):
+    """Schedule compiler (ccc_footstep_compile, host buffers): schedule.FootstepPlans -> schedule.ZmpTables."""
+    from .schedule import ZmpTables
+
+    tables = tables if tables is not None else ZmpTables(plans.P, plans.N)
+    ps, ts = plans.as_struct(), tables.as_struct()
+    _check(lib().ccc_footstep_compile(C.addressof(ps), C.addressof(ts), _abi.CCC_MEM_HOST, None), "ccc_footstep_compile")
+    return tables
+
+
+class ZmpMpcEngine:
+    """planOnce of CCC::LinearMpcZmp (method 0) / CCC::IntrinsicallyStableMpc (method 1) for a batch of problems
+    whose reference data are rows of compiled stage tables: QP vectors assembled, QPs solved and the planned ZMP
+    post-processed on the device (ccc_zmp_mpc_plan).  `mpc` is the host class of linear_mpc.py (its constructor did
+    the batch-invariant setup: Q, A, C, A_seq / P)."""
+
+    def __init__(self, mpc, max_batch, max_plans):
+        from . import linear_mpc
+
+        self.mpc = m1 = mpc.mpc_1d
+        self.method = 1 if isinstance(m1, linear_mpc.IntrinsicallyStableMpc1d) else 0
+        self._h = lib().ccc_zmp_mpc_create(self.method, m1.horizon_steps, int(max_batch), int(max_plans))
+        if not self._h:
+            raise EngineError(f"ccc_zmp_mpc_create failed: {last_error()}")
+        self._mats = [np.ascontiguousarray(m1.Q), np.ascontiguousarray(m1.C)]
+        if self.method == 1:
+            self._mats += [np.ascontiguousarray(m1.A), np.ascontiguousarray(m1.P)]
+        else:
+            self._mats += [np.ascontiguousarray(m1.seq_ext.A_seq)]
+        self._uploaded = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ccc_zmp_mpc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def plan(self, state, plan_id, tables, control_dt=-1.0, want_qp_info=True):
+        """state: method 0 [B][2][3] (pos, vel, acc per axis), method 1 [B][2][2] (capture point, planned zmp per
+        axis); plan_id [B]; tables: schedule.ZmpTables -> (planned_zmp [B][2], iters [2B], status [2B])."""
+        m1 = self.mpc
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        plan_id = np.ascontiguousarray(plan_id, dtype=np.int32)
+        B = len(plan_id)
+        bt = _abi.ZmpMpcBatch()
+        bt.method, bt.horizon_steps, bt.batch, bt.n_plans = self.method, m1.horizon_steps, B, tables.lim_min.shape[0]
+        bt.control_dt = control_dt if control_dt > 0 else m1.horizon_dt
+        if self.method == 0:
+            bt.com_height_over_g = -float(m1.model.C[0, 2])
+        else:
+            bt.weight_zmp = m1.weight_zmp
+        if not self._uploaded:
+            bt.Q, bt.C = _abi.ptr(self._mats[0]), _abi.ptr(self._mats[1])
+            if self.method == 1:
+                bt.A, bt.P = _abi.ptr(self._mats[2]), _abi.ptr(self._mats[3])
+            else:
+                bt.A_seq = _abi.ptr(self._mats[2])
+        bt.plan_id, bt.state, bt.tables = _abi.ptr(plan_id), _abi.ptr(state), tables.as_struct()
+        planned = np.zeros((B, 2))
+        iters = np.zeros(2 * B, dtype=np.int32) if want_qp_info else None
+        status = np.zeros(2 * B, dtype=np.int32) if want_qp_info else None
+        rs = _abi.ZmpMpcResult()
+        rs.planned_zmp, rs.iters, rs.status = _abi.ptr(planned), _abi.ptr(iters), _abi.ptr(status)
+        _check(lib().ccc_zmp_mpc_plan(self._h, C.addressof(bt), C.addressof(rs), _abi.CCC_MEM_HOST, None), "ccc_zmp_mpc_plan")
+        self._uploaded = True
+        return planned, iters, status
+
+    @property
+    def last_launches(self):
+        return int(lib().ccc_zmp_mpc_last_launches(self._h))
 
 
 class LinearMpcXyEngine:

@@ -28,7 +28,9 @@ class LinearMpcZmp1d:
 
     def build_qp(self, initial_param, zmp_limits):
         """initial_param [B][3] (pos, vel, acc); zmp_limits [B][N][2] -> QpProblemSet (:54-60)."""
-        ax0 = initial_param @ self.seq_ext.A_seq.T  # [B][N]
+        # A_seq x0 as (a0 x0 + a1 x1) + a2 x2, the order of the device assembly (csrc/zmp_mpc.cu)
+        A = self.seq_ext.A_seq
+        ax0 = (A[None, :, 0] * initial_param[:, 0:1] + A[None, :, 1] * initial_param[:, 1:2]) + A[None, :, 2] * initial_param[:, 2:3]
         d = np.concatenate([ax0 - zmp_limits[:, :, 0], -ax0 + zmp_limits[:, :, 1]], axis=1)
         return QpProblemSet(self.Q, self.C, d)
 
@@ -41,7 +43,7 @@ class LinearMpcZmp1d:
         if control_dt < 0:
             control_dt = self.horizon_dt
         com_acc = initial_param[:, 2] + control_dt * com_jerk
-        com_pos = initial_param[:, 0] + control_dt * initial_param[:, 1] + 0.5 * control_dt**2 * initial_param[:, 2]
+        com_pos = (initial_param[:, 0] + control_dt * initial_param[:, 1]) + (0.5 * (control_dt * control_dt)) * initial_param[:, 2]
         zmp = np.clip(com_pos + self.model.C[0, 2] * com_acc, zmp_limits[:, 0, 0], zmp_limits[:, 0, 1])
         self.last_result = res
         return zmp
@@ -84,7 +86,12 @@ class IntrinsicallyStableMpc1d:
     def build_qp(self, capture_point, planned_zmp, ref_zmp, zmp_limits):
         """capture_point, planned_zmp [B]; ref_zmp [B][N]; zmp_limits [B][N][2] (:63-91)."""
         b = (capture_point - planned_zmp)[:, None]
-        c = self.weight_zmp * (planned_zmp[:, None] - ref_zmp) @ self.P    # P' (z0 1 - z_ref), row form
+        # w_zmp P' (z0 1 - z_ref): the sum over the stages runs sequentially (the order of the device assembly)
+        v = planned_zmp[:, None] - ref_zmp
+        acc = np.zeros_like(v)
+        for i in range(self.horizon_steps):  # P is lower triangular: the skipped terms are exact zeros
+            acc[:, :i + 1] = acc[:, :i + 1] + self.P[i][None, :i + 1] * v[:, i:i + 1]
+        c = self.weight_zmp * acc
         d = np.concatenate([-zmp_limits[:, :, 0] + planned_zmp[:, None], zmp_limits[:, :, 1] - planned_zmp[:, None]], axis=1)
         return QpProblemSet(self.Q, self.C, d, self.A, b, c)
 

@@ -359,6 +359,83 @@ int32_t ccc_linear_mpc_xy_solve(ccc_linear_mpc_xy_ws_t * ws,
                                 void * stream);
 int32_t ccc_linear_mpc_xy_last_launches(const ccc_linear_mpc_xy_ws_t * ws);
 
+/* ---- schedule compiler: footstep plans -> stage tables -----------------------------------------------
+ * Batched, stateless counterpart of the reference tests' FootstepManager (tests/src/FootstepManager.h): what
+ * FootstepManager::update(current_time) (:147-209) builds — the knot lists ref_zmp_list_ / ref_footstance_list_ —
+ * and what refZmp(t) (:228-237) / zmpLimits(t) (:242-254) read from them, sampled on the horizon grid
+ * t_k = current_time + k horizon_dt (+ eps_reps x 1e-6: the reference adds its epsilon_t once in refZmp / zmpLimits
+ * and once more in make*RefData, :356-380), for P plans at once.  "Stateless": the foot stance at current_time is
+ * the initial stance with every footstep whose swing_end_time <= current_time applied and the pending list is the
+ * footsteps whose transit_end_time >= current_time — what a manager updated once per control cycle holds. */
+typedef struct
+{
+  int32_t n_plans;       /* P */
+  int32_t max_steps;     /* F: row stride of the footstep arrays */
+  int32_t horizon_steps; /* N */
+  int32_t eps_reps;      /* 1e-6 is added this many times to every sample time (1 or 2, see above) */
+  double horizon_dt;
+  double manager_horizon;  /* FootstepManager::horizon_duration_ (:461, default 10 s) */
+  double foot_size[2];     /* FootstepManager::foot_size_ (:464) */
+  const double * current_time; /* [P] */
+  const double * stance0;      /* [P][2][2] initial foot positions: Left, Right (:136-137) */
+  const int32_t * n_steps;     /* [P] */
+  const int32_t * foot;        /* [P][F] 0 = Left, 1 = Right */
+  const double * pos;          /* [P][F][2] */
+  const double * times;        /* [P][F][4] transit_start, swing_start, swing_end, transit_end (Footstep, :36-77) */
+} ccc_footstep_plans_t;
+
+typedef struct
+{
+  double * ref_zmp; /* [P][N][2] */
+  double * lim_min; /* [P][N][2] */
+  double * lim_max; /* [P][N][2] */
+} ccc_zmp_tables_t;
+
+/* Stateless: no workspace.  Host pointers (synchronous) or device pointers (enqueued on `stream`). */
+int32_t ccc_footstep_compile(const ccc_footstep_plans_t * plans, ccc_zmp_tables_t * tables, int32_t mem, void * stream);
+
+/* ---- CCC::LinearMpcZmp / CCC::IntrinsicallyStableMpc planOnce on stage tables, on the device -----------
+ * procOnce of both methods for B problems x 2 axes whose reference data are rows of compiled tables (problem b reads
+ * plan plan_id[b]): the QP vectors are assembled on the device, the 2B one-dimensional QPs go through the ccc_qp
+ * engine, the planned ZMP is post-processed there.
+ *  method 0, LinearMpcZmp1d::procOnce (src/LinearMpcZmp.cpp:46-81): d = [A_seq x0 - lo; -A_seq x0 + hi], planned ZMP
+ *    = clamp(C (A_d x0 + B_d u_0), lo_0, hi_0) with the control_dt model written out as the reference does (:71-79);
+ *  method 1, IntrinsicallyStableMpc1d::procOnce (src/IntrinsicallyStableMpc.cpp:63-104): b = cp - z0,
+ *    c = w_zmp P'(z0 1 - z_ref), d = [-lo + z0; hi - z0], planned ZMP = clamp(z0 + control_dt u_0, lo_0, hi_0).
+ * The QP matrices (batch invariant, from the host-side setup of the controller: InvariantSequentialExtension,
+ * P, the stability constraint) are passed once per call. */
+typedef struct
+{
+  int32_t method;        /* 0: LinearMpcZmp, 1: IntrinsicallyStableMpc */
+  int32_t horizon_steps; /* N = number of QP variables */
+  int32_t batch;         /* B problems (2B QPs: x axes first, then y axes) */
+  int32_t n_plans;       /* P */
+  double control_dt;     /* resolved (> 0) */
+  double com_height_over_g; /* method 0: -C(0,2) of ComZmpModelJerkInput = h / g */
+  double weight_zmp;     /* method 1 */
+  const double * Q;      /* [N][N] obj_mat_ */
+  const double * A;      /* [1][N] eq_mat_ (method 1) or NULL */
+  const double * C;      /* [2N][N] ineq_mat_ */
+  const double * A_seq;  /* [N][3] (method 0) */
+  const double * P;      /* [N][N] (method 1) */
+  const int32_t * plan_id; /* [B] */
+  const double * state;  /* method 0: [B][2][3] (pos, vel, acc) per axis; method 1: [B][2][2] (capture point, planned zmp) per axis */
+  ccc_zmp_tables_t tables; /* device (CCC_MEM_DEVICE) or host (CCC_MEM_HOST) tables of the P plans */
+} ccc_zmp_mpc_batch_t;
+
+typedef struct
+{
+  double * planned_zmp; /* [B][2] */
+  int32_t * iters;      /* [2B] active-set iterations of every QP, or NULL */
+  int32_t * status;     /* [2B] or NULL */
+} ccc_zmp_mpc_result_t;
+
+typedef struct ccc_zmp_mpc_ws ccc_zmp_mpc_ws_t;
+ccc_zmp_mpc_ws_t * ccc_zmp_mpc_create(int32_t method, int32_t horizon_steps, int32_t max_batch, int32_t max_plans);
+void ccc_zmp_mpc_destroy(ccc_zmp_mpc_ws_t * ws);
+int32_t ccc_zmp_mpc_plan(ccc_zmp_mpc_ws_t * ws, const ccc_zmp_mpc_batch_t * batch, ccc_zmp_mpc_result_t * result, int32_t mem, void * stream);
+int32_t ccc_zmp_mpc_last_launches(const ccc_zmp_mpc_ws_t * ws);
+
 /* ---- CCC::PreviewControl<3,1,1>::calcOptimalInput ------------------------------------------------
  * Batched online part of preview control:  u[b] = -K x[b] + F ref_seq[b]   (gains K (1x3), F (1xN) shared).
  * Replaces: PreviewControl::calcOptimalInput (reference include/CCC/PreviewControl.h:86-89) as called from
