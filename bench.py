@@ -252,6 +252,43 @@ def other_configs(threads):
     qp_case("LinearMpcXY: reference test schedule, n = 240, 15 equalities, 480 bound rows, batch 1184", lambda q: q(psxy), 1,
             6 * 8 + 240 * 8 + 240 * 8 + 8 + 32, 128)
 
+    # config 5 again, full size, with the footstep plans compiled and the QP vectors assembled on the device: the host
+    # hands over 256 plans and 131072 (capture point, planned ZMP) pairs and reads 131072 planned ZMPs back
+    from centroidalcontrolcollection_b200 import schedule
+
+    rng5 = np.random.Generator(np.random.PCG64(20260104))
+    lengths, widths = rng5.uniform(0.1, 0.3, 16), rng5.uniform(0.16, 0.24, 16)
+    plans = schedule.FootstepPlans(256, 8, mpc5.mpc_1d.horizon_steps, w5["horizon_dt"], eps_reps=2)
+    for p_ in range(256):
+        sl, sw = lengths[p_ % 16], widths[(p_ // 16) % 16]
+        plans.current_time[p_] = 1.8
+        plans.stance0[p_] = [[0.0, 0.5 * sw], [0.0, -0.5 * sw]]
+        for foot, x, ts in [(0, sl, 2.0), (1, 2 * sl, 3.0), (0, 3 * sl, 4.0), (1, 4 * sl, 5.0), (0, 3 * sl, 6.0), (1, 3 * sl, 7.0)]:
+            plans.append_footstep(p_, foot, (x, 0.5 * sw if foot == 0 else -0.5 * sw), ts, 0.2, 0.8)
+    plan_id = np.repeat(np.arange(256, dtype=np.int32), 512)
+    state5 = np.ascontiguousarray(np.stack([w5["capture_point"], w5["planned_zmp"]], axis=2))
+    eng5 = engine.ZmpMpcEngine(mpc5, len(plan_id), 256)
+
+    def run5():
+        tables = engine.footstep_compile(plans)
+        return eng5.plan(state5, plan_id, tables, w5["control_dt"], want_qp_info=True)
+
+    run5()
+    (planned5, iters5, status5), dt5 = _timed(run5, 3)
+    launches5 = eng5.last_launches + 1
+    eng5.close()
+    k = 4096
+    ref5 = mpc5.plan_batch(lambda ps: binding.qp_solve(ps, n_threads=threads), w5["capture_point"][:k], w5["planned_zmp"][:k],
+                           w5["ref_zmp"][:k], w5["lim_min"][:k], w5["lim_max"][:k], w5["control_dt"])
+    out.append({"workload": "config 5 on the device: 256 footstep plans compiled + " + w5["name"], "unit": "2-axis solves/s",
+                "e2e": len(plan_id) / dt5, "qps": int(2 * len(plan_id)), "n": 100, "n_eq": 1, "n_ineq": 200,
+                "mean_active_set_iterations": float(iters5.mean()), "solved_frac": float((status5 == 0).mean()), "gpu_launches": launches5,
+                "h2d_bytes": int(state5.nbytes + plan_id.nbytes + plans.times.nbytes + plans.pos.nbytes), "d2h_bytes": int(planned5.nbytes + iters5.nbytes + status5.nbytes),
+                "algorithmic_bytes_per_solve": 2 * 16 + 4 + 16,
+                "parity": {"planned_zmp_max_abs_diff_vs_host_class_with_oracle_qp": float(np.abs(ref5 - planned5[:k]).max()), "checked": k,
+                           "of": int(len(plan_id))},
+                "api": "ccc_footstep_compile + ccc_zmp_mpc_plan (CCC_MEM_HOST)"})
+
     # LinearMpcXY over a sweep of schedules, everything after the callback sampling on the device
     sweep = workloads.linear_mpc_xy_sweep(n_sched=256, per_sched=16)
     engxy = engine.LinearMpcXyEngine(sweep.N, sweep.n, sweep.n_eq, sweep.batch, sweep.S)
