@@ -34,10 +34,27 @@ def build(force=False, verbose=False, ab_variants=None):
         ab_variants = os.environ.get("CCC_AB_VARIANTS", "0") not in ("", "0")
     if not force and not needs_build():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-DCCC_AB_VARIANTS"] if ab_variants else []) + (["-Xptxas", "-v"] if verbose else [])
-    cmd += ["-t", "0", "-o", LIB] + sources()
-    subprocess.check_call(cmd)
+    # Several processes may get here at once (one rank per GPU under torchrun): one builds, the others wait on the
+    # lock and find the library up to date; the library appears by an atomic rename, never half written.
+    import fcntl
+
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            cmd = [nvcc] + NVCC_FLAGS + (["-DCCC_AB_VARIANTS"] if ab_variants else []) + (["-Xptxas", "-v"] if verbose else [])
+            tmp = f"{LIB}.tmp.{os.getpid()}"
+            cmd += ["-t", "0", "-o", tmp] + sources()
+            try:
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

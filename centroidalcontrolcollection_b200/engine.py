@@ -170,6 +170,14 @@ class DdpZmpEngine(_DdpEngineBase):
 
     _prefix = "ccc_ddp_zmp"
 
+    @staticmethod
+    def set_variant(v):
+        """Tuning hook, read when an engine is created: 1 = one thread per problem (default), 0 = the warp-per-problem
+        engine (3 of 32 lanes live).  Returns the previous value."""
+        f = lib().ccc_ddp_zmp_set_variant
+        f.restype, f.argtypes = C.c_int32, [C.c_int32]
+        return int(f(int(v)))
+
 
 class DdpCentroidalEngine(_DdpEngineBase):
     """Batched counterpart of CCC::DdpCentroidal's solver object (reference

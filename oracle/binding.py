@@ -24,7 +24,14 @@ CHOICE_BOXQP_WARM_SAME_STAGE = 16
 
 
 def build():
-    subprocess.check_call(["make", "-s", "-C", _HERE])
+    import fcntl
+
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:  # concurrent ranks / test workers build once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            subprocess.check_call(["make", "-s", "-C", _HERE])
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 class Oracle:

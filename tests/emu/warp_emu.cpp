@@ -13,6 +13,7 @@
 #include "../../centroidalcontrolcollection_b200/csrc/model_centroidal.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/model_srb.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/model_zmp.cuh"
+#include "../../centroidalcontrolcollection_b200/csrc/ddp_thread_zmp.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/qp_cta_core.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/preview_core.cuh"
 
@@ -507,4 +508,14 @@ extern "C" int32_t ccc_emu_ddp_zmp_solve(const ccc_ddp_zmp_batch_t * bt, const c
                                      row[3] = z[2];
                                    }
                                  });
+}
+
+/** The thread-per-problem DdpZmp solver (csrc/ddp_thread_zmp.cuh) compiled for the host: the same source the
+ *  zmp_thread_kernel runs, with the engine's strided per-problem storage (stride = batch). */
+extern "C" int32_t ccc_emu_ddp_zmp_thread_solve(const ccc_ddp_zmp_batch_t * bt, const ccc_ddp_config_t * c, ccc_ddp_result_t * r)
+{
+  const int N = bt->horizon_steps, B = bt->batch;
+  std::vector<double> slab(ccc_thread::zmp_work_doubles(N) * (size_t)B, 0.0);
+  for(int b = 0; b < B; b++) ccc_thread::zmp_thread_run(*bt, *c, *r, ccc_thread::zmp_work_at(slab.data(), N, (size_t)B, (size_t)b), b);
+  return CCC_OK;
 }

@@ -65,5 +65,16 @@ def ddp_zmp_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
     return res
 
 
+def ddp_zmp_thread_solve(problem_set, cfg, trace_len=0):
+    """csrc/ddp_thread_zmp.cuh (one thread per problem) compiled for the host."""
+    L = lib()
+    L.ccc_emu_ddp_zmp_thread_solve.restype = C.c_int32
+    L.ccc_emu_ddp_zmp_thread_solve.argtypes = [C.c_void_p] * 3
+    res = problem_set.new_result(trace_len)
+    bs, rs = problem_set.as_struct(), res.as_struct()
+    assert L.ccc_emu_ddp_zmp_thread_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs)) == 0
+    return res
+
+
 def last_qp_overflows():
     return int(lib().ccc_emu_qp_last_overflows())

@@ -3,6 +3,7 @@
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from centroidalcontrolcollection_b200 import problem
 
@@ -152,3 +153,39 @@ def test_emulated_kernel_matches_oracle(oracle):
     ref = oracle.ddp_zmp_solve(ps, cfg, trace_len=4)
     for feat in (1, 2):
         assert_ddp_parity(ref, emu_lib.ddp_zmp_solve(ps, cfg, trace_len=4, chunk=2, feat=feat))
+
+
+def _zmp_problem_set(B, N, seed, cold_frac=0.3, stiff=0):
+    """B DdpZmp problems over two walking-plan schedules: perturbed states, warm starts near m g and cold starts."""
+    rng = np.random.default_rng(seed)
+    ref_zmp, com_z = np.zeros((2, N + 1, 3)), np.ones((2, N + 1))
+    for s, t0 in enumerate((1.9, 2.6)):
+        fm = walking_plan()
+        fm.update(t0)
+        for k in range(N + 1):
+            ref_zmp[s, k, :2] = fm.ref_zmp(t0 + k * 0.02)
+        com_z[s] = 1.0 + 0.02 * s
+    x0 = np.zeros((B, 6))
+    x0[:, 0::2] = np.array([0.0, 0.0, 1.0]) + rng.uniform(-0.03, 0.03, (B, 3))
+    x0[:, 1::2] = rng.uniform(-0.1, 0.1, (B, 3))
+    u_init = np.tile(np.array([0.0, 0.0, 100 * G]), (B, N, 1)) * (1 + 0.05 * rng.standard_normal((B, N, 3)))
+    cold = rng.uniform(size=B) < cold_frac
+    u_init[cold, :, :2] = 0.3  # far-off ZMP and force guesses: more iterations, shortened steps
+    u_init[cold, :, 2] *= rng.uniform(0.3, 2.5, (int(cold.sum()), 1))
+    if stiff:  # low, fast-moving CoM: shortened and rejected line-search steps, lambda increases
+        x0[:, 4] = 1.0 - 0.07 * stiff * rng.uniform(0, 1, B)
+        x0[:, 5] = -0.5 * stiff
+        x0[:, 1] = 0.3 * stiff
+    return problem.DdpZmpProblemSet(ref_zmp, com_z, rng.integers(0, 2, B), x0, 100.0, 0.02, u_init=u_init)
+
+
+@pytest.mark.parametrize("max_iter", [1, 3, 60])
+def test_thread_per_problem_solver_matches_oracle(oracle, max_iter):
+    """csrc/ddp_thread_zmp.cuh, the source of the one-thread-per-problem kernel, compiled for the host."""
+    for stiff in (0, 3, 10):
+        ps = _zmp_problem_set(24, 30, seed=7, stiff=stiff)
+        cfg = problem.ddp_config(max_iter=max_iter)
+        ref = oracle.ddp_zmp_solve(ps, cfg, trace_len=8)
+        assert_ddp_parity(ref, emu_lib.ddp_zmp_thread_solve(ps, cfg, trace_len=8))
+        if max_iter == 60 and stiff:
+            assert ref.iters.max() > 6 and (ref.alpha_idx[:, :8] > 0).any()
