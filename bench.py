@@ -315,6 +315,47 @@ def other_configs(threads):
                 "parity": {"bit_exact_vs_oracle": parity_xy, "checked": int(k), "of": int(sweep.batch)},
                 "api": "ccc_linear_mpc_xy_solve(CCC_MEM_HOST): stage models, ZOH, condensing, DMMA B'WB, QP setup per schedule, QP"})
 
+    # DdpZmp (the seventh north-star method): 65536 warm-started problems on 4 sampled walking-plan schedules, max_iter 3
+    # as the reference's test loop uses (tests/src/TestDdpZmp.cpp:88); one thread per problem
+    import torch
+
+    wz = workloads.ddp_zmp_batch(batch=65536)
+    psz = problem.DdpZmpProblemSet(wz["ref_zmp"], wz["com_z"], wz["sched_id"], wz["x0"], wz["mass"], wz["dt"], u_init=wz["u_init"])
+    cfgz = problem.ddp_config(max_iter=3)
+    engz = engine.DdpZmpEngine(psz.N, psz.batch, len(wz["ref_zmp"]))
+    resz = engz.solve(psz, cfgz)
+    _, dtz = _timed(lambda: engz.solve(psz, cfgz), 2)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    keepz = {k_: torch.from_numpy(np.ascontiguousarray(getattr(psz, k_))).to(dev) for k_ in ("ref_zmp", "com_z", "sched_id", "x0", "u_init")}
+    bsz = psz.as_struct()
+    for k_, t_ in keepz.items():
+        setattr(bsz, k_, t_.data_ptr())
+    d_outz = dict(x=torch.empty((psz.batch, psz.N + 1, 6), dtype=torch.float64, device=dev),
+                  u=torch.empty((psz.batch, psz.N, 3), dtype=torch.float64, device=dev),
+                  iters=torch.empty(psz.batch, dtype=torch.int32, device=dev), status=torch.empty(psz.batch, dtype=torch.int32, device=dev))
+    rsz = _abi.DdpResult()
+    for k_, t_ in d_outz.items():
+        setattr(rsz, k_, t_.data_ptr())
+    stz = torch.cuda.current_stream(dev)
+    msz = []
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stz)
+        engz.solve_device(bsz, cfgz, rsz, stz.cuda_stream)
+        e1.record(stz)
+        torch.cuda.synchronize(dev)
+        msz.append(e0.elapsed_time(e1))
+    engz.close()
+    kz = 1024
+    psz_sub = problem.DdpZmpProblemSet(wz["ref_zmp"], wz["com_z"], wz["sched_id"][:kz], wz["x0"][:kz], wz["mass"], wz["dt"], u_init=wz["u_init"][:kz])
+    refz = binding.ddp_zmp_solve(psz_sub, cfgz, n_threads=threads)
+    parity_z = bool(np.array_equal(refz.u, resz.u[:kz]) and np.array_equal(refz.x, resz.x[:kz]) and np.array_equal(refz.iters, resz.iters[:kz]))
+    out.append({"workload": wz["name"], "unit": "solves/s", "value": psz.batch / (min(msz[1:]) / 1e3), "e2e": psz.batch / dtz,
+                "kernel_ms": min(msz[1:]), "mean_ddp_iters": float(resz.iters.mean()), "gpu_launches": 1,
+                "algorithmic_bytes_per_solve": 48 + 4 + 2400 + 4848 + 2400 + 16,
+                "parity": {"bit_exact_vs_oracle": parity_z, "checked": kz, "of": int(psz.batch)},
+                "api": "ccc_ddp_zmp_solve: value = CCC_MEM_DEVICE (CUDA events), e2e = CCC_MEM_HOST (pageable host buffers, PCIe bound)"})
+
     w4 = workloads.ddp_srb_config4(batch=8192)
     ps4 = problem.DdpSrbProblemSet.from_workload(w4)
     eng4 = engine.DdpSrbEngine(ps4.N, ps4.batch, ps4.sched.S)

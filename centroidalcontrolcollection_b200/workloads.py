@@ -324,3 +324,29 @@ def linear_mpc_xy_sweep(n_sched=64, per_sched=16, horizon_steps=15, seed=2026010
         sid.append(np.full(per_sched, s, dtype=np.int32))
     sweep.set_initial_states(np.concatenate(x0), np.concatenate(sid))
     return sweep
+
+
+def ddp_zmp_batch(batch=65536, horizon_steps=100, dt=0.02, seed=20260107):
+    """DdpZmp problems as the reference's test loop poses them (tests/src/TestDdpZmp.cpp:15-135: mass 100, horizon
+    2 s / 0.02 s, the six-step walking plan): 4 schedules = the plan's reference ZMP sampled at t0 = 0, 1.9, 2.4 and
+    4.95 s, `batch` perturbed states (pos +- 0.03 around the reference ZMP, vel +- 0.1, height 1 +- 0.02) and the
+    warm start of a controller that held the CoM over the ZMP (u = (c_x, c_y, m g))."""
+    from .schedule import FootstepPlans
+
+    G = 9.80665
+    times = (0.0, 1.9, 2.4, 4.95)
+    # reference ZMP on the horizon grid through the schedule compiler's definition (_walking_limits: one epsilon, refZmp)
+    ref_zmp = np.zeros((len(times), horizon_steps + 1, 3))
+    for s, t0 in enumerate(times):
+        r, _, _ = _walking_limits(0.2, 0.2, t0, horizon_steps + 1, dt, eps_reps=1)
+        ref_zmp[s, :, :2] = r
+    rng = np.random.default_rng(seed)
+    sched_id = (np.arange(batch) % len(times)).astype(np.int32)
+    x0 = np.zeros((batch, 6))
+    x0[:, [0, 2]] = ref_zmp[sched_id, 0, :2] + rng.uniform(-0.03, 0.03, (batch, 2))
+    x0[:, [1, 3]] = rng.uniform(-0.1, 0.1, (batch, 2))
+    x0[:, 4] = 1.0 + rng.uniform(-0.02, 0.02, batch)
+    u_init = np.zeros((batch, horizon_steps, 3))
+    u_init[:, :, 0], u_init[:, :, 1], u_init[:, :, 2] = x0[:, None, 0], x0[:, None, 2], 100.0 * G
+    return dict(name=f"DdpZmp N={horizon_steps} dt={dt} 4 walking-plan schedules batch={batch} warm start max_iter=3", mass=100.0, dt=dt,
+                ref_zmp=ref_zmp, com_z=np.ones((len(times), horizon_steps + 1)), sched_id=sched_id, x0=x0, u_init=u_init)
