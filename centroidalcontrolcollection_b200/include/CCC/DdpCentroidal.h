@@ -4,8 +4,10 @@
  * WeightParam, InitialParam), same constructor (:342) and planOnce signature (:351-354), same
  * defaults, same public force_scale_limits_ (:364).  Differences, all forced by this image:
  *  - Eigen is absent, so Vector3d = std::array<double,3> and VectorXd = std::vector<double>;
- *  - ddp_solver_->config() becomes config() (a ccc_ddp_config_t, same field names);
- *    ddp_solver_->controlData().u_list becomes u_list(), traceDataList().back().iter lastIter();
+ *  - ddp_solver_ / ddp_problem_ are views (CCC/detail/DdpFacade.h) with the members the reference's callers use:
+ *    ddp_solver_->config() (max_iter, lambdas, horizon_steps, ...), ->controlData().u_list,
+ *    ->traceDataList().back().iter, ddp_problem_->dt(), ->inputDim(t); config(), u_list(b), lastIter(b) reach
+ *    the same state per problem of a batch;
  *  - new: planBatch() solves many (schedule, initial state) pairs in one engine call.
  * planOnce() = sample callbacks -> batch of one -> ccc_ddp_centroidal_solve -> u_list[0].
  * Header-only; link with libccc_b200.so.  No CPU fallback: throws std::runtime_error without a GPU.
@@ -20,6 +22,7 @@
 
 #include "../../../include/ccc_b200.h"
 #include "Contact.h"
+#include "detail/DdpFacade.h"
 
 namespace CCC
 {
@@ -93,13 +96,16 @@ public:
 public:
   /** reference :342 and src/DdpCentroidal.cpp:193-211 (solver configuration). */
   DdpCentroidal(double mass, double horizon_dt, int horizon_steps, const WeightParam & weight_param = WeightParam())
-  : mass_(mass), dt_(horizon_dt), horizon_steps_(horizon_steps), weight_param_(weight_param)
+  : ddp_solver_(std::make_shared<detail::DdpSolverFacade<VectorXd>>()), ddp_problem_(std::make_shared<detail::DdpProblemFacade>()),
+    mass_(mass), dt_(horizon_dt), horizon_steps_(horizon_steps), weight_param_(weight_param), config_(ddp_solver_->config_)
   {
     ccc_ddp_config_default(&config_);
     config_.with_input_constraint = 1;
+    config_.horizon_steps = horizon_steps;
     config_.initial_lambda = 1e-6;
     config_.lambda_min = 1e-8;
     config_.lambda_thre = 1e-7;
+    ddp_problem_->dt_ = horizon_dt;
   }
 
   ~DdpCentroidal()
@@ -118,6 +124,12 @@ public:
     BatchItem item;
     item.schedule = 0;
     item.initial_param = initial_param;
+    // ddp_problem_->setMotionParamFunc (src/DdpCentroidal.cpp:218): inputDim(t) evaluates it
+    ddp_problem_->input_dim_func_ = [motion_param_func](double t) {
+      int n = 0;
+      for(const auto & contact : motion_param_func(t).contact_list) n += contact->ridgeNum();
+      return n;
+    };
     return planBatch({motion_param_func}, {ref_data_func}, {item}, current_time)[0];
   }
 
@@ -226,6 +238,9 @@ public:
     batch_ = B;
     std::vector<VectorXd> first(B);
     for(int b = 0; b < B; b++) first[b] = u_list(b)[0];
+    // what the reference's callers read from the solver object after planOnce (problem 0 of a batch)
+    ddp_solver_->control_data_.u_list = u_list(0);
+    ddp_solver_->trace_data_list_.assign(1, {iters_[0]});
     return first;
   }
 
@@ -348,7 +363,7 @@ public:
   }
 
   /** ddp_solver_->config() of the reference (max_iter, lambdas, ...). */
-  ccc_ddp_config_t & config() { return config_; }
+  detail::DdpConfiguration & config() { return config_; }
 
   /** ddp_solver_->controlData().u_list of problem b of the last call (stage vectors sized inputDim). */
   std::vector<VectorXd> u_list(int b = 0) const
@@ -381,6 +396,10 @@ public:
   int horizonSteps() const { return horizon_steps_; }
 
 public:
+  //! DDP solver as the reference's callers see it (reference include/CCC/DdpCentroidal.h:361)
+  std::shared_ptr<detail::DdpSolverFacade<VectorXd>> ddp_solver_;
+  //! DDP problem as the reference's callers see it (:358)
+  std::shared_ptr<detail::DdpProblemFacade> ddp_problem_;
   //! Robot mass [kg]
   double mass_ = 0;
   //! Force scale limits (lower, upper), reference include/CCC/DdpCentroidal.h:364
@@ -400,7 +419,7 @@ private:
   double dt_;
   int horizon_steps_;
   WeightParam weight_param_;
-  ccc_ddp_config_t config_;
+  detail::DdpConfiguration & config_; // lives in ddp_solver_
   ccc_ddp_centroidal_ws_t * ws_ = nullptr;
   int ws_batch_ = 0, ws_sched_ = 0, batch_ = 0;
   std::vector<int32_t> m_, sched_id_, iters_, status_;

@@ -5,7 +5,9 @@
  * configuration of src/DdpSingleRigidBody.cpp:261-281; planOnce (:391-394, src :283-307); public
  * force_scale_limits_ (:405).  Eigen is absent from this image: Vector3d = std::array<double,3>,
  * Matrix3d = row-major std::array<double,9>, VectorXd = std::vector<double>.
- * ddp_solver_->config() -> config(); controlData().u_list -> u_list(b); traceDataList().back().iter -> lastIter(b).
+ * ddp_solver_ / ddp_problem_ are views (CCC/detail/DdpFacade.h) with the members the reference's callers use
+ * (config().max_iter / horizon_steps, controlData().u_list, traceDataList().back().iter, dt(), inputDim(t));
+ * config(), u_list(b), lastIter(b) reach the same state per problem of a batch.
  * New: planBatch() — many (schedule, initial state) pairs in one engine call.
  * Header-only; link with libccc_b200.so.  No CPU fallback: throws std::runtime_error without a GPU.
  */
@@ -17,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include "detail/DdpFacade.h"
 #include "detail/RidgeTables.h"
 
 namespace CCC
@@ -100,10 +103,13 @@ public:
 
 public:
   DdpSingleRigidBody(double mass, double horizon_dt, int horizon_steps, const WeightParam & weight_param = WeightParam())
-  : mass_(mass), dt_(horizon_dt), horizon_steps_(horizon_steps), weight_param_(weight_param)
+  : ddp_solver_(std::make_shared<detail::DdpSolverFacade<VectorXd>>()), ddp_problem_(std::make_shared<detail::DdpProblemFacade>()),
+    mass_(mass), dt_(horizon_dt), horizon_steps_(horizon_steps), weight_param_(weight_param), config_(ddp_solver_->config_)
   {
     ccc_ddp_config_default(&config_);
     config_.with_input_constraint = 1;
+    config_.horizon_steps = horizon_steps;
+    ddp_problem_->dt_ = horizon_dt;
     config_.initial_lambda = 1e-6;
     config_.lambda_min = 1e-8;
     config_.lambda_thre = 1e-7;
@@ -123,6 +129,12 @@ public:
   {
     BatchItem item;
     item.initial_param = initial_param;
+    // ddp_problem_->setMotionParamFunc (src/DdpSingleRigidBody.cpp:288): inputDim(t) evaluates it
+    ddp_problem_->input_dim_func_ = [motion_param_func](double t) {
+      int n = 0;
+      for(const auto & contact : motion_param_func(t).contact_list) n += contact->ridgeNum();
+      return n;
+    };
     return planBatch({motion_param_func}, {ref_data_func}, {item}, current_time)[0];
   }
 
@@ -220,10 +232,12 @@ public:
     batch_ = B;
     std::vector<VectorXd> first(B);
     for(int b = 0; b < B; b++) first[b] = u_list(b)[0];
+    ddp_solver_->control_data_.u_list = u_list(0);
+    ddp_solver_->trace_data_list_.assign(1, {iters_[0]});
     return first;
   }
 
-  ccc_ddp_config_t & config() { return config_; }
+  detail::DdpConfiguration & config() { return config_; }
 
   std::vector<VectorXd> u_list(int b = 0) const
   {
@@ -252,6 +266,9 @@ public:
   int horizonSteps() const { return horizon_steps_; }
 
 public:
+  //! DDP solver / problem as the reference's callers see them (reference include/CCC/DdpSingleRigidBody.h:398-402)
+  std::shared_ptr<detail::DdpSolverFacade<VectorXd>> ddp_solver_;
+  std::shared_ptr<detail::DdpProblemFacade> ddp_problem_;
   double mass_ = 0;
   //! Force scale limits (lower, upper), reference include/CCC/DdpSingleRigidBody.h:405
   std::array<double, 2> force_scale_limits_ = {0.0, 1e6};
@@ -270,7 +287,7 @@ private:
   double dt_;
   int horizon_steps_;
   WeightParam weight_param_;
-  ccc_ddp_config_t config_;
+  detail::DdpConfiguration & config_; // lives in ddp_solver_
   ccc_ddp_srb_ws_t * ws_ = nullptr;
   int ws_batch_ = 0, ws_sched_ = 0, batch_ = 0;
   detail::RidgeTables tab_;

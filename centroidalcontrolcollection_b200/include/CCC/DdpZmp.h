@@ -13,7 +13,10 @@
 #include <string>
 #include <vector>
 
+#include <memory>
+
 #include "../../../include/ccc_b200.h"
+#include "detail/DdpFacade.h"
 
 namespace CCC
 {
@@ -70,9 +73,13 @@ public:
 
 public:
   DdpZmp(double mass, double horizon_dt, int horizon_steps, const WeightParam & weight_param = WeightParam())
-  : mass_(mass), dt_(horizon_dt), horizon_steps_(horizon_steps), weight_param_(weight_param)
+  : ddp_solver_(std::make_shared<detail::DdpSolverFacade<InputDimVector>>()), ddp_problem_(std::make_shared<detail::DdpProblemFacade>()),
+    mass_(mass), dt_(horizon_dt), horizon_steps_(horizon_steps), weight_param_(weight_param), config_(ddp_solver_->config_)
   {
     ccc_ddp_config_default(&config_); // nmpc_ddp defaults; the reference only sets horizon_steps (:269)
+    config_.horizon_steps = horizon_steps;
+    ddp_problem_->dt_ = horizon_dt;
+    ddp_problem_->fixed_input_dim_ = 3;
   }
   ~DdpZmp()
   {
@@ -169,10 +176,12 @@ public:
       out[b].zmp = {u0[0], u0[1]};
       out[b].force_z = u0[2];
     }
+    ddp_solver_->control_data_.u_list = u_list(0);
+    ddp_solver_->trace_data_list_.assign(1, {iters_[0]});
     return out;
   }
 
-  ccc_ddp_config_t & config() { return config_; }
+  detail::DdpConfiguration & config() { return config_; }
   /** ddp_solver_->controlData().u_list of problem b of the last call */
   std::vector<InputDimVector> u_list(int b = 0) const
   {
@@ -197,13 +206,16 @@ public:
   int horizonSteps() const { return horizon_steps_; }
 
 public:
+  //! DDP solver / problem as the reference's callers see them (reference include/CCC/DdpZmp.h:295-299)
+  std::shared_ptr<detail::DdpSolverFacade<InputDimVector>> ddp_solver_;
+  std::shared_ptr<detail::DdpProblemFacade> ddp_problem_;
   double mass_ = 0;
 
 private:
   double dt_;
   int horizon_steps_;
   WeightParam weight_param_;
-  ccc_ddp_config_t config_;
+  detail::DdpConfiguration & config_; // lives in ddp_solver_
   ccc_ddp_zmp_ws_t * ws_ = nullptr;
   int ws_batch_ = 0, ws_sched_ = 0, batch_ = 0;
   std::vector<int32_t> sched_id_, iters_, status_;

@@ -134,18 +134,20 @@ int main()
     ip.pos = sim.pos;
     ip.vel = sim.vel;
     ip.angular_momentum = sim.L;
-    if(ddp.hasSolution())
+    // the reference's own expressions (tests/src/TestDdpCentroidal.cpp:102-116), through the ddp_solver_ / ddp_problem_ views
+    ip.u_list = ddp.ddp_solver_->controlData().u_list;
+    if(!ip.u_list.empty())
     {
-      ip.u_list = ddp.u_list();
-      for(int i = 0; i < horizon_steps; i++)
+      for(int i = 0; i < ddp.ddp_solver_->config().horizon_steps; i++)
       {
-        const int input_dim = motion_param_func(t + i * ddp.dt()).contact_list.empty() ? 0 : 16;
-        if(static_cast<int>(ip.u_list[i].size()) != input_dim) ip.u_list[i].assign(input_dim, 0.0);
+        double tmp_time = t + i * ddp.ddp_problem_->dt();
+        int input_dim = ddp.ddp_problem_->inputDim(tmp_time);
+        if(static_cast<int>(ip.u_list[i].size()) != input_dim) ip.u_list[i].assign(input_dim, 0.0); // Eigen: setZero(input_dim)
       }
     }
     CCC::VectorXd scales = ddp.planOnce(motion_param_func, ref_data_func, ip, t);
-    if(durations.empty()) first_iter = ddp.lastIter();
-    ddp.config().max_iter = 1; // from the second control cycle on (reference :116)
+    if(durations.empty()) first_iter = ddp.ddp_solver_->traceDataList().back().iter; // :129
+    ddp.ddp_solver_->config().max_iter = 1; // Set max_iter from second simulation iteration (:116)
     durations.push_back(1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count());
 
     const auto mp = motion_param_func(t);

@@ -54,20 +54,20 @@ int main()
     ip.ori = {sim.ang[2], sim.ang[1], sim.ang[0]}; // the plant keeps (X, Y, Z), the controller (Z, Y, X) (reference :92)
     ip.linear_vel = sim.vel;
     ip.angular_vel = sim.omega;
-    if(ddp.hasSolution())
+    ip.u_list = ddp.ddp_solver_->controlData().u_list; // reference :118-130 through the ddp_solver_ / ddp_problem_ views
+    if(!ip.u_list.empty())
     {
-      ip.u_list = ddp.u_list();
       for(int i = 0; i < horizon_steps; i++)
       {
-        const int input_dim = motion_param_func(t + i * ddp.dt()).contact_list.empty() ? 0 : 16;
+        const int input_dim = ddp.ddp_problem_->inputDim(t + i * ddp.ddp_problem_->dt());
         if(static_cast<int>(ip.u_list[i].size()) != input_dim) ip.u_list[i].assign(input_dim, 0.0);
       }
     }
     else
       first_iter = -1;
     const Srb::VectorXd scales = ddp.planOnce(motion_param_func, ref_data_func, ip, t);
-    if(first_iter == -1) first_iter = ddp.lastIter();
-    ddp.config().max_iter = 1; // from the second control cycle on (reference :133)
+    if(first_iter == -1) first_iter = ddp.ddp_solver_->traceDataList().back().iter; // :146
+    ddp.ddp_solver_->config().max_iter = 1; // Set max_iter from second simulation iteration (:132)
 
     const auto mp = motion_param_func(t);
     const auto rd = ref_data_func(t);

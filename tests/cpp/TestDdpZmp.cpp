@@ -11,7 +11,7 @@ int main()
   const double horizon_dt = 0.02, sim_dt = 0.005, mass = 100.0, com_height = 1.0;
   const int horizon_steps = 100;
   CCC::DdpZmp ddp(mass, horizon_dt, horizon_steps);
-  ddp.config().max_iter = 3; // reference :28
+  ddp.ddp_solver_->config().max_iter = 3; // reference :28
 
   FootstepManager fm = walkingPlan();
   ComZmpSim3d sim(mass, sim_dt);
@@ -32,8 +32,8 @@ int main()
     CCC::DdpZmp::InitialParam ip;
     ip.pos = {sim.x[0], sim.y[0], sim.z[0]};
     ip.vel = {sim.x[1], sim.y[1], sim.z[1]};
-    if(ddp.hasSolution())
-      ip.u_list = ddp.u_list();
+    if(!ddp.ddp_solver_->controlData().u_list.empty())
+      ip.u_list = ddp.ddp_solver_->controlData().u_list;
     else
       ip.u_list.assign(horizon_steps, CCC::DdpZmp::InputDimVector{sim.x[0], sim.y[0], mass * kG}); // reference :84-93
     planned = ddp.planOnce(ref_data_func, ip, t);
