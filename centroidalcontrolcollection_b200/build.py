@@ -45,6 +45,7 @@ def build(force=False, verbose=False, ab_variants=None):
                 return LIB
             nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
             cmd = [nvcc] + NVCC_FLAGS + (["-DCCC_AB_VARIANTS"] if ab_variants else []) + (["-Xptxas", "-v"] if verbose else [])
+            cmd += os.environ.get("CCC_EXTRA_NVCC_FLAGS", "").split()  # A/B measurement builds (e.g. -DCCC_NO_GAIN_PREFETCH)
             tmp = f"{LIB}.tmp.{os.getpid()}"
             cmd += ["-t", "0", "-o", tmp] + sources()
             try:

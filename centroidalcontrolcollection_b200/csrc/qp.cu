@@ -120,15 +120,15 @@ ccc_qp_ws * qp_ws_create(int n, int n_eq, int n_ineq, int max_batch, int max_gro
   const int shape = qp_shape(n);
   if(shape == 0)
   {
+    // the attribute belongs to the kernel, not to this workspace: workspaces of several shapes are alive at once (a
+    // controller whose QP size changes from tick to tick), so it is raised to the limit, not to this shape's need
     ok = ok
-         && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)ccc::QpSm<128, false, false>::bytes(n, ld)),
+         && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit),
                             "cudaFuncSetAttribute(smem)");
     ws->rcap = qp_rcap(n, n_eq);
     if(ws->rcap > 0)
       ok = ok
-           && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)ccc::QpSm<128, false, true>::bytes(n, ld, ws->rcap)),
+           && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit),
                               "cudaFuncSetAttribute(smem, packed R)")
            && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
                               "cudaFuncSetAttribute(carveout)");

@@ -134,3 +134,24 @@ def test_matrix_reuse_and_unpaired_rows(oracle):
     eng2 = engine.QpEngine(n, 0, mi, B)
     rc = engine.lib().ccc_qp_solve(eng2._h, C.addressof(bs), C.addressof(rs), _abi.CCC_MEM_HOST, None)
     assert rc != 0
+
+
+def test_workspaces_of_several_shapes_coexist(oracle):
+    """A controller whose QP size changes from tick to tick (LinearMpcZ: one variable per contact stage of the horizon)
+    keeps one workspace per shape; the shared-memory attribute of the kernels must not follow the last one created."""
+    from centroidalcontrolcollection_b200 import engine
+
+    rng = np.random.default_rng(9)
+
+    def make(n):
+        M = rng.standard_normal((n, n))
+        return QpProblemSet(M @ M.T + np.eye(n), np.vstack([-np.eye(n), np.eye(n)]), np.tile(np.full(2 * n, 0.3), (4, 1)), None, None,
+                            2 * rng.standard_normal((4, n)))
+
+    big, small = make(96), make(12)
+    e_big = engine.QpEngine(big.n, 0, big.n_ineq, 4)
+    e_small = engine.QpEngine(small.n, 0, small.n_ineq, 4)  # created later, needs far less shared memory
+    for ps, eng in ((big, e_big), (small, e_small), (big, e_big)):
+        got, ref = eng.solve(ps), oracle.qp_solve(ps)
+        for f in FIELDS:
+            assert np.array_equal(getattr(ref, f), getattr(got, f)), f
