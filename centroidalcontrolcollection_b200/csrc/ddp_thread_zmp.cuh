@@ -353,19 +353,47 @@ struct ZmpThreadSolver
       xc[i] = X(cur, 0, i);
       X(cand, 0, i) = xc[i];
     }
+    // the gains and the nominal (x, u) of a stage do not depend on the stages before it: they are loaded one stage
+    // ahead, before this stage's stores (which the compiler must assume to alias them), so that their latency hides
+    // behind the stage's arithmetic
+    double Kq[18], kq[3], uq[3], xq[6];
+    for(int j = 0; j < 3; j++)
+    {
+      for(int c = 0; c < 6; c++) Kq[j * 6 + c] = KK(0, j, c);
+      kq[j] = KL(0, j);
+      uq[j] = U(cur, 0, j);
+    }
+    for(int c = 0; c < 6; c++) xq[c] = xc[c];
     for(int k = 0; k < N; k++)
     {
-      double dx[6], uc[3], xn[6];
-      for(int c = 0; c < 6; c++) dx[c] = xc[c] - X(cur, k, c);
+      double Kg[18], kk[3], un[3], dx[6], uc[3], xn[6];
+      for(int e = 0; e < 18; e++) Kg[e] = Kq[e];
+      for(int j = 0; j < 3; j++)
+      {
+        kk[j] = kq[j];
+        un[j] = uq[j];
+      }
+      for(int c = 0; c < 6; c++) dx[c] = xc[c] - xq[c];
+      if(k + 1 < N)
+      {
+        for(int j = 0; j < 3; j++)
+        {
+          for(int c = 0; c < 6; c++) Kq[j * 6 + c] = KK(k + 1, j, c);
+          kq[j] = KL(k + 1, j);
+          uq[j] = U(cur, k + 1, j);
+        }
+        for(int c = 0; c < 6; c++) xq[c] = X(cur, k + 1, c);
+      }
       for(int j = 0; j < 3; j++)
       {
         double fb = 0.0;
-        for(int c = 0; c < 6; c++) fb = fma(KK(k, j, c), dx[c], fb);
-        uc[j] = fma(alpha, KL(k, j), U(cur, k, j)) + fb;
-        U(cand, k, j) = uc[j];
+        for(int c = 0; c < 6; c++) fb = fma(Kg[j * 6 + c], dx[c], fb);
+        uc[j] = fma(alpha, kk[j], un[j]) + fb;
       }
       stateEq(k, xc, uc, xn);
-      C(cand, k) = runningCost(k, xc, uc);
+      const double ck = runningCost(k, xc, uc);
+      for(int j = 0; j < 3; j++) U(cand, k, j) = uc[j];
+      C(cand, k) = ck;
       for(int i = 0; i < 6; i++)
       {
         xc[i] = xn[i];
@@ -520,12 +548,24 @@ CCC_TD void zmp_thread_run(const ccc_ddp_zmp_batch_t & bt, const ccc_ddp_config_
   const int rv = sv.solve(bt.x0 + (size_t)b * 6, bt.u_init ? bt.u_init + (size_t)b * N * 3 : nullptr, 1, &iters,
                           res.alpha_idx ? res.alpha_idx + (size_t)b * tl : nullptr, res.lambda_trace ? res.lambda_trace + (size_t)b * tl : nullptr,
                           tl, 1);
+  // copies out of the interleaved storage: a block of loads, then its stores (the loads of one block are in flight
+  // together instead of one round trip per element)
   if(res.x)
-    for(int k = 0; k <= N; k++)
-      for(int i = 0; i < 6; i++) res.x[((size_t)b * (N + 1) + k) * 6 + i] = sv.X(sv.cur, k, i);
+    for(int k = 0; k <= N; k += 2)
+    {
+      double v[12];
+      const int nk = k + 1 <= N ? 2 : 1;
+      for(int e = 0; e < 6 * nk; e++) v[e] = sv.X(sv.cur, k + e / 6, e % 6);
+      for(int e = 0; e < 6 * nk; e++) res.x[((size_t)b * (N + 1) + k) * 6 + e] = v[e];
+    }
   if(res.u)
-    for(int k = 0; k < N; k++)
-      for(int j = 0; j < 3; j++) res.u[((size_t)b * N + k) * 3 + j] = sv.U(sv.cur, k, j);
+    for(int k = 0; k < N; k += 4)
+    {
+      double v[12];
+      const int nk = N - k < 4 ? N - k : 4;
+      for(int e = 0; e < 3 * nk; e++) v[e] = sv.U(sv.cur, k + e / 3, e % 3);
+      for(int e = 0; e < 3 * nk; e++) res.u[((size_t)b * N + k) * 3 + e] = v[e];
+    }
   if(res.cost) res.cost[b] = sv.sumCost(sv.cur);
   if(res.iters) res.iters[b] = iters;
   if(res.status) res.status[b] = rv;

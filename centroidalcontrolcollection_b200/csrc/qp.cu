@@ -12,9 +12,10 @@ __global__ void __launch_bounds__(ccc::kQpThreads, 1) qp_setup_kernel(int n, int
                                                                        const double * C, double * Lg, double * invd, double * J0,
                                                                        double * At, double * Ct, int * ok_flag, double * J0s)
 {
+  __shared__ double s_bcast[256];
   const size_t g = blockIdx.x, nn = (size_t)n * n;
   ccc::qp_setup_cta(n, me, mi, Q + g * nn, A ? A + g * me * n : nullptr, C, Lg + g * nn, invd + g * n, J0 + g * nn, At + g * n * me, Ct,
-                    ok_flag + 4 * g, J0s ? J0s + g * n * (n | 1) : nullptr, g == 0);
+                    ok_flag + 4 * g, J0s ? J0s + g * n * (n | 1) : nullptr, g == 0, s_bcast);
 }
 
 template<int NT, bool kGlobal, bool kPackedR>
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(NT, kPackedR ? 2 : 1) qp_solve_kernel(const __
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
+constexpr size_t kSmemDynMax = kSmemLimit - 1024; // the opt-in limit covers static shared memory too (the kernels hold a few bytes)
 constexpr size_t kSmemTwoCtas = (228 * 1024 - 2 * 1024) / 2 - 128; // dynamic shared memory of one of two co-resident CTAs
 
 /** Largest number of columns a packed R may have so that two CTAs fit on an SM (0: not even the smallest useful one). */
@@ -63,7 +65,7 @@ int qp_rcap(int n, int me)
 int qp_shape(int n)
 {
   if(n > 128) return 2;
-  return ccc::QpSm<128, false, false>::bytes(n, n | 1) <= kSmemLimit ? 0 : 1;
+  return ccc::QpSm<128, false, false>::bytes(n, n | 1) <= kSmemDynMax ? 0 : 1;
 }
 
 template<class T>
@@ -123,12 +125,12 @@ ccc_qp_ws * qp_ws_create(int n, int n_eq, int n_ineq, int max_batch, int max_gro
     // the attribute belongs to the kernel, not to this workspace: workspaces of several shapes are alive at once (a
     // controller whose QP size changes from tick to tick), so it is raised to the limit, not to this shape's need
     ok = ok
-         && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit),
+         && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDynMax),
                             "cudaFuncSetAttribute(smem)");
     ws->rcap = qp_rcap(n, n_eq);
     if(ws->rcap > 0)
       ok = ok
-           && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit),
+           && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDynMax),
                               "cudaFuncSetAttribute(smem, packed R)")
            && ccc_host::check(cudaFuncSetAttribute(qp_solve_kernel<128, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
                               "cudaFuncSetAttribute(carveout)");

@@ -21,7 +21,7 @@
 
 namespace ccc
 {
-constexpr int kQpThreads = 128; // setup kernel; the solve kernel runs NT = 128 or 256 threads
+constexpr int kQpThreads = 256; // setup kernel; the solve kernel runs NT = 128 or 256 threads
 
 struct QpParams
 {
@@ -796,50 +796,99 @@ struct QpCta
 namespace ccc
 {
 /** Batch-invariant setup, one CTA: L = chol(Q) (scratch Lg), J0 = L^-T, transposed A and C.
- *  Evaluation order: oracle/qp.hpp DenseQpShared::setup. */
+ *  Evaluation order: oracle/qp.hpp DenseQpShared::setup — every entry is the oracle's sequential fma chain over
+ *  j ascending.  The oracle writes the chains entry by entry (left looking); here they advance together, one term per
+ *  step j (right looking): once column j of L (of L^-1) is final, every later entry takes its j-th term.  The terms
+ *  of one entry still arrive in ascending j, so the bits are the same, but a step is n^2 / 2 independent fma spread
+ *  over the CTA with coalesced accesses (thread = column) instead of n-long dependent chains per thread
+ *  (n = 240: 7.0 ms -> well under 1 ms, profiles/r02_summary.md).
+ *  Lg holds the trailing matrix on and below the diagonal and L' above it (column j of L contiguous). */
 CCC_DEV void qp_setup_cta(int n, int me, int mi, const double * Q, const double * A, const double * C, double * Lg,
-                          double * invd, double * J0, double * At, double * Ct, int * ok_flag, double * J0s = nullptr,
-                          bool write_ct = true)
+                          double * invd, double * J0, double * At, double * Ct, int * ok_flag, double * J0s, bool write_ct,
+                          double * bcast /* n doubles of shared memory: the column every thread reads in a step */)
 {
   const int tid = thread_id();
   if(tid == 0) *ok_flag = 1;
+  // trailing matrix = lower triangle of Q; J0 = identity (the right-hand sides e_i, row i)
+  for(int i = 0; i < n; i++)
+    for(int k = tid; k < n; k += kQpThreads)
+    {
+      if(k <= i) Lg[(size_t)i * n + k] = Q[(size_t)i * n + k];
+      J0[(size_t)i * n + k] = i == k ? 1.0 : 0.0;
+    }
   cta_sync();
-  for(int k = 0; k < n; k++)
+  constexpr int kU = 32; // entries in flight per thread: the loads of a block are issued before its fma / stores
+  for(int j = 0; j < n; j++)
   {
+    // column j is final: pivot (every thread evaluates it for itself), L(i, j) = a(i, j) / d, kept as row j of L'
+    // (above the diagonal of Lg, for the second phase) and in shared memory (for this step)
+    double acc = Lg[(size_t)j * n + j];
+    const bool bad = !(acc > 0.0);
+    if(bad) acc = 1.0;
+    const double dd = dsqrt(acc);
+    const double inv = 1.0 / dd;
     if(tid == 0)
     {
-      double acc = Q[k * n + k];
-      for(int j = 0; j < k; j++) acc = dfma(-Lg[k * n + j], Lg[k * n + j], acc);
-      if(!(acc > 0.0))
+      if(bad) *ok_flag = 0;
+      invd[j] = inv;
+    }
+    for(int i = j + 1 + tid; i < n; i += kQpThreads)
+    {
+      const double l = Lg[(size_t)i * n + j] * inv;
+      Lg[(size_t)j * n + i] = l;
+      bcast[i] = l;
+    }
+    cta_sync();
+    // j-th term of every later entry a(i, k), j < k <= i: thread k owns column k
+    for(int k = j + 1 + tid; k < n; k += kQpThreads)
+    {
+      const double lk = bcast[k];
+      int i = k;
+      for(; i + kU <= n; i += kU)
       {
-        *ok_flag = 0;
-        acc = 1.0;
+        double v[kU];
+        CCC_UNROLL
+        for(int e = 0; e < kU; e++) v[e] = Lg[(size_t)(i + e) * n + k];
+        CCC_UNROLL
+        for(int e = 0; e < kU; e++) v[e] = dfma(-bcast[i + e], lk, v[e]);
+        CCC_UNROLL
+        for(int e = 0; e < kU; e++) Lg[(size_t)(i + e) * n + k] = v[e];
       }
-      const double dd = dsqrt(acc);
-      Lg[k * n + k] = dd;
-      invd[k] = 1.0 / dd;
-    }
-    cta_sync();
-    for(int i = k + 1 + tid; i < n; i += kQpThreads)
-    {
-      double a = Q[i * n + k];
-      for(int j = 0; j < k; j++) a = dfma(-Lg[i * n + j], Lg[k * n + j], a);
-      Lg[i * n + k] = a * invd[k];
+      for(; i < n; i++) Lg[(size_t)i * n + k] = dfma(-bcast[i], lk, Lg[(size_t)i * n + k]);
     }
     cta_sync();
   }
-  // row i of J0 = L^-1 e_i (forward substitution), one thread per row; z lives in row i of J0
-  for(int i = tid; i < n; i += kQpThreads)
+  // J0 row i = L^-1 e_i: z(i, r) = (delta_ir - sum_{j < r} L(r, j) z(i, j)) / d_r; entries r < i are exact zeros and
+  // their terms leave the later chains unchanged, so only rows i <= j take the j-th term
+  for(int j = 0; j < n; j++)
   {
-    double * zrow = J0 + (size_t)i * n;
-    for(int r = 0; r < n; r++)
+    const double inv = invd[j];
+    for(int i = tid; i <= j; i += kQpThreads)
     {
-      double acc = r == i ? 1.0 : 0.0;
-      for(int j = 0; j < r; j++) acc = dfma(-Lg[r * n + j], zrow[j], acc);
-      zrow[r] = acc * invd[r];
+      const double z = J0[(size_t)i * n + j] * inv;
+      J0[(size_t)i * n + j] = z;
+      bcast[i] = z;
     }
+    cta_sync();
+    const double * Lt = Lg + (size_t)j * n;
+    for(int r = j + 1 + tid; r < n; r += kQpThreads)
+    {
+      const double lrj = Lt[r];
+      int i = 0;
+      for(; i + kU <= j + 1; i += kU)
+      {
+        double v[kU];
+        CCC_UNROLL
+        for(int e = 0; e < kU; e++) v[e] = J0[(size_t)(i + e) * n + r];
+        CCC_UNROLL
+        for(int e = 0; e < kU; e++) v[e] = dfma(-lrj, bcast[i + e], v[e]);
+        CCC_UNROLL
+        for(int e = 0; e < kU; e++) J0[(size_t)(i + e) * n + r] = v[e];
+      }
+      for(; i <= j; i++) J0[(size_t)i * n + r] = dfma(-lrj, bcast[i], J0[(size_t)i * n + r]);
+    }
+    cta_sync();
   }
-  cta_sync();
   if(J0s)
   {
     const int ld = n | 1;

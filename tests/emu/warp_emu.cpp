@@ -382,8 +382,10 @@ extern "C" int32_t ccc_emu_qp_solve(const ccc_qp_batch_t * bt, ccc_qp_result_t *
   if(n > 256 || me + mi > (n > 128 ? 1024 : 512)) return CCC_ERR_INVALID;
   std::vector<double> Lg((size_t)n * n, 0.0), invd(n), J0((size_t)n * n), At((size_t)n * (me ? me : 1)), Ct((size_t)n * mi);
   int ok_flag_buf[4] = {0, 0, 0, 0};
+  std::vector<double> bcast(256, 0.0);
   ccc_emu::run_cta(ccc::kQpThreads, [&]() {
-    ccc::qp_setup_cta(n, me, mi, bt->Q, bt->A, bt->C, Lg.data(), invd.data(), J0.data(), At.data(), Ct.data(), ok_flag_buf);
+    ccc::qp_setup_cta(n, me, mi, bt->Q, bt->A, bt->C, Lg.data(), invd.data(), J0.data(), At.data(), Ct.data(), ok_flag_buf, nullptr, true,
+                      bcast.data());
   });
   ccc::QpParams P{};
   P.n = n;
