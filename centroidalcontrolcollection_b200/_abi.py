@@ -196,6 +196,23 @@ class ZmpMpcResult(C.Structure):
     _fields_ = [("planned_zmp", C.c_void_p), ("iters", C.c_void_p), ("status", C.c_void_p)]
 
 
+class DcmTrackingBatch(C.Structure):
+    """ccc_dcm_tracking_batch_t"""
+
+    _fields_ = [("batch", C.c_int32), ("n_plans", C.c_int32), ("max_knots", C.c_int32), ("reserved0", C.c_int32),
+                ("omega", C.c_double), ("feedback_gain", C.c_double), ("plan_id", C.c_void_p), ("dcm", C.c_void_p),
+                ("current_time", C.c_void_p), ("current_zmp", C.c_void_p), ("n_knots", C.c_void_p), ("knot_time", C.c_void_p),
+                ("knot_zmp", C.c_void_p)]
+
+
+class FootGuidedBatch(C.Structure):
+    """ccc_foot_guided_batch_t"""
+
+    _fields_ = [("batch", C.c_int32), ("n_plans", C.c_int32), ("omega", C.c_double), ("plan_id", C.c_void_p),
+                ("capture_point", C.c_void_p), ("current_time", C.c_void_p), ("transit_start_zmp", C.c_void_p),
+                ("transit_end_zmp", C.c_void_p), ("transit_start_time", C.c_void_p), ("transit_duration", C.c_void_p)]
+
+
 def ptr(a):
     """Address of a C-contiguous numpy array (or None)."""
     if a is None:

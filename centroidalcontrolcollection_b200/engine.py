@@ -23,6 +23,7 @@ EXPORTS = [
     "ccc_ddp_zmp_create", "ccc_ddp_zmp_destroy", "ccc_ddp_zmp_solve", "ccc_ddp_zmp_last_launches",
     "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
     "ccc_fp64_peak_tflops",
+    "ccc_dcm_tracking_plan", "ccc_foot_guided_plan",
     "ccc_footstep_compile", "ccc_zmp_mpc_create", "ccc_zmp_mpc_destroy", "ccc_zmp_mpc_plan", "ccc_zmp_mpc_last_launches",
     "ccc_linear_mpc_xy_create", "ccc_linear_mpc_xy_destroy", "ccc_linear_mpc_xy_solve", "ccc_linear_mpc_xy_last_launches",
 ]
@@ -89,6 +90,9 @@ def lib():
         L.ccc_qp_set_packed.argtypes = [C.c_int32]
         L.ccc_preview_input.restype = C.c_int32
         L.ccc_preview_input.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]
+        for fn in ("ccc_dcm_tracking_plan", "ccc_foot_guided_plan"):
+            getattr(L, fn).restype = C.c_int32
+            getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_footstep_compile.restype = C.c_int32
         L.ccc_footstep_compile.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_zmp_mpc_create.restype = C.c_void_p
@@ -243,6 +247,20 @@ class QpEngine:
         """Tuning hook: 1 (default) = first pass with a packed R, two CTAs per SM, full-R pass for the problems whose
         active set outgrows it; 0 = the full-R kernel alone (one CTA per SM, round 1)."""
         lib().ccc_qp_set_packed(int(on))
+
+
+def dcm_tracking_plan(batch_struct, batch):
+    """ccc_dcm_tracking_plan with host buffers -> control ZMP [B][2] (closed_form.DcmTracking.plan_batch builds the struct)."""
+    out = np.zeros((batch, 2))
+    _check(lib().ccc_dcm_tracking_plan(C.addressof(batch_struct), out.ctypes.data, _abi.CCC_MEM_HOST, None), "ccc_dcm_tracking_plan")
+    return out
+
+
+def foot_guided_plan(batch_struct, batch):
+    """ccc_foot_guided_plan with host buffers -> planned ZMP [B][2]."""
+    out = np.zeros((batch, 2))
+    _check(lib().ccc_foot_guided_plan(C.addressof(batch_struct), out.ctypes.data, _abi.CCC_MEM_HOST, None), "ccc_foot_guided_plan")
+    return out
 
 
 def footstep_compile(plans, tables=None):

@@ -436,6 +436,48 @@ void ccc_zmp_mpc_destroy(ccc_zmp_mpc_ws_t * ws);
 int32_t ccc_zmp_mpc_plan(ccc_zmp_mpc_ws_t * ws, const ccc_zmp_mpc_batch_t * batch, ccc_zmp_mpc_result_t * result, int32_t mem, void * stream);
 int32_t ccc_zmp_mpc_last_launches(const ccc_zmp_mpc_ws_t * ws);
 
+/* ---- closed-form ZMP controllers ---------------------------------------------------------------------
+ * CCC::DcmTracking::planOnce (reference src/DcmTracking.cpp:7-48, Englsberger et al. 2013) and
+ * CCC::FootGuidedControl::planOnce (src/FootGuidedControl.cpp:11-92, Sugihara 2017 / Kojio 2019) for a batch of
+ * initial parameters; problem b reads the reference data of plan plan_id[b].  Both are a handful of exp() and
+ * arithmetic per problem: elementwise kernels, no workspace.  exp() is the CUDA library's (<= 1 ulp from the
+ * correctly rounded value): results agree with a libm evaluation to ~1e-15 relative, not bit for bit.
+ * The reference throws on inconsistent times (a switching time in the past, a negative transition duration, a
+ * transition that does not end in the future); host-buffer calls return CCC_ERR_INVALID for those, device-pointer
+ * calls write NaN for the offending problems. */
+typedef struct
+{
+  int32_t batch;     /* B */
+  int32_t n_plans;   /* P */
+  int32_t max_knots; /* K: row stride of the switching lists */
+  int32_t reserved0;
+  double omega;         /* sqrt(g / com_height) (include/CCC/DcmTracking.h:51) */
+  double feedback_gain; /* DcmTracking::feedback_gain_ (default 2.0) */
+  const int32_t * plan_id;     /* [B] */
+  const double * dcm;          /* [B][2] InitialParam: current DCM */
+  const double * current_time; /* [P] */
+  const double * current_zmp;  /* [P][2] RefData.current_zmp */
+  const int32_t * n_knots;     /* [P] entries of RefData.time_zmp_list (>= 0) */
+  const double * knot_time;    /* [P][K] ascending (the map's keys) */
+  const double * knot_zmp;     /* [P][K][2] */
+} ccc_dcm_tracking_batch_t;
+int32_t ccc_dcm_tracking_plan(const ccc_dcm_tracking_batch_t * batch, double * control_zmp /* [B][2] */, int32_t mem, void * stream);
+
+typedef struct
+{
+  int32_t batch;   /* B */
+  int32_t n_plans; /* P */
+  double omega;    /* sqrt(g / com_height) (include/CCC/FootGuidedControl.h:51) */
+  const int32_t * plan_id;           /* [B] */
+  const double * capture_point;      /* [B][2] InitialParam */
+  const double * current_time;       /* [P] */
+  const double * transit_start_zmp;  /* [P][2] RefData (include/CCC/FootGuidedControl.h:78-91) */
+  const double * transit_end_zmp;    /* [P][2] */
+  const double * transit_start_time; /* [P] */
+  const double * transit_duration;   /* [P] */
+} ccc_foot_guided_batch_t;
+int32_t ccc_foot_guided_plan(const ccc_foot_guided_batch_t * batch, double * planned_zmp /* [B][2] */, int32_t mem, void * stream);
+
 /* ---- CCC::PreviewControl<3,1,1>::calcOptimalInput ------------------------------------------------
  * Batched online part of preview control:  u[b] = -K x[b] + F ref_seq[b]   (gains K (1x3), F (1xN) shared).
  * Replaces: PreviewControl::calcOptimalInput (reference include/CCC/PreviewControl.h:86-89) as called from

@@ -41,6 +41,7 @@ class FootstepManager:
         self.horizon_duration = 10.0
         self.foot_size = np.array([0.1, 0.05])
         self.ref_zmp_list, self.ref_footstance_list = {}, {}
+        self.prev_footstep = None
 
     def append_footstep(self, fs):  # :217-226
         if self.footstep_list and fs.transit_start_time < self.footstep_list[-1].transit_end_time:
@@ -52,7 +53,7 @@ class FootstepManager:
         if fl and fl[0].swing_end_time <= t:
             self.footstance[fl[0].foot] = fl[0].pos
         while fl and fl[0].transit_end_time < t:
-            fl.pop(0)
+            self.prev_footstep = fl.pop(0)
         zl, sl = {}, {}
 
         def emplace(d, k, v):  # std::map::emplace keeps the first value of a key
@@ -105,6 +106,52 @@ class FootstepManager:
     def make_ismpc_ref_data(self, t):  # :370-380
         t += EPS_T
         return self.ref_zmp(t), self.zmp_limits(t)
+
+
+def make_dcm_tracking_ref_data(fm, current_time, horizon_duration=5.0):
+    """FootstepManager::makeDcmTrackingRefData (:260-274; the reference declares horizon_duration as int) ->
+    (current_zmp[2], [(time, zmp[2]), ...])."""
+    t = current_time + EPS_T
+    i = bisect.bisect_right(fm._zk, t)
+    current_zmp = fm.ref_zmp_list[fm._zk[i - 1]]
+    knots = []
+    while i < len(fm._zk) and fm._zk[i] < t + int(horizon_duration):
+        knots.append((fm._zk[i], fm.ref_zmp_list[fm._zk[i]]))
+        i += 1
+    return current_zmp, knots
+
+
+def make_foot_guided_control_ref_data(fm, current_time):
+    """FootstepManager::makeFootGuidedControlRefData (:279-351) -> dict(transit_start_zmp, transit_end_zmp,
+    transit_start_time, transit_duration)."""
+    t = current_time + EPS_T
+    constant_zmp_duration, concat_thre, horizon_margin = 1.0, 0.1, 1e-3
+    fl = fm.footstep_list
+    if not fl:
+        mid = mid_pos(fm.footstance)
+        return dict(transit_start_zmp=mid, transit_end_zmp=mid.copy(), transit_start_time=t + constant_zmp_duration, transit_duration=0.0)
+    fs = fl[0]
+    if t < fs.swing_start_time:
+        rd = dict(transit_start_zmp=mid_pos(fm.footstance), transit_end_zmp=fm.footstance[opposite(fs.foot)].copy(),
+                  transit_start_time=fs.transit_start_time, transit_duration=fs.swing_start_time - fs.transit_start_time)
+        prev = fm.prev_footstep
+        if prev is not None and prev.foot == opposite(fs.foot) and fs.transit_start_time - prev.transit_end_time < concat_thre:
+            rd["transit_start_zmp"] = fm.footstance[opposite(prev.foot)].copy()
+            rd["transit_start_time"] = prev.swing_end_time
+            rd["transit_duration"] = fs.swing_start_time - prev.swing_end_time
+    else:
+        tmp = dict(fm.footstance)
+        tmp[fs.foot] = fs.pos
+        rd = dict(transit_start_zmp=fm.footstance[opposite(fs.foot)].copy(), transit_end_zmp=mid_pos(tmp),
+                  transit_start_time=fs.swing_end_time, transit_duration=fs.transit_end_time - fs.swing_end_time)
+        if len(fl) >= 2:
+            nxt = fl[1]
+            if nxt.foot == opposite(fs.foot) and nxt.transit_start_time - fs.transit_end_time < concat_thre:
+                rd["transit_end_zmp"] = fs.pos.copy()
+                rd["transit_duration"] = nxt.swing_start_time - fs.swing_end_time
+    if rd["transit_start_time"] + rd["transit_duration"] < t + horizon_margin:
+        rd["transit_duration"] += horizon_margin
+    return rd
 
 
 def walking_plan(step_length=0.2, step_width=0.2, transit_duration=0.2, swing_duration=0.8):
