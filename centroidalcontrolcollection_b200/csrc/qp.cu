@@ -105,7 +105,7 @@ ccc_qp_ws * qp_ws_create(int n, int n_eq, int n_ineq, int max_batch, int max_gro
   ok = ok && dev_alloc(ws->At, G * N * ME) && dev_alloc(ws->Ct, N * MI) && dev_alloc(ws->ok_flag, 4 * G) && dev_alloc(ws->counter, 4) && dev_alloc(ws->ovf_list, B);
   if(staging)
   {
-    ok = ok && dev_alloc(ws->d_Q, N * N) && dev_alloc(ws->d_A, N * ME) && dev_alloc(ws->d_C, N * MI);
+    ok = ok && dev_alloc(ws->d_Q, G * N * N) && dev_alloc(ws->d_A, G * N * ME) && dev_alloc(ws->d_C, N * MI) && dev_alloc(ws->d_grp, B);
     ok = ok && dev_alloc(ws->d_c, B * N) && dev_alloc(ws->d_b, B * ME) && dev_alloc(ws->d_d, B * MI) && dev_alloc(ws->d_x, B * N);
     ok = ok && dev_alloc(ws->d_iters, B) && dev_alloc(ws->d_status, B) && dev_alloc(ws->d_nact, B) && dev_alloc(ws->d_active, B * N);
   }
@@ -199,7 +199,7 @@ ccc_qp_ws_t * ccc_qp_create(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max
 void ccc_qp_destroy(ccc_qp_ws_t * ws)
 {
   if(!ws) return;
-  void * ptrs[] = {ws->ovf_list, ws->J0s, ws->gmat, ws->Lg,  ws->invd, ws->J0,  ws->At,  ws->Ct,     ws->ok_flag, ws->counter, ws->d_Q,    ws->d_A,
+  void * ptrs[] = {ws->d_grp, ws->ovf_list, ws->J0s, ws->gmat, ws->Lg,  ws->invd, ws->J0,  ws->At,  ws->Ct,     ws->ok_flag, ws->counter, ws->d_Q,    ws->d_A,
                    ws->d_C, ws->d_c,  ws->d_b, ws->d_d, ws->d_x,    ws->d_iters, ws->d_status, ws->d_nact, ws->d_active};
   for(void * p : ptrs)
     if(p) cudaFree(p);
@@ -262,9 +262,26 @@ extern "C" {
 
 int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_t * res, int32_t mem, void * stream_v)
 {
+  return ccc_qp_solve_grouped(ws, bt, 1, nullptr, res, mem, stream_v);
+}
+
+ccc_qp_ws_t * ccc_qp_create_grouped(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max_batch, int32_t max_groups)
+{
+  return ccc_host::qp_ws_create(n, n_eq, n_ineq, max_batch, max_groups, true);
+}
+
+int32_t ccc_qp_solve_grouped(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, int32_t n_groups, const int32_t * group_id, ccc_qp_result_t * res,
+                             int32_t mem, void * stream_v)
+{
   using ccc_host::check;
   if(!ws || !bt || !res) return ccc_host::fail(CCC_ERR_INVALID, "null argument");
   const int n = bt->n, me = bt->n_eq, mi = bt->n_ineq, B = bt->batch;
+  const size_t Gn = n_groups;
+  if(n_groups <= 0 || n_groups > ws->max_groups) return ccc_host::fail(CCC_ERR_ALLOC, "more matrix groups than the workspace holds");
+  if(n_groups > 1 && !group_id) return ccc_host::fail(CCC_ERR_INVALID, "group_id is NULL");
+  if(mem == CCC_MEM_HOST && group_id)
+    for(int b = 0; b < B; b++)
+      if(group_id[b] < 0 || group_id[b] >= n_groups) return ccc_host::fail(CCC_ERR_INVALID, "group_id out of range");
   if(n != ws->n || me != ws->me || mi != ws->mi) return ccc_host::fail(CCC_ERR_INVALID, "sizes differ from the workspace's");
   if(B <= 0 || B > ws->max_batch) return ccc_host::fail(CCC_ERR_ALLOC, "batch exceeds workspace");
   const bool reuse = bt->Q == nullptr; // Q == NULL: keep the matrices (and their factorisation) of the previous call
@@ -279,8 +296,8 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   if((dst) && !check(cudaMemcpyAsync(dst, src, (nbytes), cudaMemcpyDeviceToHost, stream), "D2H")) return CCC_ERR_CUDA
   if(mem == CCC_MEM_HOST && !reuse)
   {
-    CCC_H2D(ws->d_Q, Q, sizeof(double) * n * n, st);
-    if(me) CCC_H2D(ws->d_A, A, sizeof(double) * me * n, st);
+    CCC_H2D(ws->d_Q, Q, sizeof(double) * Gn * n * n, st);
+    if(me) CCC_H2D(ws->d_A, A, sizeof(double) * Gn * me * n, st);
     CCC_H2D(ws->d_C, C, sizeof(double) * mi * n, st);
     Q = ws->d_Q;
     A = ws->d_A;
@@ -288,10 +305,16 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
   }
   if(!reuse)
   {
-    const int rc = ccc_host::qp_setup_launch(ws, 1, Q, A, C, st);
+    const int rc = ccc_host::qp_setup_launch(ws, n_groups, Q, A, C, st);
     if(rc != CCC_OK) return rc;
   }
-  ccc::QpParams P = ccc_host::qp_params(ws, B, nullptr);
+  const int * grp = group_id;
+  if(mem == CCC_MEM_HOST && group_id)
+  {
+    CCC_H2D(ws->d_grp, group_id, sizeof(int) * B, st);
+    grp = ws->d_grp;
+  }
+  ccc::QpParams P = ccc_host::qp_params(ws, B, grp);
   if(mem != CCC_MEM_HOST)
   {
     P.c = bt->c;
@@ -327,6 +350,7 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * bt, ccc_qp_result_
     }
     ccc::QpParams Pk = P;
     Pk.B = (int)nb;
+    Pk.grp = grp ? grp + lo : nullptr;
     Pk.c = bt->c ? ws->d_c + lo * n : nullptr;
     Pk.b = ws->d_b + lo * me;
     Pk.d = ws->d_d + lo * mi;

@@ -17,7 +17,7 @@ struct ccc_qp_ws
   int n_sm = 148;
   // staging for CCC_MEM_HOST
   double *d_Q = nullptr, *d_A = nullptr, *d_C = nullptr, *d_c = nullptr, *d_b = nullptr, *d_d = nullptr, *d_x = nullptr;
-  int *d_iters = nullptr, *d_status = nullptr, *d_nact = nullptr, *d_active = nullptr;
+  int *d_iters = nullptr, *d_status = nullptr, *d_nact = nullptr, *d_active = nullptr, *d_grp = nullptr;
   cudaStream_t own_stream = nullptr;
   // chunked host path: copy streams and their events
   static constexpr int kMaxChunks = 64;

@@ -22,6 +22,7 @@ EXPORTS = [
     "ccc_ddp_srb_create", "ccc_ddp_srb_destroy", "ccc_ddp_srb_solve", "ccc_ddp_srb_last_launches",
     "ccc_ddp_zmp_create", "ccc_ddp_zmp_destroy", "ccc_ddp_zmp_solve", "ccc_ddp_zmp_last_launches",
     "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
+    "ccc_qp_create_grouped", "ccc_qp_solve_grouped",
     "ccc_fp64_peak_tflops",
     "ccc_dcm_tracking_plan", "ccc_foot_guided_plan",
     "ccc_footstep_compile", "ccc_zmp_mpc_create", "ccc_zmp_mpc_destroy", "ccc_zmp_mpc_plan", "ccc_zmp_mpc_last_launches",
@@ -84,6 +85,10 @@ def lib():
         L.ccc_qp_destroy.restype = None
         L.ccc_qp_solve.restype = C.c_int32
         L.ccc_qp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.ccc_qp_create_grouped.restype = C.c_void_p
+        L.ccc_qp_create_grouped.argtypes = [C.c_int32] * 5
+        L.ccc_qp_solve_grouped.restype = C.c_int32
+        L.ccc_qp_solve_grouped.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_qp_last_launches.restype = C.c_int32
         L.ccc_qp_last_launches.argtypes = [C.c_void_p]
         L.ccc_qp_set_packed.restype = None
@@ -213,8 +218,8 @@ class QpEngine:
     """Batched counterpart of QpSolverCollection::QpSolver (reference src/LinearMpcZmp.cpp:21,69,
     src/IntrinsicallyStableMpc.cpp:28,93): one workspace per problem shape, solves batches that share Q, A, C."""
 
-    def __init__(self, n, n_eq, n_ineq, max_batch):
-        self._h = lib().ccc_qp_create(int(n), int(n_eq), int(n_ineq), int(max_batch))
+    def __init__(self, n, n_eq, n_ineq, max_batch, max_groups=1):
+        self._h = lib().ccc_qp_create_grouped(int(n), int(n_eq), int(n_ineq), int(max_batch), int(max_groups))
         if not self._h:
             raise EngineError(f"ccc_qp_create failed: {last_error()}")
         self.shape = (n, n_eq, n_ineq)
@@ -232,6 +237,14 @@ class QpEngine:
         res = result if result is not None else problem_set.new_result()
         bs, rs = problem_set.as_struct(), res.as_struct()
         _check(lib().ccc_qp_solve(self._h, C.addressof(bs), C.addressof(rs), _abi.CCC_MEM_HOST, None), "ccc_qp_solve")
+        return res
+
+    def solve_grouped(self, grouped, result=None):
+        """Host buffers in / out for a qp.QpGroupedProblemSet (one factorisation per matrix group)."""
+        res = result if result is not None else grouped.new_result()
+        bs, rs = grouped.as_struct(), res.as_struct()
+        _check(lib().ccc_qp_solve_grouped(self._h, C.addressof(bs), int(grouped.G), _abi.ptr(grouped.group_id), C.addressof(rs),
+                                          _abi.CCC_MEM_HOST, None), "ccc_qp_solve_grouped")
         return res
 
     def solve_device(self, batch_struct, result_struct, stream=0):

@@ -301,6 +301,16 @@ void ccc_qp_destroy(ccc_qp_ws_t * ws);
 int32_t ccc_qp_solve(ccc_qp_ws_t * ws, const ccc_qp_batch_t * batch, ccc_qp_result_t * result, int32_t mem, void * stream);
 int32_t ccc_qp_last_launches(const ccc_qp_ws_t * ws);
 
+/* Matrix groups: problem b uses Q / A of group group_id[b] (batch->Q is [G][n][n], batch->A [G][n_eq][n]; C stays
+ * shared), one factorisation per group per call.  For sweeps in which the QP matrices themselves vary: LinearMpcXY
+ * over contact schedules (ccc_linear_mpc_xy_solve does this internally), the wrench distribution of
+ * PreviewControlCentroidal (ForceColl::WrenchDistribution::run as called at reference
+ * src/PreviewControlCentroidal.cpp:127-128: the grasp matrix depends on each problem's CoM position).
+ * ccc_qp_solve(ws, batch, ...) == ccc_qp_solve_grouped(ws, batch, 1, NULL, ...). */
+ccc_qp_ws_t * ccc_qp_create_grouped(int32_t n, int32_t n_eq, int32_t n_ineq, int32_t max_batch, int32_t max_groups);
+int32_t ccc_qp_solve_grouped(ccc_qp_ws_t * ws, const ccc_qp_batch_t * batch, int32_t n_groups, const int32_t * group_id,
+                             ccc_qp_result_t * result, int32_t mem, void * stream);
+
 /* ---- CCC::LinearMpcXY::planOnce on the device, over a sweep of contact / reference schedules -------------
  * Everything LinearMpcXY::planOnce does after sampling its callbacks (reference src/LinearMpcXY.cpp:102-181),
  * for B initial states that use S sampled schedules (problem b uses sched_id[b]):

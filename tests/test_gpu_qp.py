@@ -155,3 +155,26 @@ def test_workspaces_of_several_shapes_coexist(oracle):
         got, ref = eng.solve(ps), oracle.qp_solve(ps)
         for f in FIELDS:
             assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+
+
+def test_matrix_groups(oracle):
+    """ccc_qp_solve_grouped: every problem uses the Q / A of its group; bit-exact against the oracle group by group."""
+    from centroidalcontrolcollection_b200 import engine
+    from centroidalcontrolcollection_b200.qp import QpGroupedProblemSet
+
+    rng = np.random.default_rng(12)
+    n, me, mi, G, B = 20, 2, 40, 37, 500
+    Q = np.zeros((G, n, n))
+    for g in range(G):
+        M = rng.standard_normal((n, n))
+        Q[g] = M @ M.T + np.eye(n)
+    gp = QpGroupedProblemSet(Q, np.vstack([-np.eye(n), np.eye(n)]), np.tile(np.full(mi, 0.4), (B, 1)), rng.integers(0, G, B),
+                             rng.standard_normal((G, me, n)), 0.05 * rng.standard_normal((B, me)), 3 * rng.standard_normal((B, n)))
+    eng = engine.QpEngine(n, me, mi, B, max_groups=G)
+    got = eng.solve_grouped(gp)
+    ref = gp.solve_by_group(lambda ps: oracle.qp_solve(ps))
+    for f in FIELDS:
+        assert np.array_equal(getattr(ref, f), getattr(got, f)), f
+    assert (got.status == 0).all() and (got.n_active > me).any()
+    with pytest.raises(engine.EngineError):
+        engine.QpEngine(n, me, mi, B, max_groups=3).solve_grouped(gp)
