@@ -104,7 +104,11 @@ public:
   {
     auto & fl = footstep_list_;
     if(!fl.empty() && fl.front().swing_end_time <= t) footstance_[fl.front().foot] = fl.front().pos;
-    while(!fl.empty() && fl.front().transit_end_time < t) fl.pop_front();
+    while(!fl.empty() && fl.front().transit_end_time < t)
+    {
+      prev_footstep_ = std::make_shared<Footstep>(fl.front());
+      fl.pop_front();
+    }
     ref_zmp_list_.clear();
     ref_footstance_list_.clear();
     if(fl.empty())
@@ -158,8 +162,68 @@ public:
     return {sub(region[0], scale(0.5, foot_size_)), add(region[1], scale(0.5, foot_size_))};
   }
 
+  /** FootstepManager::makeDcmTrackingRefData (reference tests/src/FootstepManager.h:260-274; horizon_duration is an int
+   *  there): current ZMP and the switching list within the horizon. */
+  void makeDcmTrackingRefData(double current_time, Vec2 & current_zmp, std::map<double, Vec2> & time_zmp_list, int horizon_duration = 5) const
+  {
+    current_time += 1e-6;
+    current_zmp = std::prev(ref_zmp_list_.upper_bound(current_time))->second;
+    time_zmp_list.clear();
+    for(auto it = ref_zmp_list_.upper_bound(current_time); it != ref_zmp_list_.end() && it->first < current_time + horizon_duration; it++)
+      time_zmp_list.emplace(*it);
+  }
+
+  /** FootstepManager::makeFootGuidedControlRefData (:279-351). */
+  void makeFootGuidedControlRefData(double current_time, Vec2 & start_zmp, Vec2 & end_zmp, double & start_time, double & duration) const
+  {
+    current_time += 1e-6;
+    const double constant_zmp_duration = 1.0, concat_thre = 0.1, horizon_margin = 1e-3;
+    if(footstep_list_.empty())
+    {
+      start_zmp = midPos(footstance_);
+      end_zmp = start_zmp;
+      start_time = current_time + constant_zmp_duration;
+      duration = 0;
+      return;
+    }
+    const Footstep & fs = footstep_list_.front();
+    if(current_time < fs.swing_start_time)
+    {
+      start_zmp = midPos(footstance_);
+      end_zmp = footstance_.at(opposite(fs.foot));
+      start_time = fs.transit_start_time;
+      duration = fs.swing_start_time - fs.transit_start_time;
+      if(prev_footstep_ && prev_footstep_->foot == opposite(fs.foot) && fs.transit_start_time - prev_footstep_->transit_end_time < concat_thre)
+      {
+        start_zmp = footstance_.at(opposite(prev_footstep_->foot));
+        start_time = prev_footstep_->swing_end_time;
+        duration = fs.swing_start_time - prev_footstep_->swing_end_time;
+      }
+    }
+    else
+    {
+      start_zmp = footstance_.at(opposite(fs.foot));
+      Footstance tmp = footstance_;
+      tmp[fs.foot] = fs.pos;
+      end_zmp = midPos(tmp);
+      start_time = fs.swing_end_time;
+      duration = fs.transit_end_time - fs.swing_end_time;
+      if(footstep_list_.size() >= 2)
+      {
+        const Footstep & nxt = footstep_list_[1];
+        if(nxt.foot == opposite(fs.foot) && nxt.transit_start_time - fs.transit_end_time < concat_thre)
+        {
+          end_zmp = fs.pos;
+          duration = nxt.swing_start_time - fs.swing_end_time;
+        }
+      }
+    }
+    if(start_time + duration < current_time + horizon_margin) duration += horizon_margin;
+  }
+
   Footstance footstance_;
   std::deque<Footstep> footstep_list_;
+  std::shared_ptr<Footstep> prev_footstep_;
   double horizon_duration_ = 10.0;
   Vec2 foot_size_ = {0.1, 0.05};
   std::map<double, Vec2> ref_zmp_list_;

@@ -6,6 +6,7 @@
  * libccc_b200.so on the GPU.  It is linked INSTEAD of libccc_b200.so by tests/test_cpp_dropin.py only; the
  * product library has no CPU path and nothing in the package refers to this file.
  */
+#include <cmath>
 #include <vector>
 
 #include "../../include/ccc_b200.h"
@@ -81,6 +82,66 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * w, const ccc_qp_batch_t * b, ccc_qp_result_t 
 int32_t ccc_preview_input(int32_t batch, int32_t n, const double * K, const double * F, const double * x, const double * ref, double * u, int32_t, void *)
 {
   return ccc_oracle_preview_input(batch, n, K, F, x, ref, u);
+}
+/* The closed-form controllers have no solver behind them; the shim evaluates the reference's expressions
+ * (src/DcmTracking.cpp:7-48, src/FootGuidedControl.cpp:11-69) with libm so that the C++ drop-ins' host logic runs on the CPU. */
+int32_t ccc_dcm_tracking_plan(const ccc_dcm_tracking_batch_t * bt, double * out, int32_t, void *)
+{
+  const int K = bt->max_knots;
+  for(int b = 0; b < bt->batch; b++)
+  {
+    const int p = bt->plan_id[b];
+    if(p < 0 || p >= bt->n_plans) return CCC_ERR_INVALID;
+    const int nk = bt->n_knots[p];
+    const double t = bt->current_time[p];
+    const double * kt = bt->knot_time + static_cast<size_t>(p) * K;
+    const double * kz = bt->knot_zmp + static_cast<size_t>(p) * K * 2;
+    for(int i = 0; i < nk; i++)
+      if(kt[i] < t) return CCC_ERR_INVALID;
+    for(int a = 0; a < 2; a++)
+    {
+      const double cz = bt->current_zmp[2 * p + a];
+      double target = cz;
+      if(nk > 0)
+      {
+        double dcm_switch = kz[(nk - 1) * 2 + a];
+        for(int i = nk - 2; i >= 0; i--) dcm_switch = kz[i * 2 + a] + std::exp(-1 * bt->omega * (kt[i + 1] - kt[i])) * (dcm_switch - kz[i * 2 + a]);
+        target = cz + std::exp(bt->omega * (t - kt[0])) * (dcm_switch - cz);
+      }
+      out[2 * b + a] = cz + (1.0 + bt->feedback_gain / bt->omega) * (bt->dcm[2 * b + a] - target);
+    }
+  }
+  return CCC_OK;
+}
+int32_t ccc_foot_guided_plan(const ccc_foot_guided_batch_t * bt, double * out, int32_t, void *)
+{
+  for(int b = 0; b < bt->batch; b++)
+  {
+    const int p = bt->plan_id[b];
+    if(p < 0 || p >= bt->n_plans) return CCC_ERR_INVALID;
+    const double w = bt->omega, t = bt->current_time[p], ts = bt->transit_start_time[p], td = bt->transit_duration[p], te = ts + td;
+    if(!(td >= 0) || !(te >= t + 1e-6)) return CCC_ERR_INVALID;
+    for(int a = 0; a < 2; a++)
+    {
+      const double cp = bt->capture_point[2 * b + a], zs = bt->transit_start_zmp[2 * p + a], ze = bt->transit_end_zmp[2 * p + a];
+      double z;
+      if(td == 0)
+        z = zs + 2 * ((cp - zs) - (ze - zs) * std::exp(-1 * w * (ts - t))) / (1.0 - std::exp(-2 * w * (ts - t)));
+      else
+      {
+        const double vel = (ze - zs) / td;
+        if(t <= ts)
+          z = zs + (2 * (cp - zs) + 2 * vel / w * (std::exp(-1 * w * (te - t)) - std::exp(-1 * w * (ts - t)))) / (1.0 - std::exp(-2 * w * (te - t)));
+        else
+        {
+          const double cur = zs + vel * (t - ts);
+          z = cur + (2 * (cp - cur) + 2 * vel / w * (std::exp(-1 * w * (te - t)) - 1.0)) / (1.0 - std::exp(-2 * w * (te - t)));
+        }
+      }
+      out[2 * b + a] = z;
+    }
+  }
+  return CCC_OK;
 }
 const char * ccc_last_error(void) { return "oracle shim"; }
 int32_t ccc_device_count(void) { return 0; }
