@@ -6,6 +6,7 @@
  * libccc_b200.so on the GPU.  It is linked INSTEAD of libccc_b200.so by tests/test_cpp_dropin.py only; the
  * product library has no CPU path and nothing in the package refers to this file.
  */
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -78,6 +79,53 @@ int32_t ccc_qp_solve(ccc_qp_ws_t * w, const ccc_qp_batch_t * b, ccc_qp_result_t 
   bt.A = b->n_eq ? w->A.data() : nullptr;
   bt.C = w->C.data();
   return ccc_oracle_qp_solve(&bt, r, ccc_oracle_hardware_threads());
+}
+ccc_qp_ws_t * ccc_qp_create_grouped(int32_t, int32_t, int32_t, int32_t, int32_t) { return new ccc_qp_ws; }
+/** Matrix groups on the one-group oracle: group by group, results scattered back. */
+int32_t ccc_qp_solve_grouped(ccc_qp_ws_t * w, const ccc_qp_batch_t * b, int32_t n_groups, const int32_t * gid, ccc_qp_result_t * r, int32_t mem, void * st)
+{
+  if(n_groups == 1 || !gid) return ccc_qp_solve(w, b, r, mem, st);
+  const size_t n = b->n, me = b->n_eq, mi = b->n_ineq;
+  for(int g = 0; g < n_groups; g++)
+  {
+    std::vector<int> idx;
+    for(int k = 0; k < b->batch; k++)
+      if(gid[k] == g) idx.push_back(k);
+    if(idx.empty()) continue;
+    const size_t nb = idx.size();
+    std::vector<double> c(nb * n, 0.0), bb(nb * me), d(nb * mi), x(nb * n);
+    std::vector<int32_t> it(nb), stt(nb), na(nb), act(nb * n);
+    for(size_t k = 0; k < nb; k++)
+    {
+      if(b->c) std::copy(b->c + idx[k] * n, b->c + (idx[k] + 1) * n, c.begin() + k * n);
+      if(me) std::copy(b->b + idx[k] * me, b->b + (idx[k] + 1) * me, bb.begin() + k * me);
+      std::copy(b->d + idx[k] * mi, b->d + (idx[k] + 1) * mi, d.begin() + k * mi);
+    }
+    ccc_qp_batch_t bt = *b;
+    bt.batch = static_cast<int32_t>(nb);
+    bt.Q = b->Q + g * n * n;
+    bt.A = me ? b->A + g * me * n : nullptr;
+    bt.c = b->c ? c.data() : nullptr;
+    bt.b = me ? bb.data() : nullptr;
+    bt.d = d.data();
+    ccc_qp_result_t rr{};
+    rr.x = x.data();
+    rr.iters = it.data();
+    rr.status = stt.data();
+    rr.n_active = na.data();
+    rr.active = act.data();
+    const int rc = ccc_oracle_qp_solve(&bt, &rr, 1);
+    if(rc != CCC_OK) return rc;
+    for(size_t k = 0; k < nb; k++)
+    {
+      if(r->x) std::copy(x.begin() + k * n, x.begin() + (k + 1) * n, r->x + idx[k] * n);
+      if(r->iters) r->iters[idx[k]] = it[k];
+      if(r->status) r->status[idx[k]] = stt[k];
+      if(r->n_active) r->n_active[idx[k]] = na[k];
+      if(r->active) std::copy(act.begin() + k * n, act.begin() + (k + 1) * n, r->active + idx[k] * n);
+    }
+  }
+  return CCC_OK;
 }
 int32_t ccc_preview_input(int32_t batch, int32_t n, const double * K, const double * F, const double * x, const double * ref, double * u, int32_t, void *)
 {
