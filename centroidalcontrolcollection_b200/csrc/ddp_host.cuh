@@ -98,13 +98,14 @@ static __global__ void init_queue_kernel(SolveQueue q, int B)
 static __global__ void pack_tables_kernel(const double * __restrict__ ridge,
                                    const double * __restrict__ vertex,
                                    double * __restrict__ tab,
-                                   int stages,
+                                   size_t stages,
                                    int m_max,
                                    int rows)
 {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(idx >= stages * 192) return;
-  const int st = idx / 192, r = idx - st * 192;
+  const size_t st = idx / 192;
+  const int r = (int)(idx - st * 192);
   const int comp = r >> 5, j = r & 31;
   double v = 0.0;
   if(j < m_max)
@@ -448,8 +449,8 @@ struct DdpEngine
 
     // stage tables -> lane-contiguous layout
     {
-      const int total = S * N * 192;
-      pack_tables_kernel<<<(total + 255) / 256, 256, 0, st>>>(in.ridge, in.vertex, tab, S * N, mm, M::TAB_ROWS);
+      const size_t total = (size_t)S * N * 192;
+      pack_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in.ridge, in.vertex, tab, (size_t)S * N, mm, M::TAB_ROWS);
       launches++;
       launches += extra_pack(st, tab);
     }

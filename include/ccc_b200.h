@@ -16,6 +16,9 @@
  *    device, the call only enqueues work on `stream` (a cudaStream_t passed as void*);
  *  - return value: 0 = ok, <0 = CCC_ERR_*; never throws; per-problem solver outcome
  *    is reported in `status[]`, mirroring nmpc_ddp's procOnce return codes;
+ *  - table contents (stage input dimensions m <= m_max, sched_id / plan_id / group_id ranges) are validated for
+ *    CCC_MEM_HOST calls, which return CCC_ERR_INVALID; CCC_MEM_DEVICE calls cannot read them without a
+ *    synchronisation and do NOT check them: out-of-range values there are undefined behaviour, as for any kernel;
  *  - there is NO CPU fallback: with no CUDA device every solve returns CCC_ERR_CUDA.
  */
 #ifndef CCC_B200_H
