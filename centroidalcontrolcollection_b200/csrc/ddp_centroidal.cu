@@ -247,7 +247,7 @@ int32_t ccc_ddp_centroidal_closed_loop(ccc_ddp_centroidal_ws_t * ws,
   }
   {
     const size_t total = grid_entries * 192;
-    ccc_host::pack_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_ridge, d_vertex, lb.tab, (int)grid_entries, mm,
+    ccc_host::pack_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_ridge, d_vertex, lb.tab, (size_t)grid_entries, mm,
                                                                                    ccc::CentroidalModel::TAB_ROWS);
     eng.launches++;
   }
