@@ -326,4 +326,20 @@ void ccc_ddp_centroidal_set_chunk(int32_t chunk)
   ccc_host::g_chunk() = chunk < 0 ? 0 : chunk;
 }
 
+/** Small-batch policy of every DDP engine (A/B measurements and tests): team = 1 runs batches of at most one problem per
+ *  SM on the team kernel (ddp_team.cuh: one CTA per problem, concurrent line-search rollouts); spread = 1 spreads batches
+ *  smaller than the resident warps over all SMs.  Negative values leave a setting unchanged.  Both default to 1; results
+ *  do not depend on either. */
+void ccc_ddp_set_small_batch_policy(int32_t team, int32_t spread)
+{
+  if(team >= 0) ccc_host::g_team() = team ? 1 : 0;
+  if(spread >= 0) ccc_host::g_spread() = spread ? 1 : 0;
+}
+
+/** 1 if the workspace's last solve ran on the team kernel. */
+int32_t ccc_ddp_centroidal_last_team(const ccc_ddp_centroidal_ws_t * ws)
+{
+  return ws ? ws->eng.last_team : 0;
+}
+
 } // extern "C"

@@ -9,11 +9,13 @@
 #pragma once
 #include "../../include/ccc_b200.h"
 #include "common_host.cuh"
+#include "ddp_team.cuh"
 #include "ddp_warp_core.cuh"
 
 namespace ccc_host
 {
 constexpr int kResumeFlag = 1 << 30;
+constexpr int kTeam = 8; // warps per problem of the small-batch kernel (ddp_team.cuh)
 
 /** Work queue shared by all warps of the persistent kernel (device memory).
  *  slot[i] >= 0: problem id (| kResumeFlag if it is a suspended solve); -1: not published yet.
@@ -26,6 +28,7 @@ struct SolveQueue
   int * tail; // next free slot
   int * done; // finished problems
   int capacity;
+  int warps_active; // warps of a CTA that take tickets (small batches are spread over the SMs instead of filling a few)
 };
 
 template<class M, int WARPS, int CTAS, bool CONSTRAINED, int FEAT = ccc::kFeatDefault>
@@ -37,6 +40,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
   double * s = smem + (threadIdx.x >> 5) * Warp::sm::TOTAL;
   const int lane = threadIdx.x & 31;
   unsigned ring_parity = 0;
+  if((int)(threadIdx.x >> 5) >= q.warps_active) return; // (no CTA-wide barrier anywhere in this kernel)
   Warp::init_warp(s);
   for(;;)
   {
@@ -79,6 +83,21 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
       }
     }
   }
+}
+
+/** Small batches (B <= number of SMs): one CTA of TEAM warps per problem, concurrent line-search rollouts
+ *  (ddp_team.cuh).  Bit-identical to ddp_solve_kernel. */
+template<class M, int TEAM, bool CONSTRAINED>
+__global__ void __launch_bounds__(TEAM * 32, 1) ddp_team_kernel(const __grid_constant__ ccc::DdpParams<M> P)
+{
+  extern __shared__ __align__(16) double smem[];
+  ccc::team_solve<M, CONSTRAINED, ccc::kFeatAbort, TEAM>(P, smem, (int)blockIdx.x);
+}
+
+template<class M>
+constexpr size_t team_smem_bytes()
+{
+  return (size_t)(kTeam * ccc::SmLayout<M::NX, M::NXP>::TOTAL + ccc::team_ctl_doubles<kTeam>()) * sizeof(double);
 }
 
 static __global__ void init_queue_kernel(SolveQueue q, int B)
@@ -194,6 +213,16 @@ inline int & g_variant()
   static int v = 0; // the product default (Variants<M>::table)
   return v;
 }
+inline int & g_team()
+{
+  static int t = 1; // 1: batches of at most one problem per SM run on the team kernel (ddp_team.cuh)
+  return t;
+}
+inline int & g_spread()
+{
+  static int sp = 1; // 1: batches smaller than the resident warps are spread over all SMs
+  return sp;
+}
 inline int & g_chunk()
 {
   static int c = 32; // DDP iterations per visit before a solve is suspended and re-queued
@@ -221,7 +250,8 @@ template<class M>
 struct DdpEngine
 {
   static constexpr int NX = M::NX;
-  int N = 0, max_batch = 0, max_sched = 0, device = 0, launches = 0;
+  int N = 0, max_batch = 0, max_sched = 0, device = 0, launches = 0, n_sm = 148;
+  int last_team = 0; // 1 if the last solve ran on the team kernel
   // solver workspace
   double *tab = nullptr, *xbuf = nullptr, *ubuf = nullptr, *gains = nullptr, *u32 = nullptr, *uo32 = nullptr;
   int *qslot = nullptr, *qctl = nullptr;
@@ -249,11 +279,15 @@ struct DdpEngine
     max_batch = B_;
     max_sched = S_;
     cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     const size_t n = horizon_steps, B = B_, S = S_;
+    // trajectory buffers: nominal + candidate per problem; the team kernel keeps kTeam candidates for up to n_sm problems
+    const size_t team_B = B < (size_t)n_sm ? B : (size_t)n_sm;
+    const size_t traj = 2 * B > (kTeam + 1) * team_B ? 2 * B : (kTeam + 1) * team_B;
     bool ok = true;
     ok = ok && dev_alloc(tab, S * n * 32 * M::TAB_ROWS);
-    ok = ok && dev_alloc(xbuf, 2 * B * (n + 1) * NX);
-    ok = ok && dev_alloc(ubuf, 2 * B * n * 32);
+    ok = ok && dev_alloc(xbuf, traj * (n + 1) * NX);
+    ok = ok && dev_alloc(ubuf, traj * n * 32);
     ok = ok && dev_alloc(gains, B * n * 32 * M::NXP);
     ok = ok && dev_alloc(u32, B * n * 32);
     ok = ok && dev_alloc(uo32, B * n * 32);
@@ -282,6 +316,10 @@ struct DdpEngine
         ok = check(cudaFuncSetAttribute(vt[v].kernel[c], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(vt[v].warps * ccc::SmLayout<M::NX, M::NXP>::TOTAL * sizeof(double))),
                    "cudaFuncSetAttribute(smem)");
+    ok = ok && check(cudaFuncSetAttribute(ddp_team_kernel<M, kTeam, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_smem_bytes<M>()),
+                     "cudaFuncSetAttribute(team smem)");
+    ok = ok && check(cudaFuncSetAttribute(ddp_team_kernel<M, kTeam, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_smem_bytes<M>()),
+                     "cudaFuncSetAttribute(team smem)");
     return ok;
   }
 
@@ -346,6 +384,20 @@ struct DdpEngine
   int launch_solve(ccc::DdpParams<M> & P, const ccc_ddp_config_t * cfg, cudaStream_t st)
   {
     const int B = P.B;
+    last_team = 0;
+    if(g_team() && B <= n_sm)
+    {
+      // one problem per SM: the team kernel (no queue, no suspension)
+      P.chunk_iters = 0;
+      if(cfg->with_input_constraint)
+        ddp_team_kernel<M, kTeam, true><<<B, kTeam * 32, team_smem_bytes<M>(), st>>>(P);
+      else
+        ddp_team_kernel<M, kTeam, false><<<B, kTeam * 32, team_smem_bytes<M>(), st>>>(P);
+      launches++;
+      last_team = 1;
+      if(!check(cudaGetLastError(), "launch ddp_team_kernel")) return CCC_ERR_CUDA;
+      return CCC_OK;
+    }
     // work queue: every problem once, plus room for re-queued (suspended) solves
     int nv = 0;
     const auto * vt = Variants<M>::table(nv);
@@ -370,14 +422,21 @@ struct DdpEngine
     launches++;
     // persistent grid: exactly the CTAs that are co-resident (warps spin on the queue, so every
     // launched CTA must be running)
-    int n_sm = 148, per_sm = 0;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    int per_sm = 0;
     if(!check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, var.warps * 32, smem_bytes), "occupancy"))
       return CCC_ERR_CUDA;
     if(per_sm < 1) return fail(CCC_ERR_CUDA, "solve kernel does not fit on an SM");
     if(per_sm > var.ctas) per_sm = var.ctas;
     int grid = (B + var.warps - 1) / var.warps;
     if(grid > n_sm * per_sm) grid = n_sm * per_sm;
+    q.warps_active = var.warps;
+    if(g_spread() && B < n_sm * per_sm * var.warps)
+    {
+      // fewer problems than resident warps: use every SM with ceil(B / grid) warps each (a warp on a less crowded SM
+      // runs its serial recursion faster) instead of eight warps on B / 8 SMs
+      grid = B < n_sm * per_sm ? B : n_sm * per_sm;
+      q.warps_active = (B + grid - 1) / grid;
+    }
     kernel<<<grid, var.warps * 32, smem_bytes, st>>>(P, q);
     launches++;
     if(!check(cudaGetLastError(), "launch ddp_solve_kernel")) return CCC_ERR_CUDA;

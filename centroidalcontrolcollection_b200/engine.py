@@ -61,6 +61,10 @@ def lib():
         L.ccc_ddp_centroidal_set_variant.argtypes = [C.c_int32]
         L.ccc_ddp_centroidal_set_chunk.restype = None
         L.ccc_ddp_centroidal_set_chunk.argtypes = [C.c_int32]
+        L.ccc_ddp_set_small_batch_policy.restype = None
+        L.ccc_ddp_set_small_batch_policy.argtypes = [C.c_int32, C.c_int32]
+        L.ccc_ddp_centroidal_last_team.restype = C.c_int32
+        L.ccc_ddp_centroidal_last_team.argtypes = [C.c_void_p]
         L.ccc_ddp_centroidal_closed_loop.restype = C.c_int32
         L.ccc_ddp_centroidal_closed_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_ddp_srb_create.restype = C.c_void_p
@@ -212,6 +216,18 @@ class DdpCentroidalEngine(_DdpEngineBase):
     def set_chunk(iters):
         """Tuning hook: DDP iterations per visit before a solve is suspended and re-queued (0 = never)."""
         lib().ccc_ddp_centroidal_set_chunk(int(iters))
+
+    @staticmethod
+    def set_small_batch_policy(team=-1, spread=-1):
+        """Tuning hook of every DDP engine (results never depend on it): team = 1 (default) runs batches of at most one
+        problem per SM on the team kernel (csrc/ddp_team.cuh: one CTA per problem, concurrent line-search rollouts),
+        spread = 1 (default) spreads batches smaller than the resident warps over all SMs; -1 leaves a setting as it is."""
+        lib().ccc_ddp_set_small_batch_policy(int(team), int(spread))
+
+    @property
+    def last_team(self):
+        """True if the last solve of this workspace ran on the team kernel."""
+        return bool(lib().ccc_ddp_centroidal_last_team(self._h))
 
 
 class QpEngine:

@@ -10,6 +10,7 @@
 // collective (__syncwarp, shuffles, ballot) is a barrier over the live fibres.
 #define CCC_WARP_EMU 1
 #include "../../include/ccc_b200.h"
+#include "../../centroidalcontrolcollection_b200/csrc/ddp_team.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/model_centroidal.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/model_srb.cuh"
 #include "../../centroidalcontrolcollection_b200/csrc/model_zmp.cuh"
@@ -198,6 +199,15 @@ namespace
 {
 int g_chunk = 0;
 int g_feat = 1;
+int g_team = 0;
+constexpr int kTeam = 8; // ccc_host::kTeam (ddp_host.cuh)
+}
+
+/** 1: emulate the small-batch kernel (ddp_team.cuh: a CTA of 8 warps per problem, concurrent line-search rollouts)
+ *  instead of the warp-per-problem kernel. */
+extern "C" void ccc_emu_set_team(int32_t team)
+{
+  g_team = team;
 }
 
 /** Which build of the solver core to emulate (ddp_warp_core.cuh kFeat*): 0 = no feature bits, 1 = the product default,
@@ -242,7 +252,8 @@ int32_t emuSolve(int N, int B, int S, int mm, const int32_t * sched_id, const in
     for(size_t bk = 0; bk < (size_t)B * N; bk++)
       for(int j = 0; j < mm; j++) u_init[bk * 32 + j] = u_init_in[bk * mm + j];
   }
-  std::vector<double> xbuf((size_t)2 * B * (N + 1) * NX, 0.0), ubuf((size_t)2 * B * N * 32, 0.0),
+  const size_t ntraj = g_team ? kTeam + 1 : 2;
+  std::vector<double> xbuf(ntraj * B * (N + 1) * NX, 0.0), ubuf(ntraj * B * N * 32, 0.0),
       gains((size_t)B * N * 32 * M::NXP, 0.0), out_u((size_t)B * N * 32, 0.0);
   ccc::DdpParams<M> P{};
   P.N = N;
@@ -284,6 +295,23 @@ int32_t emuSolve(int N, int B, int S, int mm, const int32_t * sched_id, const in
     if(!(w_run[i] >= 0.0)) P.abort_ok = 0;
   for(int i = 0; i < NX; i++)
     if(!(w_term[i] >= 0.0)) P.abort_ok = 0;
+  if(g_team)
+  {
+    // ddp_team_kernel: one CTA of kTeam warps per problem, run to completion
+    P.chunk_iters = 0;
+    std::vector<double> tsm((size_t)kTeam * sm::TOTAL + ccc::team_ctl_doubles<kTeam>() + 2, 0.0);
+    for(int b = 0; b < B; b++)
+      ccc_emu::run_cta(kTeam * 32, [&]() {
+        if(P.cfg.with_input_constraint)
+          ccc::team_solve<M, true, ccc::kFeatAbort, kTeam>(P, tsm.data(), b);
+        else
+          ccc::team_solve<M, false, ccc::kFeatAbort, kTeam>(P, tsm.data(), b);
+      });
+    if(r->u)
+      for(size_t bk = 0; bk < (size_t)B * N; bk++)
+        for(int j = 0; j < mm; j++) r->u[bk * mm + j] = out_u[bk * 32 + j];
+    return CCC_OK;
+  }
   std::vector<double> smem(sm::TOTAL + 2, 0.0);
   unsigned ring_parity = 0;
   // the kernel's round-robin queue, replayed by one emulated warp: (problem, resumed?) entries

@@ -19,10 +19,12 @@ def lib():
     return _LIB
 
 
-def ddp_centroidal_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
-    """feat: 0 = no feature bits, 1 = product default, 2 = every feature of the solver core (ddp_warp_core.cuh kFeat*)."""
+def ddp_centroidal_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1, team=0):
+    """feat: 0 = no feature bits, 1 = product default, 2 = every feature of the solver core (ddp_warp_core.cuh kFeat*).
+    team = 1: the small-batch kernel (ddp_team.cuh, a CTA of 8 warps per problem) instead of a warp per problem."""
     lib().ccc_emu_set_chunk(int(chunk))
     lib().ccc_emu_set_feat(int(feat))
+    lib().ccc_emu_set_team(int(team))
     res = problem_set.new_result(trace_len)
     bs, rs = problem_set.as_struct(), res.as_struct()
     rc = lib().ccc_emu_ddp_centroidal_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))
@@ -30,9 +32,10 @@ def ddp_centroidal_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
     return res
 
 
-def ddp_srb_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
+def ddp_srb_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1, team=0):
     lib().ccc_emu_set_chunk(int(chunk))
     lib().ccc_emu_set_feat(int(feat))
+    lib().ccc_emu_set_team(int(team))
     res = problem_set.new_result(trace_len)
     bs, rs = problem_set.as_struct(), res.as_struct()
     rc = lib().ccc_emu_ddp_srb_solve(C.addressof(bs), C.addressof(cfg), C.addressof(rs))
@@ -56,6 +59,7 @@ def qp_solve(problem_set, rcap=0):
 def ddp_zmp_solve(problem_set, cfg, trace_len=0, chunk=0, feat=1):
     L = lib()
     L.ccc_emu_set_feat(int(feat))
+    L.ccc_emu_set_team(0)
     L.ccc_emu_ddp_zmp_solve.restype = C.c_int32
     L.ccc_emu_ddp_zmp_solve.argtypes = [C.c_void_p] * 3
     L.ccc_emu_set_chunk(int(chunk))
