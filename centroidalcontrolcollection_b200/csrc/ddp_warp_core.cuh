@@ -44,6 +44,13 @@ struct DdpResume
   int cur, iter;
 };
 
+// The once-per-stage state-sized loops of the backward pass (T = Vxx Fx, Qxx, Qux rows) are unrolled M::STAGE_UNROLL
+// iterations at a time (same operations in the same order whatever the factor).  Fully unrolled they are straight-line
+// code that every stage fetches cold: with 12 states the per-stage straight-line part of the kernel is 44 KB and a quarter
+// of all stall samples are instruction fetches (profiles/r02_summary.md §5); rolled three at a time DdpSingleRigidBody
+// runs 5.5 % faster, while the 9-state DdpCentroidal kernel is 1.5 % faster fully unrolled (r02g_ab_stage_unroll.txt).
+#define CCC_STAGE_UNROLL CCC_UNROLL_N(M::STAGE_UNROLL)
+
 template<class M>
 struct DdpParams
 {
@@ -138,6 +145,13 @@ struct DdpWarp
 {
   static constexpr int NX = M::NX, NXP = M::NXP, R0 = M::R0, NREF = M::NREF;
   static constexpr bool kTma = (FEAT & kFeatTma) != 0, kAbort = (FEAT & kFeatAbort) != 0;
+#if defined(CCC_NO_ROLLED_TILE_LOOPS)
+  static constexpr bool kRolled = false;
+#elif defined(CCC_FORCE_ROLLED_TILE_LOOPS)
+  static constexpr bool kRolled = true;
+#else
+  static constexpr bool kRolled = M::STAGE_UNROLL < NX; // compact-code forms of the Quu assembly and Quu K loops too
+#endif
   static constexpr int GBLK = 32 * NXP; // doubles per stage of the gain lists (either layout fits: NXP >= NX + 1)
   using sm = SmLayout<NX, NXP>;
   const DdpParams<M> & P;
@@ -408,7 +422,7 @@ struct DdpWarp
       double acc[NQE];
       CCC_UNROLL
       for(int q = 0; q < NQE; q++) acc[q] = 0.0;
-      CCC_UNROLL
+      CCC_STAGE_UNROLL
       for(int c = 0; c < NX; c++)
       {
         CCC_UNROLL
@@ -434,7 +448,7 @@ struct DdpWarp
       double acc[NQE];
       CCC_UNROLL
       for(int q = 0; q < NQE; q++) acc[q] = 0.0;
-      CCC_UNROLL
+      CCC_STAGE_UNROLL
       for(int c = 0; c < NX; c++)
       {
         CCC_UNROLL
@@ -502,7 +516,7 @@ struct DdpWarp
     // Qux row of this lane: Fu' (Vxx Fx), parked in shared memory until the gain solve and the
     // cost-to-go update need it (rows of inactive lanes are +0.0)
     double * QUXR = s + sm::QUXR;
-    CCC_UNROLL
+    CCC_STAGE_UNROLL
     for(int c = 0; c < NX; c++)
     {
       double acc = 0.0;
@@ -515,34 +529,60 @@ struct DdpWarp
     double H[32];
     CCC_UNROLL
     for(int j = 0; j < 32; j++) H[j] = 0.0;
-    CCC_UNROLL
-    for(int j = 0; j < 32; j++)
-    {
-      if(j == 16 && m <= 16) break;
-      double acc = 0.0;
-      CCC_UNROLL
-      for(int r = 0; r < 3; r++)
-      {
-        d2 w = ld2(WT + j * 6 + 2 * r);
-        acc = dfma(Fu[2 * r], w.x, acc);
-        acc = dfma(Fu[2 * r + 1], w.y, acc);
-      }
-      H[j] = 0.0 + acc; // off-diagonal entries (the diagonal is quu_diag above)
-    }
-    warp_sync(); // everyone is done reading WT (aliases A)
     double * A = s + sm::A;
     double * S = s + sm::SYM;
-    // the lower triangle is the definition (oracle); it is written in row form and mirrored in column form, so that
-    // every later reload of a row (after each factorisation, which borrows the registers) is 16 aligned LDS.128 and
-    // the compact gather a plain indexed read of one row
-    CCC_UNROLL
-    for(int j = 0; j < 31; j++)
+    if(kRolled)
     {
-      if(j == 16 && m <= 16) break;
-      if(active && j < lane)
+      // compact-code form: a rolled loop over the columns that writes each entry straight into the tile (both
+      // triangles); the row comes back into registers with load_sym_row below, as after every factorisation
+      CCC_UNROLL_N(2)
+      for(int j = 0; j < m; j++)
       {
-        S[lane * kLda + j] = H[j];
-        S[j * kLda + lane] = H[j];
+        double acc = 0.0;
+        CCC_UNROLL
+        for(int r = 0; r < 3; r++)
+        {
+          d2 w = ld2(WT + j * 6 + 2 * r);
+          acc = dfma(Fu[2 * r], w.x, acc);
+          acc = dfma(Fu[2 * r + 1], w.y, acc);
+        }
+        const double h = 0.0 + acc;
+        if(active && j < lane)
+        {
+          S[lane * kLda + j] = h;
+          S[j * kLda + lane] = h;
+        }
+      }
+    }
+    else
+    {
+      CCC_UNROLL
+      for(int j = 0; j < 32; j++)
+      {
+        if(j == 16 && m <= 16) break;
+        double acc = 0.0;
+        CCC_UNROLL
+        for(int r = 0; r < 3; r++)
+        {
+          d2 w = ld2(WT + j * 6 + 2 * r);
+          acc = dfma(Fu[2 * r], w.x, acc);
+          acc = dfma(Fu[2 * r + 1], w.y, acc);
+        }
+        H[j] = 0.0 + acc; // off-diagonal entries (the diagonal is quu_diag above)
+      }
+      warp_sync(); // everyone is done reading WT (aliases A)
+      // the lower triangle is the definition (oracle); it is written in row form and mirrored in column form, so that
+      // every later reload of a row (after each factorisation, which borrows the registers) is 16 aligned LDS.128 and
+      // the compact gather a plain indexed read of one row
+      CCC_UNROLL
+      for(int j = 0; j < 31; j++)
+      {
+        if(j == 16 && m <= 16) break;
+        if(active && j < lane)
+        {
+          S[lane * kLda + j] = H[j];
+          S[j * kLda + lane] = H[j];
+        }
       }
     }
     if(active) S[lane * kLda + lane] = quu_diag + lambda;
@@ -671,19 +711,40 @@ struct DdpWarp
     double Z[NX];
     CCC_UNROLL
     for(int c = 0; c < NX; c++) Z[c] = 0.0;
-    CCC_UNROLL
-    for(int j = 0; j < 32; j++)
+    if(kRolled)
     {
-      if(j == 16 && m <= 16) break;
-      const double h = H[j];
-      CCC_UNROLL
-      for(int c = 0; c + 1 < NX; c += 2)
+      // compact-code form: the row of Quu comes from the tile (it was just reloaded from there: same values)
+      const double * hrow = S + lane * kLda;
+      CCC_UNROLL_N(2)
+      for(int j = 0; j < m; j++)
       {
-        const d2 kc = ld2(KB + j * NXP + c);
-        Z[c] = dfma(h, kc.x, Z[c]);
-        Z[c + 1] = dfma(h, kc.y, Z[c + 1]);
+        const double h = hrow[j];
+        CCC_UNROLL
+        for(int c = 0; c + 1 < NX; c += 2)
+        {
+          const d2 kc = ld2(KB + j * NXP + c);
+          Z[c] = dfma(h, kc.x, Z[c]);
+          Z[c + 1] = dfma(h, kc.y, Z[c + 1]);
+        }
+        if(NX & 1) Z[NX - 1] = dfma(h, KB[j * NXP + NX - 1], Z[NX - 1]);
       }
-      if(NX & 1) Z[NX - 1] = dfma(h, KB[j * NXP + NX - 1], Z[NX - 1]);
+    }
+    else
+    {
+      CCC_UNROLL
+      for(int j = 0; j < 32; j++)
+      {
+        if(j == 16 && m <= 16) break;
+        const double h = H[j];
+        CCC_UNROLL
+        for(int c = 0; c + 1 < NX; c += 2)
+        {
+          const d2 kc = ld2(KB + j * NXP + c);
+          Z[c] = dfma(h, kc.x, Z[c]);
+          Z[c + 1] = dfma(h, kc.y, Z[c + 1]);
+        }
+        if(NX & 1) Z[NX - 1] = dfma(h, KB[j * NXP + NX - 1], Z[NX - 1]);
+      }
     }
     {
       // k'Qu, k'Quu k (dV) and ||k||^2, ||u||^2 (small-gradient measure) through one scattered 4-way tree sum

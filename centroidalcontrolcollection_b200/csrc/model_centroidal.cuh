@@ -11,6 +11,7 @@ namespace ccc
 struct CentroidalModel
 {
   static constexpr int NX = 9;       // states
+  static constexpr int STAGE_UNROLL = 9; // once-per-stage state-sized loops (ddp_warp_core.cuh): fully unrolled
   static constexpr int NXP = 10;     // even row stride of the K / QuuK / Qux staging buffers
   static constexpr int R0 = 3;       // Fu is non-zero in rows 3..8
   static constexpr int NREF = 3;     // referenced states: CoM position

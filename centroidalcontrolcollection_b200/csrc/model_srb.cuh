@@ -57,6 +57,7 @@ struct Inertia3
 struct SrbModel
 {
   static constexpr int NX = 12;
+  static constexpr int STAGE_UNROLL = 3; // once-per-stage state-sized loops (ddp_warp_core.cuh), rolled three at a time: instruction-cache footprint
   static constexpr int NXP = 14;     // even row stride of the K / QuuK / Qux staging buffers: 12 gains + k
   static constexpr int R0 = 6;       // Fu is non-zero in rows 6..11
   static constexpr int NREF = 6;     // referenced states: position and orientation
@@ -66,7 +67,8 @@ struct SrbModel
     double dt, mass;
   };
 
-  /** matAngularVelToEulerDot (:26-38) */
+  /** matAngularVelToEulerDot (:26-38).  (Inline at both call sites: as an out-of-line function shared by the rollouts and
+   *  the backward pass it measured 9 % slower, profiles/r02g_ab_srb_euler.txt.) */
   CCC_DEV static void euler_mat(double o0, double o1, double (&E)[9], double & sa, double & ca, double & sb, double & cb)
   {
     sincos_canon(o0, sa, ca);

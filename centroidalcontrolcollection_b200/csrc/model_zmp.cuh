@@ -15,6 +15,7 @@ namespace ccc
 struct ZmpModel
 {
   static constexpr int NX = 6;
+  static constexpr int STAGE_UNROLL = 6; // once-per-stage state-sized loops (ddp_warp_core.cuh): fully unrolled
   static constexpr int NXP = 8;
   static constexpr int R0 = 0;       // Fu column = all six rows
   static constexpr int NREF = 6;     // every state has a (possibly zero-weighted) reference
