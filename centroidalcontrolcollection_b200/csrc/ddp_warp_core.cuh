@@ -50,6 +50,9 @@ struct DdpResume
 // of all stall samples are instruction fetches (profiles/r02_summary.md §5); rolled three at a time DdpSingleRigidBody
 // runs 5.5 % faster, while the 9-state DdpCentroidal kernel is 1.5 % faster fully unrolled (r02g_ab_stage_unroll.txt).
 #define CCC_STAGE_UNROLL CCC_UNROLL_N(M::STAGE_UNROLL)
+#ifndef CCC_TILE_UNROLL
+#  define CCC_TILE_UNROLL 2 // unroll factor of the rolled (compact-code) Quu assembly / Quu K loops
+#endif
 
 template<class M>
 struct DdpParams
@@ -535,7 +538,7 @@ struct DdpWarp
     {
       // compact-code form: a rolled loop over the columns that writes each entry straight into the tile (both
       // triangles); the row comes back into registers with load_sym_row below, as after every factorisation
-      CCC_UNROLL_N(2)
+      CCC_UNROLL_N(CCC_TILE_UNROLL)
       for(int j = 0; j < m; j++)
       {
         double acc = 0.0;
@@ -715,7 +718,7 @@ struct DdpWarp
     {
       // compact-code form: the row of Quu comes from the tile (it was just reloaded from there: same values)
       const double * hrow = S + lane * kLda;
-      CCC_UNROLL_N(2)
+      CCC_UNROLL_N(CCC_TILE_UNROLL)
       for(int j = 0; j < m; j++)
       {
         const double h = hrow[j];

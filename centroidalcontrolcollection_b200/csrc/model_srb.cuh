@@ -57,7 +57,10 @@ struct Inertia3
 struct SrbModel
 {
   static constexpr int NX = 12;
-  static constexpr int STAGE_UNROLL = 3; // once-per-stage state-sized loops (ddp_warp_core.cuh), rolled three at a time: instruction-cache footprint
+#ifndef CCC_SRB_STAGE_UNROLL
+#  define CCC_SRB_STAGE_UNROLL 3
+#endif
+  static constexpr int STAGE_UNROLL = CCC_SRB_STAGE_UNROLL; // once-per-stage state-sized loops (ddp_warp_core.cuh), rolled three at a time: instruction-cache footprint
   static constexpr int NXP = 14;     // even row stride of the K / QuuK / Qux staging buffers: 12 gains + k
   static constexpr int R0 = 6;       // Fu is non-zero in rows 6..11
   static constexpr int NREF = 6;     // referenced states: position and orientation

@@ -1,6 +1,6 @@
 """Quick A/B timing of the two warp-per-problem DDP kernels on fixed workloads (host-buffer API, best of 3), with a hash of
 the results so that builds can be compared bit for bit:
-    python tools/ab_quick.py [label]
+    python tools/ab_quick.py [label] [centroidal|srb]
   centroidal: config 3, 16384 cold starts to convergence;  srb: config 4, 4096 cold starts, 40 iterations."""
 import hashlib
 import os
@@ -33,12 +33,16 @@ def best(fn, reps=3):
     return r, min(ts)
 
 
-w = workloads.ddp_centroidal_config3(batch=16384)
-ps = problem.DdpCentroidalProblemSet.from_workload(w)
-eng = engine.DdpCentroidalEngine(ps.N, ps.batch, ps.sched.S)
-res, t = best(lambda: eng.solve(ps, problem.ddp_centroidal_config()))
-print(f"{label:28s} centroidal 16384: {t * 1e3:8.1f} ms  {16384 / t:8.0f} solves/s  digest {digest(res)}", flush=True)
-eng.close()
+only = sys.argv[2] if len(sys.argv) > 2 else ""
+if only in ("", "centroidal"):
+    w = workloads.ddp_centroidal_config3(batch=16384)
+    ps = problem.DdpCentroidalProblemSet.from_workload(w)
+    eng = engine.DdpCentroidalEngine(ps.N, ps.batch, ps.sched.S)
+    res, t = best(lambda: eng.solve(ps, problem.ddp_centroidal_config()))
+    print(f"{label:28s} centroidal 16384: {t * 1e3:8.1f} ms  {16384 / t:8.0f} solves/s  digest {digest(res)}", flush=True)
+    eng.close()
+if only == "centroidal":
+    sys.exit(0)
 w = workloads.ddp_srb_config4(batch=4096)
 ps = problem.DdpSrbProblemSet.from_workload(w)
 eng = engine.DdpSrbEngine(ps.N, ps.batch, ps.sched.S)
