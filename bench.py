@@ -394,6 +394,29 @@ def other_configs(threads):
                 "algorithmic_bytes_per_solve": 96 + 4 + 101 * 12 * 8 + m_sum * 8 + 16,
                 "parity": {"bit_exact_vs_oracle": parity4, "checked": int(k), "of": int(ps4.batch)}, "api": "ccc_ddp_srb_solve(CCC_MEM_HOST)"})
     eng4.close()
+
+    # planOnce-sized calls (the reference's own caller: one problem per control tick): small batches run on the team
+    # kernel (one CTA of 8 warps per problem, the line search as one round of concurrent rollouts)
+    def small_batch(B):
+        wb = workloads.ddp_centroidal_config3(batch=B, n_sched=1)
+        pb = problem.DdpCentroidalProblemSet.from_workload(wb)
+        eb = engine.DdpCentroidalEngine(pb.N, B, 1)
+        cfg = problem.ddp_centroidal_config()
+        cold, t_cold = _timed(lambda: eb.solve(pb, cfg), 3)
+        refb = binding.ddp_centroidal_solve(pb, cfg, n_threads=threads)
+        par = bool(np.array_equal(refb.x, cold.x) and np.array_equal(refb.u, cold.u) and np.array_equal(refb.iters, cold.iters))
+        pb.u_init = cold.u.copy()
+        cfg1 = problem.ddp_centroidal_config(max_iter=1)
+        _, t_warm = _timed(lambda: eb.solve(pb, cfg1), 20)
+        team = bool(eb.last_team)
+        eb.close()
+        return {"batch": B, "cold_solve_ms": t_cold * 1e3, "cold_ddp_iters_max": int(cold.iters.max()), "warm_tick_ms": t_warm * 1e3,
+                "team_kernel": team, "bit_exact_vs_oracle": par}
+
+    out.append({"workload": "DdpCentroidal N=50, planOnce-sized batches (latency, not throughput)", "unit": "ms per call",
+                "cases": [small_batch(1), small_batch(148)],
+                "api": "ccc_ddp_centroidal_solve(CCC_MEM_HOST), pageable buffers, time.perf_counter around the call, best of 3 / 20; "
+                       "warm tick = max_iter 1 from the converged plan (tests/src/TestDdpCentroidal.cpp:116)"})
     return out
 
 
