@@ -1,6 +1,6 @@
 """Quick A/B timing of the two warp-per-problem DDP kernels on fixed workloads (host-buffer API, best of 3), with a hash of
 the results so that builds can be compared bit for bit:
-    python tools/ab_quick.py [label] [centroidal|srb]
+    python tools/ab_quick.py [label] [centroidal|srb|""] [variant]
   centroidal: config 3, 16384 cold starts to convergence;  srb: config 4, 4096 cold starts, 40 iterations."""
 import hashlib
 import os
@@ -34,6 +34,9 @@ def best(fn, reps=3):
 
 
 only = sys.argv[2] if len(sys.argv) > 2 else ""
+variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # ddp_host.cuh Variants (0 = product default)
+engine.DdpCentroidalEngine.set_variant(variant)
+label = f"{label} variant {variant}"
 if only in ("", "centroidal"):
     w = workloads.ddp_centroidal_config3(batch=16384)
     ps = problem.DdpCentroidalProblemSet.from_workload(w)
