@@ -336,6 +336,12 @@ void ccc_ddp_set_small_batch_policy(int32_t team, int32_t spread)
   if(spread >= 0) ccc_host::g_spread() = spread ? 1 : 0;
 }
 
+/** Tuning hook: 0 = host-buffer calls always use one copy per array (A/B of the packed staging block of small calls). */
+void ccc_ddp_set_packed_io(int32_t on)
+{
+  ccc_host::g_packed_io() = on ? 1 : 0;
+}
+
 /** 1 if the workspace's last solve ran on the team kernel. */
 int32_t ccc_ddp_centroidal_last_team(const ccc_ddp_centroidal_ws_t * ws)
 {

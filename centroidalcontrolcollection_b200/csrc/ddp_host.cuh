@@ -7,6 +7,8 @@
 // its iteration budget for this visit is suspended and re-queued behind everything else.
 // Compile with -fmad=false: only the explicit fma() calls of the cores may fuse.
 #pragma once
+#include <cstring>
+
 #include "../../include/ccc_b200.h"
 #include "common_host.cuh"
 #include "ddp_team.cuh"
@@ -223,6 +225,11 @@ inline int & g_spread()
   static int sp = 1; // 1: batches smaller than the resident warps are spread over all SMs
   return sp;
 }
+inline int & g_packed_io()
+{
+  static int p = 1; // 1: host-buffer calls whose buffers fit the staging block move through it (DdpEngine::solve)
+  return p;
+}
 inline int & g_chunk()
 {
   static int c = 32; // DDP iterations per visit before a solve is suspended and re-queued
@@ -266,6 +273,11 @@ struct DdpEngine
   unsigned * d_clamped = nullptr;
   size_t trace_cap = 0;
   cudaStream_t own_stream = nullptr;
+  // small host-buffer calls (a planOnce-sized batch): every input goes through ONE pinned staging block and one H2D copy,
+  // every output through one D2H copy — a dozen small cudaMemcpyAsync calls from pageable memory cost more than the copies
+  static constexpr size_t kStageBytes = 1u << 20;
+  char *h_stage = nullptr, *d_stage = nullptr;
+  int last_packed = 0; // 1 if the last host-buffer solve went through the staging block
 
   bool create(int horizon_steps, int B_, int S_)
   {
@@ -309,6 +321,7 @@ struct DdpEngine
     ok = ok && dev_alloc(d_status, B);
     ok = ok && dev_alloc(d_clamped, B * n);
     ok = ok && check(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    ok = ok && check(cudaMallocHost(reinterpret_cast<void **>(&h_stage), kStageBytes), "cudaMallocHost") && dev_alloc(d_stage, kStageBytes);
     int nv = 0;
     const auto * vt = Variants<M>::table(nv);
     for(int v = 0; v < nv && ok; v++)
@@ -330,6 +343,8 @@ struct DdpEngine
     for(void * p : ptrs)
       if(p) cudaFree(p);
     if(own_stream) cudaStreamDestroy(own_stream);
+    if(h_stage) cudaFreeHost(h_stage);
+    if(d_stage) cudaFree(d_stage);
   }
 
   /** Everything of the kernel parameters that does not depend on where inputs / outputs live (device pointers
@@ -464,12 +479,78 @@ struct DdpEngine
     unsigned * o_clamped = res->clamped;
     const size_t tl = (size_t)res->trace_len;
 
+    // layout of the staging block (offsets in bytes, 16-byte aligned): inputs first, outputs behind them
+    struct Blk
+    {
+      const void * src;
+      void * dst;
+      size_t bytes, off;
+    };
+    Blk bin[7] = {{in.sched_id, nullptr, sizeof(int) * (size_t)B, 0},
+                  {in.m, nullptr, sizeof(int) * (size_t)S * N, 0},
+                  {in.ridge, nullptr, sizeof(double) * (size_t)S * N * mm * 3, 0},
+                  {in.vertex, nullptr, sizeof(double) * (size_t)S * N * mm * 3, 0},
+                  {in.ref, nullptr, sizeof(double) * (size_t)S * (N + 1) * M::NREF, 0},
+                  {in.x0, nullptr, sizeof(double) * (size_t)B * NX, 0},
+                  {in.u_init, nullptr, in.u_init ? sizeof(double) * (size_t)B * N * mm : 0, 0}};
+    Blk bout[8] = {{nullptr, res->x, sizeof(double) * (size_t)B * (N + 1) * NX, 0},
+                   {nullptr, res->u, sizeof(double) * (size_t)B * N * mm, 0},
+                   {nullptr, res->cost, sizeof(double) * (size_t)B, 0},
+                   {nullptr, res->iters, sizeof(int) * (size_t)B, 0},
+                   {nullptr, res->status, sizeof(int) * (size_t)B, 0},
+                   {nullptr, tl ? res->alpha_idx : nullptr, (size_t)B * tl, 0},
+                   {nullptr, tl ? res->lambda_trace : nullptr, sizeof(double) * (size_t)B * tl, 0},
+                   {nullptr, res->clamped, sizeof(unsigned) * (size_t)B * N, 0}};
+    size_t in_total = 0, all_total = 0;
+    bool packed = false;
+    last_packed = 0;
+
     if(mem == CCC_MEM_HOST)
     {
       for(int i = 0; i < S * N; i++)
         if(in.m[i] < 0 || in.m[i] > mm) return fail(CCC_ERR_INVALID, "stage input dimension outside [0, m_max]");
       for(int i = 0; i < B; i++)
         if(in.sched_id[i] < 0 || in.sched_id[i] >= S) return fail(CCC_ERR_INVALID, "sched_id out of range");
+      size_t off = 0;
+      for(Blk & b : bin)
+      {
+        b.off = off;
+        off += (b.bytes + 15) & ~(size_t)15;
+      }
+      in_total = off;
+      for(Blk & b : bout)
+      {
+        if(!b.dst) b.bytes = 0;
+        b.off = off;
+        off += (b.bytes + 15) & ~(size_t)15;
+      }
+      all_total = off;
+      packed = g_packed_io() && all_total <= kStageBytes;
+    }
+    if(packed)
+    {
+      for(const Blk & b : bin)
+        if(b.bytes) std::memcpy(h_stage + b.off, b.src, b.bytes);
+      if(!check(cudaMemcpyAsync(d_stage, h_stage, in_total, cudaMemcpyHostToDevice, st), "H2D")) return CCC_ERR_CUDA;
+      in.sched_id = reinterpret_cast<const int *>(d_stage + bin[0].off);
+      in.m = reinterpret_cast<const int *>(d_stage + bin[1].off);
+      in.ridge = reinterpret_cast<const double *>(d_stage + bin[2].off);
+      in.vertex = reinterpret_cast<const double *>(d_stage + bin[3].off);
+      in.ref = reinterpret_cast<const double *>(d_stage + bin[4].off);
+      in.x0 = reinterpret_cast<const double *>(d_stage + bin[5].off);
+      if(in.u_init) in.u_init = reinterpret_cast<const double *>(d_stage + bin[6].off);
+      o_x = res->x ? reinterpret_cast<double *>(d_stage + bout[0].off) : nullptr;
+      o_u = res->u ? reinterpret_cast<double *>(d_stage + bout[1].off) : nullptr;
+      o_cost = res->cost ? reinterpret_cast<double *>(d_stage + bout[2].off) : nullptr;
+      o_iters = res->iters ? reinterpret_cast<int *>(d_stage + bout[3].off) : nullptr;
+      o_status = res->status ? reinterpret_cast<int *>(d_stage + bout[4].off) : nullptr;
+      o_alpha = (res->alpha_idx && tl) ? reinterpret_cast<signed char *>(d_stage + bout[5].off) : nullptr;
+      o_lambda = (res->lambda_trace && tl) ? reinterpret_cast<double *>(d_stage + bout[6].off) : nullptr;
+      o_clamped = res->clamped ? reinterpret_cast<unsigned *>(d_stage + bout[7].off) : nullptr;
+      last_packed = 1;
+    }
+    else if(mem == CCC_MEM_HOST)
+    {
       if(tl > 0 && trace_cap < (size_t)max_batch * tl)
       {
         if(d_alpha) cudaFree(d_alpha);
@@ -545,7 +626,16 @@ struct DdpEngine
       launches++;
     }
 
-    if(mem == CCC_MEM_HOST)
+    if(packed)
+    {
+      if(all_total > in_total
+         && !check(cudaMemcpyAsync(h_stage + in_total, d_stage + in_total, all_total - in_total, cudaMemcpyDeviceToHost, st), "D2H"))
+        return CCC_ERR_CUDA;
+      if(!check(cudaStreamSynchronize(st), "cudaStreamSynchronize")) return CCC_ERR_CUDA;
+      for(const Blk & b : bout)
+        if(b.bytes) std::memcpy(b.dst, h_stage + b.off, b.bytes);
+    }
+    else if(mem == CCC_MEM_HOST)
     {
 #define CCC_D2H(dst, src, n) \
   if((dst) && !check(cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, st), "D2H")) return CCC_ERR_CUDA

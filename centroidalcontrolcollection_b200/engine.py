@@ -63,6 +63,8 @@ def lib():
         L.ccc_ddp_centroidal_set_chunk.argtypes = [C.c_int32]
         L.ccc_ddp_set_small_batch_policy.restype = None
         L.ccc_ddp_set_small_batch_policy.argtypes = [C.c_int32, C.c_int32]
+        L.ccc_ddp_set_packed_io.restype = None
+        L.ccc_ddp_set_packed_io.argtypes = [C.c_int32]
         L.ccc_ddp_centroidal_last_team.restype = C.c_int32
         L.ccc_ddp_centroidal_last_team.argtypes = [C.c_void_p]
         L.ccc_ddp_centroidal_closed_loop.restype = C.c_int32
@@ -223,6 +225,12 @@ class DdpCentroidalEngine(_DdpEngineBase):
         problem per SM on the team kernel (csrc/ddp_team.cuh: one CTA per problem, concurrent line-search rollouts),
         spread = 1 (default) spreads batches smaller than the resident warps over all SMs; -1 leaves a setting as it is."""
         lib().ccc_ddp_set_small_batch_policy(int(team), int(spread))
+
+    @staticmethod
+    def set_packed_io(on):
+        """Tuning hook of every DDP engine: 1 (default) = host-buffer calls whose arrays fit a 1 MB staging block move through
+        it with one H2D and one D2H copy (planOnce-sized batches); 0 = one copy per array."""
+        lib().ccc_ddp_set_packed_io(int(on))
 
     @property
     def last_team(self):

@@ -58,9 +58,27 @@ def test_team_kernel_single_problem_tick(eng_mod, oracle):
     ref = oracle.ddp_centroidal_solve(ps, cfg, trace_len=64)
     assert_ddp_parity(ref, got, bit_exact=True)
     ps.u_init = ref.u.copy()
-    for mi in (0, 1, 2):
-        c = problem.ddp_centroidal_config(max_iter=mi)
-        assert_ddp_parity(oracle.ddp_centroidal_solve(ps, c, trace_len=4), eng.solve(ps, c, trace_len=4), bit_exact=True)
+    # with and without the packed staging block of small host-buffer calls (one H2D + one D2H instead of one per array)
+    for packed in (1, 0):
+        eng_mod.DdpCentroidalEngine.set_packed_io(packed)
+        try:
+            for mi in (0, 1, 2):
+                c = problem.ddp_centroidal_config(max_iter=mi)
+                assert_ddp_parity(oracle.ddp_centroidal_solve(ps, c, trace_len=4), eng.solve(ps, c, trace_len=4), bit_exact=True)
+            # outputs the caller does not ask for stay untouched
+            res = ps.new_result(0)
+            keep_x = res.x.copy()
+            bs, rs = ps.as_struct(), res.as_struct()
+            rs.x = None
+            import ctypes as C
+
+            from centroidalcontrolcollection_b200 import _abi
+
+            cfg1 = problem.ddp_centroidal_config(max_iter=1)
+            rc = eng_mod.lib().ccc_ddp_centroidal_solve(eng._h, C.addressof(bs), C.addressof(cfg1), C.addressof(rs), _abi.CCC_MEM_HOST, None)
+            assert rc == 0 and np.array_equal(res.x, keep_x)
+        finally:
+            eng_mod.DdpCentroidalEngine.set_packed_io(1)
 
 
 def test_team_kernel_late_and_failed_line_searches(eng_mod, oracle):

@@ -20,6 +20,27 @@ cfg = problem.ddp_centroidal_config()
 cfg1 = problem.ddp_centroidal_config(max_iter=1)
 cfg0 = problem.ddp_centroidal_config(max_iter=0)
 POLICIES = (("team", 1, 1), ("spread", 0, 1), ("packed", 0, 0))
+if "--io" in sys.argv:
+    # A/B of the packed staging block of small host-buffer calls (default on) under the default policy
+    for io in (1, 0, 1, 0):
+        engine.DdpCentroidalEngine.set_packed_io(io)
+        for B in (1, 8):
+            wb = workloads.ddp_centroidal_config3(batch=B, n_sched=1)
+            pb = problem.DdpCentroidalProblemSet.from_workload(wb)
+            eb = engine.DdpCentroidalEngine(pb.N, B, 1)
+            rb = eb.solve(pb, cfg)
+            pb.u_init = rb.u.copy()
+            ts = []
+            for _ in range(5):
+                eb.solve(pb, cfg1)
+            for _ in range(200):
+                t0 = time.perf_counter()
+                eb.solve(pb, cfg1)
+                ts.append(time.perf_counter() - t0)
+            print(f"packed staging {io}: batch {B}, warm tick median {np.median(ts) * 1e3:.3f} ms, best {min(ts) * 1e3:.3f} ms", flush=True)
+            eb.close()
+    engine.DdpCentroidalEngine.set_packed_io(1)
+    sys.exit(0)
 
 
 def timed(fn, reps):
