@@ -125,7 +125,10 @@ void ccc_ddp_centroidal_destroy(ccc_ddp_centroidal_ws_t * ws);
 
 /* Solve `batch->batch` independent DdpCentroidal problems: rollout, then up to
  * cfg->max_iter iterations of {derivatives, backward pass with BoxQP, line search, lambda
- * schedule} per problem, one warp per problem.
+ * schedule} per problem, one warp per problem; a batch of at most one problem per SM (the reference's own caller
+ * solves ONE problem per control tick) gets a thread block of eight warps per problem instead, with the line-search
+ * candidates rolled out concurrently.  Results do not depend on the batch size or the kernel chosen.
+ * CCC_MEM_HOST calls whose arrays fit 1 MB move through one pinned staging block (one copy in, one copy out).
  * Replaces: nmpc_ddp::DDPSolver<9,Dynamic>::solve as called at reference
  * src/DdpCentroidal.cpp:229,233 together with the DdpProblem callbacks at :32-177. */
 int32_t ccc_ddp_centroidal_solve(ccc_ddp_centroidal_ws_t * ws,
