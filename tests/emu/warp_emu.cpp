@@ -41,6 +41,8 @@ bool g_done[kMaxThreads];
 int g_cur = 0, g_nthreads = 32, g_alive = 0;
 int g_arrived[kCtaGroup + 1] = {};
 unsigned long g_gen[kCtaGroup + 1] = {};
+int g_wait_group[kMaxThreads];          // barrier group a fibre is parked at, or -1
+unsigned long g_wait_gen[kMaxThreads];  // ... and the generation it waits to see pass
 double g_xd[kMaxThreads];
 int g_xi[kMaxThreads];
 std::function<void()> g_body;
@@ -52,7 +54,9 @@ void yield()
   for(int s = 1; s <= g_nthreads; s++)
   {
     int c = (from + s) % g_nthreads;
-    if(!g_done[c])
+    // a fibre parked at a barrier that has not moved is not worth a context switch (the seven helper warps of a team
+    // wait at the CTA barrier for the whole backward pass of the leader)
+    if(!g_done[c] && !(g_wait_group[c] >= 0 && g_gen[g_wait_group[c]] == g_wait_gen[c]))
     {
       nxt = c;
       break;
@@ -73,7 +77,10 @@ void barrier(int group, int size)
   }
   else
   {
+    g_wait_group[g_cur] = group;
+    g_wait_gen[g_cur] = gen;
     while(g_gen[group] == gen) yield();
+    g_wait_group[g_cur] = -1;
   }
 }
 
@@ -151,6 +158,7 @@ void run_cta(int nthreads, const std::function<void()> & body)
   for(int i = 0; i < nthreads; i++)
   {
     g_done[i] = false;
+    g_wait_group[i] = -1;
     getcontext(&g_ctx[i]);
     g_ctx[i].uc_stack.ss_sp = g_stacks.data() + kStack * i;
     g_ctx[i].uc_stack.ss_size = kStack;
