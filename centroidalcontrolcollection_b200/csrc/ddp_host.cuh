@@ -232,7 +232,7 @@ inline int & g_packed_io()
 }
 inline int & g_chunk()
 {
-  static int c = 32; // DDP iterations per visit before a solve is suspended and re-queued
+  static int c = 64; // DDP iterations per visit before a solve is suspended and re-queued (sweep: profiles/r02i_ab_chunk*.txt)
   return c;
 }
 
