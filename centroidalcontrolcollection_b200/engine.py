@@ -256,10 +256,15 @@ class QpEngine:
 
     __del__ = close
 
-    def solve(self, problem_set, result=None):
-        """Host buffers in/out (H2D + setup + solve + D2H, synchronous)."""
+    def solve(self, problem_set, result=None, reuse_matrices=False):
+        """Host buffers in/out (H2D + setup + solve + D2H, synchronous).  reuse_matrices: Q = A = C = NULL, i.e. the
+        matrices and their factorisation of the previous call on this workspace are kept and only the per-problem vectors
+        are new — what a controller does on every tick after its first (CCC/detail/QpEngine.h matrices_resident_; the
+        reference fills qp_coeff_'s matrices in its constructor and only rewrites the vectors in procOnce)."""
         res = result if result is not None else problem_set.new_result()
         bs, rs = problem_set.as_struct(), res.as_struct()
+        if reuse_matrices:
+            bs.Q = bs.A = bs.C = None
         _check(lib().ccc_qp_solve(self._h, C.addressof(bs), C.addressof(rs), _abi.CCC_MEM_HOST, None), "ccc_qp_solve")
         return res
 
