@@ -53,6 +53,23 @@ def test_host_models_and_preview_control_closed_loop():
     _run(_compile("TestHostModels", None))
 
 
+@pytest.mark.parametrize("mode", ["standin", "absent", "disabled"])
+def test_eigen_interop_header(mode):
+    """CCC/EigenInterop.h (conversions between the drop-in classes' std::array / std::vector and Eigen's vector types) in its
+    three states: <Eigen/Core> found (a minimal stand-in, tests/cpp/eigen_standin: Eigen is not in this image), not found,
+    and found but switched off with CCC_B200_NO_EIGEN."""
+    exe = os.path.join(CPP, f"TestEigenInterop_{mode}.bin")
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-o", exe, os.path.join(CPP, "TestEigenInterop.cpp")]
+    if mode != "absent":
+        cmd += ["-I" + os.path.join(CPP, "eigen_standin")]
+    if mode == "disabled":
+        cmd += ["-DCCC_B200_NO_EIGEN"]
+    subprocess.check_call(cmd)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "ALL CHECKS PASSED" in r.stdout, r.stdout + r.stderr
+    assert ("EigenInterop active" in r.stdout) == (mode == "standin")
+
+
 @pytest.mark.parametrize("name", ENGINE_TESTS)
 def test_cpp_host_logic_with_oracle_engine(name):
     """The reference scenarios through the C++ classes with the CPU oracle standing in for the engine."""
