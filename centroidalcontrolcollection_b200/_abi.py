@@ -213,6 +213,14 @@ class FootGuidedBatch(C.Structure):
                 ("transit_end_zmp", C.c_void_p), ("transit_start_time", C.c_void_p), ("transit_duration", C.c_void_p)]
 
 
+class SingularPreviewBatch(C.Structure):
+    """ccc_singular_preview_batch_t"""
+
+    _fields_ = [("batch", C.c_int32), ("n_plans", C.c_int32), ("horizon_steps", C.c_int32), ("reserved0", C.c_int32),
+                ("omega", C.c_double), ("horizon_dt", C.c_double), ("control_dt", C.c_double), ("plan_id", C.c_void_p),
+                ("state", C.c_void_p), ("ref_zmp", C.c_void_p)]
+
+
 def ptr(a):
     """Address of a C-contiguous numpy array (or None)."""
     if a is None:

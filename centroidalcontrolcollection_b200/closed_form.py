@@ -1,5 +1,6 @@
-"""Host classes of the two closed-form ZMP controllers: DcmTracking (reference include/CCC/DcmTracking.h,
-src/DcmTracking.cpp) and FootGuidedControl (include/CCC/FootGuidedControl.h, src/FootGuidedControl.cpp).
+"""Host classes of the closed-form ZMP controllers: DcmTracking (reference include/CCC/DcmTracking.h,
+src/DcmTracking.cpp), FootGuidedControl (include/CCC/FootGuidedControl.h, src/FootGuidedControl.cpp) and
+SingularPreviewControlZmp (include/CCC/SingularPreviewControlZmp.h, src/SingularPreviewControlZmp.cpp).
 
 `plan_once` is the reference's planOnce for one problem in numpy scalars (the check of the batched kernels);
 `plan_batch` flattens P reference-data records and B initial parameters into the C-ABI structs and runs
@@ -96,6 +97,52 @@ class FootGuidedControl:
                     transit_duration=np.array([r["transit_duration"] for r in ref_data], dtype=np.float64))
         bt = _abi.FootGuidedBatch()
         bt.batch, bt.n_plans, bt.omega = B, P, self.omega
+        for k, v in keep.items():
+            setattr(bt, k, ptr(v))
+        return run(bt, B)
+
+
+class SingularPreviewControlZmp:
+    """Urata's singular LQ preview regulation (reference include/CCC/SingularPreviewControlZmp.h:46-51, 102-106)."""
+
+    def __init__(self, com_height, horizon_duration, horizon_dt):
+        self.horizon_dt = horizon_dt
+        self.horizon_steps = int(math.ceil(horizon_duration / horizon_dt))
+        self.omega = math.sqrt(G / com_height)
+
+    def sample(self, ref_zmp_func, current_time):
+        """planOnce's sampling of the reference (src/SingularPreviewControlZmp.cpp:66-71) -> [N][2]."""
+        return np.array([np.asarray(ref_zmp_func(current_time + i * self.horizon_dt), dtype=np.float64) for i in range(self.horizon_steps)])
+
+    def proc_once_1d(self, ref_zmp_seq, planned_zmp, pos, vel, control_dt):
+        """src/SingularPreviewControlZmp.cpp:23-57 in Python floats, the expressions term by term (std::pow(b, 2) as b * b)."""
+        w, dt = self.omega, self.horizon_dt
+        k0 = (1 + w * dt) / dt + w / (1 + w * dt)
+        k1 = -1 * (2 + w * dt) / dt
+        k2 = -1 * (2 + w * dt) / (w * dt)
+        u_fb = -1 * ((k0 * planned_zmp + k1 * pos) + k2 * vel)
+        s0 = float(ref_zmp_seq[-1]) * (1 + w * dt) / (w * dt)
+        b = 1 + w * dt
+        for i in range(len(ref_zmp_seq) - 2, 0, -1):
+            s0 = float(ref_zmp_seq[i]) + s0 / b
+        u_ff = float(ref_zmp_seq[0]) / dt - w * (2 + w * dt) * s0 / (b * b)
+        return planned_zmp + control_dt * (u_fb + u_ff)
+
+    def plan_once(self, ref_zmp_func, pos, vel, planned_zmp, current_time, control_dt=-1):
+        """2-D planOnce (:59-88) on the host."""
+        control_dt = self.horizon_dt if control_dt < 0 else control_dt
+        seq = self.sample(ref_zmp_func, current_time)
+        return np.array([self.proc_once_1d(seq[:, a], float(planned_zmp[a]), float(pos[a]), float(vel[a]), control_dt) for a in range(2)])
+
+    def plan_batch(self, run, ref_zmp, state, plan_id, control_dt=-1):
+        """ref_zmp [P][N][2] (sampled sequences); state [B][2][3] per axis (planned_zmp, pos, vel); plan_id [B]."""
+        keep = dict(plan_id=np.ascontiguousarray(plan_id, dtype=np.int32), state=np.ascontiguousarray(state, dtype=np.float64),
+                    ref_zmp=np.ascontiguousarray(ref_zmp, dtype=np.float64))
+        P, B = keep["ref_zmp"].shape[0], len(keep["plan_id"])
+        assert keep["ref_zmp"].shape == (P, self.horizon_steps, 2) and keep["state"].shape == (B, 2, 3)
+        bt = _abi.SingularPreviewBatch()
+        bt.batch, bt.n_plans, bt.horizon_steps = B, P, self.horizon_steps
+        bt.omega, bt.horizon_dt, bt.control_dt = self.omega, self.horizon_dt, (self.horizon_dt if control_dt < 0 else control_dt)
         for k, v in keep.items():
             setattr(bt, k, ptr(v))
         return run(bt, B)

@@ -1,5 +1,5 @@
-// closed_form.cu — ccc_dcm_tracking_plan / ccc_foot_guided_plan (include/ccc_b200.h): the two closed-form ZMP
-// controllers of the reference, batched; one thread per problem, both axes.
+// closed_form.cu — ccc_dcm_tracking_plan / ccc_foot_guided_plan / ccc_singular_preview_plan (include/ccc_b200.h): the
+// closed-form ZMP controllers of the reference, batched; one thread per problem (and axis).
 //
 // Replaces: CCC::DcmTracking::planOnce (reference src/DcmTracking.cpp:7-48) and CCC::FootGuidedControl1d::planOnce
 // (src/FootGuidedControl.cpp:11-69) x 2 axes (:71-92).  The expressions are the reference's, term by term (the file is
@@ -101,6 +101,44 @@ __global__ void foot_guided_kernel(ccc_foot_guided_batch_t in, double * __restri
     }
     out[2 * b + a] = bad ? nan : planned_zmp;
   }
+}
+
+/** Feed-forward term of SingularPreviewControlZmp1d::procOnce (reference src/SingularPreviewControlZmp.cpp:38-48) for one
+ *  (plan, axis): S0 by the backward recursion of equation (25), then u_ff of equation (26).  One thread per (plan, axis). */
+__global__ void singular_preview_ff_kernel(int P, int N, double omega, double dt, const double * __restrict__ ref_zmp, double * __restrict__ u_ff)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if(idx >= 2 * P) return;
+  const int p = idx >> 1, a = idx & 1;
+  const double * seq = ref_zmp + (size_t)p * N * 2 + a; // stride 2
+  const double b = 1 + omega * dt;
+  double S0 = seq[(size_t)(N - 1) * 2] * (1 + omega * dt) / (omega * dt);
+  for(int i = N - 2; i >= 1; i--) S0 = seq[(size_t)i * 2] + S0 / b;
+  u_ff[idx] = seq[0] / dt - omega * (2 + omega * dt) * S0 / (b * b);
+}
+
+/** Feedback term (equation (16), :30-36), u = u_fb + u_ff (equation (9)) and the ZMP update (:52-55); one thread per
+ *  (problem, axis). */
+__global__ void singular_preview_kernel(ccc_singular_preview_batch_t in, const double * __restrict__ u_ff, double * __restrict__ out)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if(idx >= 2 * in.batch) return;
+  const int b = idx >> 1, a = idx & 1;
+  const int p = in.plan_id[b];
+  if(p < 0 || p >= in.n_plans)
+  {
+    out[idx] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  const double omega = in.omega, dt = in.horizon_dt;
+  const double * x = in.state + (size_t)idx * 3;
+  const double K0 = (1 + omega * dt) / dt + omega / (1 + omega * dt);
+  const double K1 = -1 * (2 + omega * dt) / dt;
+  const double K2 = -1 * (2 + omega * dt) / (omega * dt);
+  // Eigen's 3-vector dot product: K[0] x[0] + K[1] x[1] + K[2] x[2], left to right
+  const double u_fb = -1 * ((K0 * x[0] + K1 * x[1]) + K2 * x[2]);
+  const double u = u_fb + u_ff[2 * p + a];
+  out[idx] = x[0] + in.control_dt * u;
 }
 
 /** Host-buffer staging: one device allocation for the doubles, one for the ints; `push` copies and returns the device address. */
@@ -215,6 +253,43 @@ int32_t ccc_foot_guided_plan(const ccc_foot_guided_batch_t * bt, double * planne
   if(!st.ok) return CCC_ERR_CUDA;
   foot_guided_kernel<<<(B + 127) / 128, 128>>>(d, out);
   if(!check(cudaGetLastError(), "launch foot_guided_kernel")) return CCC_ERR_CUDA;
+  return check(cudaMemcpy(planned_zmp, out, sizeof(double) * B * 2, cudaMemcpyDeviceToHost), "D2H") ? CCC_OK : CCC_ERR_CUDA;
+}
+
+int32_t ccc_singular_preview_plan(const ccc_singular_preview_batch_t * bt, double * planned_zmp, int32_t mem, void * stream)
+{
+  using ccc_host::check;
+  if(!bt || !planned_zmp) return ccc_host::fail(CCC_ERR_INVALID, "null argument");
+  const int B = bt->batch, P = bt->n_plans, N = bt->horizon_steps;
+  if(B <= 0 || P <= 0 || N < 1 || !(bt->omega > 0) || !(bt->horizon_dt > 0))
+    return ccc_host::fail(CCC_ERR_INVALID, "ccc_singular_preview_plan: sizes / omega / horizon_dt");
+  if(!bt->plan_id || !bt->state || !bt->ref_zmp) return ccc_host::fail(CCC_ERR_INVALID, "null input");
+  if(mem != CCC_MEM_HOST)
+  {
+    // device pointers: the per-plan feed-forward terms need scratch of their own (freed on the stream's order)
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    double * u_ff = nullptr;
+    if(!check(cudaMallocAsync(reinterpret_cast<void **>(&u_ff), sizeof(double) * 2 * (size_t)P, st), "cudaMallocAsync")) return CCC_ERR_CUDA;
+    singular_preview_ff_kernel<<<(2 * P + 127) / 128, 128, 0, st>>>(P, N, bt->omega, bt->horizon_dt, bt->ref_zmp, u_ff);
+    singular_preview_kernel<<<(2 * B + 127) / 128, 128, 0, st>>>(*bt, u_ff, planned_zmp);
+    const bool ok = check(cudaGetLastError(), "launch singular_preview_kernel");
+    cudaFreeAsync(u_ff, st);
+    return ok ? CCC_OK : CCC_ERR_CUDA;
+  }
+  for(int b = 0; b < B; b++)
+    if(bt->plan_id[b] < 0 || bt->plan_id[b] >= P) return ccc_host::fail(CCC_ERR_INVALID, "plan_id out of range");
+  if(!have_device()) return ccc_host::fail(CCC_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+  Stage st(sizeof(double) * ((size_t)B * 8 + (size_t)P * (2 * (size_t)N + 2)) + sizeof(int) * (size_t)B + 256);
+  ccc_singular_preview_batch_t d = *bt;
+  d.plan_id = st.push(bt->plan_id, B);
+  d.state = st.push(bt->state, (size_t)B * 6);
+  d.ref_zmp = st.push(bt->ref_zmp, (size_t)P * N * 2);
+  double * u_ff = st.room<double>((size_t)P * 2);
+  double * out = st.room<double>((size_t)B * 2);
+  if(!st.ok) return CCC_ERR_CUDA;
+  singular_preview_ff_kernel<<<(2 * P + 127) / 128, 128>>>(P, N, bt->omega, bt->horizon_dt, d.ref_zmp, u_ff);
+  singular_preview_kernel<<<(2 * B + 127) / 128, 128>>>(d, u_ff, out);
+  if(!check(cudaGetLastError(), "launch singular_preview_kernel")) return CCC_ERR_CUDA;
   return check(cudaMemcpy(planned_zmp, out, sizeof(double) * B * 2, cudaMemcpyDeviceToHost), "D2H") ? CCC_OK : CCC_ERR_CUDA;
 }
 

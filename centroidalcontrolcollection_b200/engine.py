@@ -24,7 +24,7 @@ EXPORTS = [
     "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
     "ccc_qp_create_grouped", "ccc_qp_solve_grouped",
     "ccc_fp64_peak_tflops",
-    "ccc_dcm_tracking_plan", "ccc_foot_guided_plan",
+    "ccc_dcm_tracking_plan", "ccc_foot_guided_plan", "ccc_singular_preview_plan",
     "ccc_footstep_compile", "ccc_zmp_mpc_create", "ccc_zmp_mpc_destroy", "ccc_zmp_mpc_plan", "ccc_zmp_mpc_last_launches",
     "ccc_linear_mpc_xy_create", "ccc_linear_mpc_xy_destroy", "ccc_linear_mpc_xy_solve", "ccc_linear_mpc_xy_last_launches",
 ]
@@ -101,7 +101,7 @@ def lib():
         L.ccc_qp_set_packed.argtypes = [C.c_int32]
         L.ccc_preview_input.restype = C.c_int32
         L.ccc_preview_input.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]
-        for fn in ("ccc_dcm_tracking_plan", "ccc_foot_guided_plan"):
+        for fn in ("ccc_dcm_tracking_plan", "ccc_foot_guided_plan", "ccc_singular_preview_plan"):
             getattr(L, fn).restype = C.c_int32
             getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.ccc_footstep_compile.restype = C.c_int32
@@ -302,6 +302,13 @@ def foot_guided_plan(batch_struct, batch):
     """ccc_foot_guided_plan with host buffers -> planned ZMP [B][2]."""
     out = np.zeros((batch, 2))
     _check(lib().ccc_foot_guided_plan(C.addressof(batch_struct), out.ctypes.data, _abi.CCC_MEM_HOST, None), "ccc_foot_guided_plan")
+    return out
+
+
+def singular_preview_plan(batch_struct, batch):
+    """ccc_singular_preview_plan with host buffers -> planned ZMP [B][2] (closed_form.SingularPreviewControlZmp.plan_batch)."""
+    out = np.zeros((batch, 2))
+    _check(lib().ccc_singular_preview_plan(C.addressof(batch_struct), out.ctypes.data, _abi.CCC_MEM_HOST, None), "ccc_singular_preview_plan")
     return out
 
 

@@ -494,6 +494,28 @@ typedef struct
 } ccc_foot_guided_batch_t;
 int32_t ccc_foot_guided_plan(const ccc_foot_guided_batch_t * batch, double * planned_zmp /* [B][2] */, int32_t mem, void * stream);
 
+/* ---- CCC::SingularPreviewControlZmp ---------------------------------------------------------------------
+ * Urata's singular LQ preview regulation (reference src/SingularPreviewControlZmp.cpp:23-57, x 2 axes :59-88) for a batch:
+ * problem b = (planned ZMP, CoM position, CoM velocity) per axis, on the reference-ZMP sequence of plan plan_id[b]
+ * (ref_zmp_func sampled at current_time + i horizon_dt, i < N, as planOnce does at :14-19).  The feed-forward term of a
+ * plan (the backward recursion of equations (25)-(27) over the sequence) is evaluated once per plan and axis, the feedback
+ * term and the ZMP update per problem.  Arithmetic: the reference's expressions term by term, with std::pow(b, 2) as b * b
+ * (no transcendental on the path: results equal a host evaluation of the same expressions bit for bit). */
+typedef struct
+{
+  int32_t batch;         /* B */
+  int32_t n_plans;       /* P */
+  int32_t horizon_steps; /* N = ceil(horizon_duration / horizon_dt) (include/CCC/SingularPreviewControlZmp.h:48) */
+  int32_t reserved0;
+  double omega;      /* sqrt(g / com_height) */
+  double horizon_dt; /* discretisation step of the horizon */
+  double control_dt; /* step used to integrate the planned ZMP (planOnce's control_dt) */
+  const int32_t * plan_id; /* [B] */
+  const double * state;    /* [B][2][3] per axis: planned_zmp, pos, vel (InitialParam, :30-31) */
+  const double * ref_zmp;  /* [P][N][2] */
+} ccc_singular_preview_batch_t;
+int32_t ccc_singular_preview_plan(const ccc_singular_preview_batch_t * batch, double * planned_zmp /* [B][2] */, int32_t mem, void * stream);
+
 /* ---- CCC::PreviewControl<3,1,1>::calcOptimalInput ------------------------------------------------
  * Batched online part of preview control:  u[b] = -K x[b] + F ref_seq[b]   (gains K (1x3), F (1xN) shared).
  * Replaces: PreviewControl::calcOptimalInput (reference include/CCC/PreviewControl.h:86-89) as called from

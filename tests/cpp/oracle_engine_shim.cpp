@@ -191,6 +191,29 @@ int32_t ccc_foot_guided_plan(const ccc_foot_guided_batch_t * bt, double * out, i
   }
   return CCC_OK;
 }
+/* src/SingularPreviewControlZmp.cpp:23-57 per problem and axis, the reference's expressions with std::pow as written there. */
+int32_t ccc_singular_preview_plan(const ccc_singular_preview_batch_t * bt, double * out, int32_t, void *)
+{
+  const int N = bt->horizon_steps;
+  const double w = bt->omega, dt = bt->horizon_dt;
+  for(int b = 0; b < bt->batch; b++)
+  {
+    const int p = bt->plan_id[b];
+    if(p < 0 || p >= bt->n_plans) return CCC_ERR_INVALID;
+    for(int a = 0; a < 2; a++)
+    {
+      const double * x = bt->state + (static_cast<size_t>(b) * 2 + a) * 3;
+      const double * seq = bt->ref_zmp + static_cast<size_t>(p) * N * 2 + a;
+      const double K[3] = {(1 + w * dt) / dt + w / (1 + w * dt), -1 * (2 + w * dt) / dt, -1 * (2 + w * dt) / (w * dt)};
+      const double u_fb = -1 * (K[0] * x[0] + K[1] * x[1] + K[2] * x[2]);
+      double S0 = seq[static_cast<size_t>(N - 1) * 2] * (1 + w * dt) / (w * dt);
+      for(int i = N - 2; i >= 1; i--) S0 = seq[static_cast<size_t>(i) * 2] + S0 / (1 + w * dt);
+      const double u_ff = seq[0] / dt - w * (2 + w * dt) * S0 / std::pow(1 + w * dt, 2);
+      out[2 * b + a] = x[0] + bt->control_dt * (u_fb + u_ff);
+    }
+  }
+  return CCC_OK;
+}
 const char * ccc_last_error(void) { return "oracle shim"; }
 int32_t ccc_device_count(void) { return 0; }
 int32_t ccc_abi_version(void) { return CCC_B200_ABI_VERSION; }
