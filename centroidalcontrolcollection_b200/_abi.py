@@ -221,6 +221,22 @@ class SingularPreviewBatch(C.Structure):
                 ("state", C.c_void_p), ("ref_zmp", C.c_void_p)]
 
 
+class StepMpcBatch(C.Structure):
+    """ccc_step_mpc_batch_t"""
+
+    _fields_ = [("batch", C.c_int32), ("n_plans", C.c_int32), ("max_elements", C.c_int32), ("reserved0", C.c_int32),
+                ("com_height", C.c_double), ("w_free_zmp", C.c_double), ("w_fixed_zmp", C.c_double), ("w_double_support", C.c_double),
+                ("w_pos", C.c_double), ("w_vel", C.c_double), ("w_capture_point_abs", C.c_double), ("w_capture_point_rel", C.c_double),
+                ("plan_id", C.c_void_p), ("x_pos", C.c_void_p), ("x_vel", C.c_void_p), ("current_time", C.c_void_p),
+                ("n_elements", C.c_void_p), ("single", C.c_void_p), ("zmp", C.c_void_p), ("end_time", C.c_void_p)]
+
+
+class StepMpcResult(C.Structure):
+    """ccc_step_mpc_result_t"""
+
+    _fields_ = [("current_zmp", C.c_void_p), ("next_foot_zmp", C.c_void_p), ("has_next", C.c_void_p)]
+
+
 def ptr(a):
     """Address of a C-contiguous numpy array (or None)."""
     if a is None:

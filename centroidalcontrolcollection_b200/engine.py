@@ -24,7 +24,7 @@ EXPORTS = [
     "ccc_qp_create", "ccc_qp_destroy", "ccc_qp_solve", "ccc_qp_last_launches", "ccc_preview_input",
     "ccc_qp_create_grouped", "ccc_qp_solve_grouped",
     "ccc_fp64_peak_tflops",
-    "ccc_dcm_tracking_plan", "ccc_foot_guided_plan", "ccc_singular_preview_plan",
+    "ccc_dcm_tracking_plan", "ccc_foot_guided_plan", "ccc_singular_preview_plan", "ccc_step_mpc_plan",
     "ccc_footstep_compile", "ccc_zmp_mpc_create", "ccc_zmp_mpc_destroy", "ccc_zmp_mpc_plan", "ccc_zmp_mpc_last_launches",
     "ccc_linear_mpc_xy_create", "ccc_linear_mpc_xy_destroy", "ccc_linear_mpc_xy_solve", "ccc_linear_mpc_xy_last_launches",
 ]
@@ -310,6 +310,18 @@ def singular_preview_plan(batch_struct, batch):
     out = np.zeros((batch, 2))
     _check(lib().ccc_singular_preview_plan(C.addressof(batch_struct), out.ctypes.data, _abi.CCC_MEM_HOST, None), "ccc_singular_preview_plan")
     return out
+
+
+def step_mpc_plan(batch_struct, batch):
+    """ccc_step_mpc_plan with host buffers -> (current_zmp [B][2], next_foot_zmp [B][2], has_next [B]) (step_mpc.StepMpc.plan_batch)."""
+    cur, nxt, has = np.zeros((batch, 2)), np.zeros((batch, 2)), np.zeros(batch, dtype=np.int32)
+    rs = _abi.StepMpcResult()
+    rs.current_zmp, rs.next_foot_zmp, rs.has_next = cur.ctypes.data, nxt.ctypes.data, has.ctypes.data
+    L = lib()
+    L.ccc_step_mpc_plan.restype = C.c_int32
+    L.ccc_step_mpc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    _check(L.ccc_step_mpc_plan(C.addressof(batch_struct), C.addressof(rs), _abi.CCC_MEM_HOST, None), "ccc_step_mpc_plan")
+    return cur, nxt, has
 
 
 def footstep_compile(plans, tables=None):

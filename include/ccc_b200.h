@@ -516,6 +516,43 @@ typedef struct
 } ccc_singular_preview_batch_t;
 int32_t ccc_singular_preview_plan(const ccc_singular_preview_batch_t * batch, double * planned_zmp /* [B][2] */, int32_t mem, void * stream);
 
+/* ---- CCC::StepMpc ----------------------------------------------------------------------------------------
+ * Xin's step-to-step MPC (reference src/StepMpc.cpp:27-193, x 2 axes :195-247) for a batch: problem b = CoM position and
+ * velocity per axis on the reference data of plan plan_id[b] (support phases with their ZMP and end time,
+ * include/CCC/StepMpc.h:36-55).  One unknown per phase (at most CCC_STEP_MPC_MAX_ELEMENTS); a thread per problem and axis
+ * propagates the closed-form step model over the phases (StepModel, src/StepMpc.cpp:8-25: cosh / sinh of omega x duration),
+ * accumulates the weighted least-squares system term by term as the reference does (every term is a sum of rank-one
+ * updates with rows of the condensed output matrix) and solves it by Gaussian elimination with partial pivoting (the
+ * reference: Eigen colPivHouseholderQr).  The systems are ill conditioned by construction (cosh of up to three seconds of
+ * horizon squared: condition numbers of 1e8 - 1e11), so two solvers agree to ~1e-6, not to rounding; the reference's own
+ * test asks for 1e-2 (tests/src/TestStepMpc.cpp:138-141). */
+#define CCC_STEP_MPC_MAX_ELEMENTS 16
+typedef struct
+{
+  int32_t batch;        /* B */
+  int32_t n_plans;      /* P */
+  int32_t max_elements; /* K <= CCC_STEP_MPC_MAX_ELEMENTS: row stride of the element lists */
+  int32_t reserved0;
+  double com_height;
+  /* StepMpc1d::WeightParam (include/CCC/StepMpc.h:84-117) */
+  double w_free_zmp, w_fixed_zmp, w_double_support, w_pos, w_vel, w_capture_point_abs, w_capture_point_rel;
+  const int32_t * plan_id;      /* [B] */
+  const double * x_pos;         /* [B][2] InitialParam.pos */
+  const double * x_vel;         /* [B][2] InitialParam.vel */
+  const double * current_time;  /* [P] */
+  const int32_t * n_elements;   /* [P] 1 .. K */
+  const int32_t * single;       /* [P][K] Element.is_single_support */
+  const double * zmp;           /* [P][K][2] Element.zmp */
+  const double * end_time;      /* [P][K] Element.end_time */
+} ccc_step_mpc_batch_t;
+typedef struct
+{
+  double * current_zmp;   /* [B][2] PlannedData.current_zmp */
+  double * next_foot_zmp; /* [B][2] PlannedData.next_foot_zmp (0 where has_next is 0) */
+  int32_t * has_next;     /* [B] 1 if a single-support phase of the next foot lies in the horizon (std::optional has a value) */
+} ccc_step_mpc_result_t;
+int32_t ccc_step_mpc_plan(const ccc_step_mpc_batch_t * batch, const ccc_step_mpc_result_t * result, int32_t mem, void * stream);
+
 /* ---- CCC::PreviewControl<3,1,1>::calcOptimalInput ------------------------------------------------
  * Batched online part of preview control:  u[b] = -K x[b] + F ref_seq[b]   (gains K (1x3), F (1xN) shared).
  * Replaces: PreviewControl::calcOptimalInput (reference include/CCC/PreviewControl.h:86-89) as called from

@@ -221,6 +221,41 @@ public:
     if(start_time + duration < current_time + horizon_margin) duration += horizon_margin;
   }
 
+  /** One support phase of FootstepManager::makeStepMpcRefData. */
+  struct StepElement
+  {
+    bool is_single_support;
+    Vec2 zmp;
+    double end_time;
+  };
+
+  /** FootstepManager::makeStepMpcRefData (:385-448). */
+  std::vector<StepElement> makeStepMpcRefData(double current_time) const
+  {
+    current_time -= 1e-6;
+    const double constant_zmp_duration = 0.2, horizon_duration = 3.0;
+    std::vector<StepElement> el;
+    if(footstep_list_.empty())
+    {
+      el.push_back({false, midPos(footstance_), current_time + constant_zmp_duration});
+      return el;
+    }
+    Footstance tmp = footstance_;
+    if(current_time < footstep_list_.front().swing_start_time) el.push_back({false, midPos(tmp), footstep_list_.front().swing_start_time});
+    for(size_t i = 0; i < footstep_list_.size(); i++)
+    {
+      const Footstep & fs = footstep_list_[i];
+      if(i > 0 || current_time < fs.swing_end_time)
+      {
+        el.push_back({true, tmp.at(opposite(fs.foot)), fs.swing_end_time});
+        tmp[fs.foot] = fs.pos;
+      }
+      el.push_back({false, midPos(tmp), i == footstep_list_.size() - 1 ? fs.transit_end_time : footstep_list_[i + 1].swing_start_time});
+      if(el.back().end_time > current_time + horizon_duration) break;
+    }
+    return el;
+  }
+
   Footstance footstance_;
   std::deque<Footstep> footstep_list_;
   std::shared_ptr<Footstep> prev_footstep_;

@@ -6,6 +6,7 @@
  * libccc_b200.so on the GPU.  It is linked INSTEAD of libccc_b200.so by tests/test_cpp_dropin.py only; the
  * product library has no CPU path and nothing in the package refers to this file.
  */
+#include "../../centroidalcontrolcollection_b200/csrc/step_mpc_core.cuh"
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -210,6 +211,31 @@ int32_t ccc_singular_preview_plan(const ccc_singular_preview_batch_t * bt, doubl
       for(int i = N - 2; i >= 1; i--) S0 = seq[static_cast<size_t>(i) * 2] + S0 / (1 + w * dt);
       const double u_ff = seq[0] / dt - w * (2 + w * dt) * S0 / std::pow(1 + w * dt, 2);
       out[2 * b + a] = x[0] + bt->control_dt * (u_fb + u_ff);
+    }
+  }
+  return CCC_OK;
+}
+/* StepMpc: the kernel's scalar core (csrc/step_mpc_core.cuh) compiled for the host, a problem and axis at a time. */
+int32_t ccc_step_mpc_plan(const ccc_step_mpc_batch_t * bt, const ccc_step_mpc_result_t * res, int32_t, void *)
+{
+  const int K = bt->max_elements;
+  const ccc_step::Weights w = {bt->w_free_zmp, bt->w_fixed_zmp, bt->w_double_support, bt->w_pos, bt->w_vel, bt->w_capture_point_abs,
+                               bt->w_capture_point_rel};
+  for(int b = 0; b < bt->batch; b++)
+  {
+    const int p = bt->plan_id[b];
+    if(p < 0 || p >= bt->n_plans || bt->n_elements[p] < 1 || bt->n_elements[p] > K) return CCC_ERR_INVALID;
+    for(int a = 0; a < 2; a++)
+    {
+      double cur = 0, nxt = 0;
+      bool has = false;
+      if(!ccc_step::plan_1d(bt->n_elements[p], bt->single + static_cast<size_t>(p) * K, bt->zmp + static_cast<size_t>(p) * K * 2 + a, 2,
+                            bt->end_time + static_cast<size_t>(p) * K, bt->current_time[p], bt->com_height, w, bt->x_pos[2 * b + a],
+                            bt->x_vel[2 * b + a], cur, nxt, has))
+        return CCC_ERR_INVALID;
+      res->current_zmp[2 * b + a] = cur;
+      if(res->next_foot_zmp) res->next_foot_zmp[2 * b + a] = nxt;
+      if(res->has_next) res->has_next[b] = has ? 1 : 0;
     }
   }
   return CCC_OK;

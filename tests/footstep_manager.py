@@ -162,3 +162,24 @@ def walking_plan(step_length=0.2, step_width=0.2, transit_duration=0.2, swing_du
                         (RIGHT, 3 * L, 7.0)]:
         m.append_footstep(Footstep(foot, (x, w if foot == LEFT else -w), t0, transit_duration, swing_duration))
     return m
+
+
+def make_step_mpc_ref_data(fm, current_time):
+    """FootstepManager::makeStepMpcRefData (:385-448) -> [(is_single_support, zmp[2], end_time), ...]."""
+    t = current_time - EPS_T
+    constant_zmp_duration, horizon_duration = 0.2, 3.0
+    fl = fm.footstep_list
+    if not fl:
+        return [(False, mid_pos(fm.footstance), t + constant_zmp_duration)]
+    elements = []
+    tmp = {k: v.copy() for k, v in fm.footstance.items()}
+    if t < fl[0].swing_start_time:
+        elements.append((False, mid_pos(tmp), fl[0].swing_start_time))
+    for i, fs in enumerate(fl):
+        if i > 0 or t < fs.swing_end_time:
+            elements.append((True, tmp[opposite(fs.foot)].copy(), fs.swing_end_time))
+            tmp[fs.foot] = fs.pos.copy()
+        elements.append((False, mid_pos(tmp), fs.transit_end_time if i == len(fl) - 1 else fl[i + 1].swing_start_time))
+        if elements[-1][2] > t + horizon_duration:
+            break
+    return elements

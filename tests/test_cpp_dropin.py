@@ -19,7 +19,7 @@ PKG = os.path.join(ROOT, "centroidalcontrolcollection_b200")
 CPP = os.path.join(ROOT, "tests", "cpp")
 ORACLE = os.path.join(ROOT, "oracle")
 
-ENGINE_TESTS = ["TestDdpCentroidal", "TestDdpSingleRigidBody", "TestDdpZmp", "TestZmpMpc", "TestLinearMpcXY", "TestLinearMpcZ", "TestClosedForm", "TestPreviewControlCentroidal"]
+ENGINE_TESTS = ["TestDdpCentroidal", "TestDdpSingleRigidBody", "TestDdpZmp", "TestZmpMpc", "TestLinearMpcXY", "TestLinearMpcZ", "TestClosedForm", "TestPreviewControlCentroidal", "TestStepMpc"]
 
 
 def _compile(name, engine):
