@@ -673,11 +673,8 @@ struct QpCta
         const int pick = best_i;
         const double worst = best;
         if(pick < 0) break; // optimal
-        if(q >= n)
-        {
-          status = 4;
-          break;
-        }
+        // (q == n with a violated constraint left: z is the empty sum, the step below is the dual-only step that drops a
+        // blocking constraint; A and u hold n + 1 entries for the pending one — oracle/qp.hpp)
         if(kPackedR && q >= P.rcap)
         {
           status = 5; // the packed R is full: this problem goes to the full-R kernel (never leaves the library)

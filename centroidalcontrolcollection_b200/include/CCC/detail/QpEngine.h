@@ -133,7 +133,7 @@ public:
       }
     if(n_failed_ > 0)
       std::cerr << "[CCC::QpEngine] failed to solve " << n_failed_ << " of " << batch_ << " QPs (first: problem " << first
-                << ", status " << status_[first] << ": 1 infeasible, 2 iteration limit, 3 not positive definite, 4 active set full)"
+                << ", status " << status_[first] << ": 1 infeasible, 2 iteration limit, 3 not positive definite)"
                 << std::endl;
     return x_;
   }

@@ -296,7 +296,7 @@ typedef struct
 {
   double * x;         /* [B][n] minimiser */
   int32_t * iters;    /* [B] constraints picked by the dual active-set loop */
-  int32_t * status;   /* [B] 0 solved, 1 infeasible, 2 iteration limit, 3 Q not positive definite, 4 active set full */
+  int32_t * status;   /* [B] 0 solved, 1 infeasible, 2 iteration limit, 3 Q not positive definite (4 is no longer produced: a full active set takes the dual step of Goldfarb-Idnani) */
   int32_t * n_active; /* [B] size of the final active set (equalities included) */
   int32_t * active;   /* [B][n] ids in activation order (0..n_eq-1 equalities, n_eq + i inequality i), -1 padded */
 } ccc_qp_result_t;

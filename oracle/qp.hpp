@@ -374,11 +374,8 @@ struct DenseQpSolver
           }
         }
         if(ip < 0) break; // optimal
-        if(q >= n)
-        {
-          res.status = 4;
-          break;
-        }
+        // (q == n with a violated constraint left: z = J[:, q:] d[q:] is the empty sum, so the step below is the dual-only
+        // step that drops a blocking constraint, as in Goldfarb-Idnani; A and u have n + 1 entries for the pending one)
         iter++;
         if(iter > max_iter)
         {

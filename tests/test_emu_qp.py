@@ -81,3 +81,28 @@ def test_linear_mpc_xy_structure_256_threads(oracle):
     assert (ref.status == 0).all() and ref.iters[0] > 20
     viol, dual = zip(*ps.kkt_residuals(ref.x, tol=1e-7))
     assert max(viol) < 1e-7
+
+
+def test_full_active_set_takes_the_dual_step(oracle):
+    """n = 2: min |x - (3, 3)|^2 s.t. x <= 1, y <= 1, x + y <= 1.5.  The dual active-set method first makes both box rows
+    active (q = n) and then meets the violated diagonal row: Goldfarb-Idnani takes a dual-only step there (z is the empty
+    sum) and drops a box row; the solution is (0.75, 0.75) with only the diagonal row active.  Same path, same bits in the
+    oracle and the CUDA core; a larger random family with more rows than a vertex can hold as well."""
+    Q = np.eye(2)
+    C = np.array([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])
+    d = np.array([[1.0, 1.0, 1.5], [1.0, 1.0, 1.2]])
+    c = np.array([[-3.0, -3.0], [-3.0, -2.0]])
+    ps = QpProblemSet(Q, C, d, c=c)
+    ref = _same(oracle, ps)
+    assert (ref.status == 0).all()
+    assert np.allclose(ref.x[0], [0.75, 0.75], atol=1e-12)
+    viol, dual = zip(*ps.kkt_residuals(ref.x))
+    assert max(viol) < 1e-12 and max(dual) < 1e-12
+    rng = np.random.default_rng(7)
+    n, mi, B = 6, 40, 12
+    Cn = rng.standard_normal((mi, n))
+    ps = QpProblemSet(np.eye(n), Cn / np.linalg.norm(Cn, axis=1)[:, None], rng.uniform(0.05, 0.3, (B, mi)), c=-4 * rng.standard_normal((B, n)))
+    ref = _same(oracle, ps)
+    assert (ref.status == 0).all()
+    viol, dual = zip(*ps.kkt_residuals(ref.x))
+    assert max(viol) < 1e-9 and max(dual) < 1e-8

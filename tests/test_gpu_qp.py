@@ -178,3 +178,21 @@ def test_matrix_groups(oracle):
     assert (got.status == 0).all() and (got.n_active > me).any()
     with pytest.raises(engine.EngineError):
         engine.QpEngine(n, me, mi, B, max_groups=3).solve_grouped(gp)
+
+
+def test_full_active_set_takes_the_dual_step(oracle, qp_solve):
+    """q = n with a violated row left: the dual-only step of Goldfarb-Idnani; see tests/test_emu_qp.py for the
+    two-variable case worked out."""
+    Q = np.eye(2)
+    C = np.array([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])
+    ps = QpProblemSet(Q, C, np.array([[1.0, 1.0, 1.5], [1.0, 1.0, 1.2]]), c=np.array([[-3.0, -3.0], [-3.0, -2.0]]))
+    ref = _parity(oracle, qp_solve, ps)
+    assert (ref.status == 0).all() and np.allclose(ref.x[0], [0.75, 0.75], atol=1e-12)
+    rng = np.random.default_rng(7)
+    n, mi, B = 6, 40, 300
+    Cn = rng.standard_normal((mi, n))
+    ps2 = QpProblemSet(np.eye(n), Cn / np.linalg.norm(Cn, axis=1)[:, None], rng.uniform(0.05, 0.3, (B, mi)), c=-4 * rng.standard_normal((B, n)))
+    ref = _parity(oracle, qp_solve, ps2)
+    assert (ref.status == 0).all()
+    viol, dual = zip(*ps2.kkt_residuals(ref.x))
+    assert max(viol) < 1e-9 and max(dual) < 1e-8
