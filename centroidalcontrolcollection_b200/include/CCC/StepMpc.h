@@ -21,53 +21,48 @@ namespace CCC
 class StepMpc1d
 {
 public:
+  /** One support phase per element (reference :36-55): at least one; two double-support phases never follow each other. */
   struct RefData
   {
     struct Element
     {
-      //! Whether it is in single support phase
-      bool is_single_support = true;
-      //! ZMP [m]
-      double zmp = 0;
-      //! End time [sec]
-      double end_time = 0;
+      bool is_single_support = true; // single (true) or double (false) support
+      double zmp = 0;                // reference ZMP of the phase [m]
+      double end_time = 0;           // [sec]
     };
-    //! At least one element; consecutive double support phases are not allowed
     std::vector<Element> element_list;
   };
 
+  /** reference :58-68 */
   struct PlannedData
   {
-    //! Current ZMP [m]
-    double current_zmp = 0;
-    //! ZMP of the next foot [m]; null if no single support phase of the next foot lies in the horizon
-    std::optional<double> next_foot_zmp;
+    double current_zmp = 0;              // ZMP to apply now [m]
+    std::optional<double> next_foot_zmp; // landing ZMP of the next foot [m]; empty if its single support is beyond the horizon
   };
 
-  /** CoM position, CoM velocity. */
+  /** (CoM position, CoM velocity), reference :75 */
   using InitialParam = std::array<double, 2>;
 
-  /** reference :78-117 (same defaults) */
+  /** Objective weights with the reference's defaults and argument order (:78-117). */
   struct WeightParam
   {
-    double free_zmp;
-    double fixed_zmp;
-    double double_support;
-    double pos;
-    double vel;
-    double capture_point_abs;
-    double capture_point_rel;
-
-    WeightParam(double _free_zmp = 1e-2,
-                double _fixed_zmp = 1e0,
-                double _double_support = 1e0,
-                double _pos = 0.0,
-                double _vel = 0.0,
-                double _capture_point_abs = 1e1,
-                double _capture_point_rel = 1e1)
-    : free_zmp(_free_zmp), fixed_zmp(_fixed_zmp), double_support(_double_support), pos(_pos), vel(_vel),
-      capture_point_abs(_capture_point_abs), capture_point_rel(_capture_point_rel)
+    double free_zmp = 1e-2;          // ZMP of future contacts
+    double fixed_zmp = 1e0;          // ZMP of existing contacts
+    double double_support = 1e0;     // smoothness of the ZMP through a double-support phase
+    double pos = 0.0;                // CoM position
+    double vel = 0.0;                // CoM velocity
+    double capture_point_abs = 1e1;  // capture point at the phase ends, absolute
+    double capture_point_rel = 1e1;  // capture point relative to the next ZMP
+    WeightParam() {}
+    WeightParam(double w_free, double w_fixed = 1e0, double w_ds = 1e0, double w_pos = 0.0, double w_vel = 0.0, double w_cp_abs = 1e1, double w_cp_rel = 1e1)
     {
+      free_zmp = w_free;
+      fixed_zmp = w_fixed;
+      double_support = w_ds;
+      pos = w_pos;
+      vel = w_vel;
+      capture_point_abs = w_cp_abs;
+      capture_point_rel = w_cp_rel;
     }
   };
 
