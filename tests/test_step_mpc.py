@@ -137,3 +137,19 @@ def test_batched_kernel_matches_host_restatement_and_closed_loop():
     ok, planned, sim, ref = _closed_loop(plan)
     assert ok
     assert np.linalg.norm(planned - ref) < 1e-2 and np.linalg.norm(sim.pos - ref) < 1e-2 and np.linalg.norm(sim.vel) < 1e-2
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the entry points of the two controllers added last refuse loudly (no CPU path in the product)."""
+    from centroidalcontrolcollection_b200 import build, closed_form, engine
+
+    build.build()
+    if engine.lib().ccc_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    fm = fmx.walking_plan()
+    fm.update(0.0)
+    with pytest.raises(engine.EngineError, match="no CUDA device"):
+        step_mpc.StepMpc(1.0).plan_batch(engine.step_mpc_plan, [fmx.make_step_mpc_ref_data(fm, 0.0)], [0.0], np.zeros((1, 2)), np.zeros((1, 2)), [0])
+    spc = closed_form.SingularPreviewControlZmp(1.0, 2.0, 0.01)
+    with pytest.raises(engine.EngineError, match="no CUDA device"):
+        spc.plan_batch(engine.singular_preview_plan, spc.sample(fm.ref_zmp, 0.0)[None], np.zeros((1, 2, 3)), [0])
